@@ -546,7 +546,11 @@ class HholtzAdi:
 class Poisson:
     """src/solver/poisson.rs:42-236: c D2 vhat = f via eigendecomposition of axis 0."""
 
-    def __init__(self, field, c):
+    def __init__(self, field, c, eig=None):
+        """``eig`` = (lam, fwd, bwd) replaces the LAPACK eigendecomposition of axis 0 (lam already
+        carries the singularity shift).  Parity tests pass the SAME decomposition to the oracle and
+        to the CUDA solver: the shifted-singular mode amplifies LAPACK-build rounding differences
+        to ~1e-9, which would otherwise mask the 1e-10 comparison ("Poisson parity")."""
         nd = len(c)
         lap, mass, isd, self.matvec = [], [], [], []
         for axis in range(nd):
@@ -555,6 +559,15 @@ class Poisson:
             lap.append(mat_b * c[axis])
             self.matvec.append(MatVecFdma(pre) if pre is not None else None)
             isd.append(is_diag)
+        if eig is not None and not isd[0]:
+            t = FdmaTensor.__new__(FdmaTensor)
+            t.ndim, t.alpha, t.n = 2, 0.0, lap[-1].shape[0]
+            t.lam = [np.array(eig[0], copy=True)]
+            t.fwd = [np.array(eig[1], copy=True)]
+            t.bwd = [np.array(eig[2], copy=True)]
+            t.fdma = [Fdma.from_matrix_raw(lap[-1]), Fdma.from_matrix_raw(mass[-1])]
+            self.solver = t
+            return
         self.solver = FdmaTensor(lap, mass, isd, 0.0)
         # singularity hack, src/solver/poisson.rs:84-86 (shifts the WHOLE lam[0] array)
         if nd == 2 and abs(self.solver.lam[0][0]) < 1e-10:
@@ -622,7 +635,7 @@ def bc_rbc(b0, ny):
 class Navier2D:
     """``Navier2D`` with bc = "rbc", src/navier_stokes/navier.rs:49-466."""
 
-    def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False):
+    def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False, pois_eig=None):
         assert bc == "rbc", "bc='hc' is SURVEY 8f item 2"
         self.periodic = periodic
         self.scale = [aspect, 1.0]
@@ -654,7 +667,7 @@ class Navier2D:
             HholtzAdi(self.vely, [dt * self.nu / sc[0] ** 2, dt * self.nu / sc[1] ** 2]),
             HholtzAdi(self.temp, [dt * self.ka / sc[0] ** 2, dt * self.ka / sc[1] ** 2]),
         ]
-        self.solver_pres = Poisson(self.pseu, [1.0 / sc[0] ** 2, 1.0 / sc[1] ** 2])
+        self.solver_pres = Poisson(self.pseu, [1.0 / sc[0] ** 2, 1.0 / sc[1] ** 2], eig=pois_eig)
         # rhs buffer shape: navier.rs:277 (confined) / :397 (periodic)
         self.rhs_shape = self.field.vhat.shape if periodic else self.temp.v.shape
 

@@ -1,0 +1,438 @@
+"""Python host layer: same names, argument meaning and error behaviour as the reference's
+``Space2`` / ``Field2`` / ``HholtzAdi`` / ``Poisson`` / ``Navier2D`` (file:line cited per class),
+calling the C ABI only.  numpy arrays cross the boundary; everything else stays on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import B2Error, check, lib
+
+# BaseKind order of src/field.rs:173-177
+CHEBYSHEV, CHEB_DIRICHLET, CHEB_NEUMANN, CHEB_DIRICHLET_NEUMANN, FOURIER_R2C, FOURIER_C2C = range(6)
+PHYSICAL, SPECTRAL, ORTHO = 0, 1, 2
+
+
+def chebyshev(n):
+    """src/bases.rs:11-19 (funspace ``chebyshev``)."""
+    return (CHEBYSHEV, n)
+
+
+def cheb_dirichlet(n):
+    return (CHEB_DIRICHLET, n)
+
+
+def cheb_neumann(n):
+    return (CHEB_NEUMANN, n)
+
+
+def fourier_r2c(n):
+    return (FOURIER_R2C, n)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One per GPU / rank (replaces funspace ``initialize()`` -> ``Universe``, src/mpi/mod.rs:5,12)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, heap_bytes=0):
+        self._h = C.c_void_p()
+        check(lib().b2_ctx_create(device, rank, nranks, heap_bytes, C.byref(self._h)))
+        self.device, self.rank, self.nranks = device, rank, nranks
+
+    def sync(self):
+        check(lib().b2_ctx_sync(self._h))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class Space2:
+    """funspace ``Space2::new(&base0, &base1)`` (src/field.rs:81-90)."""
+
+    def __init__(self, base0, base1, ctx=None):
+        self.ctx = ctx or default_context()
+        self.bases = (base0, base1)
+        self._h = C.c_void_p()
+        check(lib().b2_space2_create(self.ctx._h, base0[0], base0[1], base1[0], base1[1], C.byref(self._h)))
+
+    def shape(self, kind):
+        r, c, cx = C.c_int(), C.c_int(), C.c_int()
+        check(lib().b2_space_shape(self._h, kind, C.byref(r), C.byref(c), C.byref(cx)))
+        return (r.value, c.value), bool(cx.value)
+
+    def shape_physical(self):
+        return self.shape(PHYSICAL)[0]
+
+    def shape_spectral(self):
+        return self.shape(SPECTRAL)[0]
+
+    def base_kind(self, axis):
+        return self.bases[axis][0]
+
+    def coords(self):
+        out = []
+        for ax in (0, 1):
+            x = np.zeros(self.bases[ax][1])
+            check(lib().b2_space_coords(self._h, ax, _dp(x)))
+            out.append(x)
+        return out
+
+
+def _host_dtype(space, kind):
+    return np.complex128 if space.shape(kind)[1] else np.float64
+
+
+class DeviceArray:
+    """A device-resident ``Array2`` in one of the three shapes of a space."""
+
+    def __init__(self, space, kind, handle=None, owner=True):
+        self.space, self.kind = space, kind
+        self._owner = owner
+        if handle is None:
+            self._h = C.c_void_p()
+            check(lib().b2_array_create(space._h, kind, C.byref(self._h)))
+        else:
+            self._h = handle
+
+    def set(self, a):
+        shape, _ = self.space.shape(self.kind)
+        a = np.ascontiguousarray(a, dtype=_host_dtype(self.space, self.kind))
+        if a.shape != tuple(shape):
+            raise B2Error(f"shape mismatch: got {a.shape}, expected {tuple(shape)}")  # reference: panic
+        check(lib().b2_array_set_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return self
+
+    def get(self):
+        shape, _ = self.space.shape(self.kind)
+        out = np.empty(shape, dtype=_host_dtype(self.space, self.kind))
+        check(lib().b2_array_get_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def axpy(self, alpha, x):
+        check(lib().b2_array_axpy(self._h, alpha, x._h))
+        return self
+
+    def norm(self):
+        v = C.c_double()
+        check(lib().b2_array_norm2(self._h, C.byref(v)))
+        return v.value
+
+
+class Field2:
+    """``FieldBase`` for N = 2 (src/field.rs:59-129): ``v``, ``vhat``, ``x``, ``dx`` and
+    ``forward / backward / to_ortho / from_ortho / gradient``."""
+
+    def __init__(self, space, handle=None):
+        self.space = space
+        self._owner = handle is None
+        if handle is None:
+            self._h = C.c_void_p()
+            check(lib().b2_field_create(space._h, C.byref(self._h)))
+        else:
+            self._h = handle
+        self.x = space.coords()
+        self.dx = [self._get_dx(x, space.base_kind(i) == FOURIER_R2C) for i, x in enumerate(self.x)]
+
+    @staticmethod
+    def _get_dx(x, periodic):  # src/field.rs:135-163
+        if periodic:
+            return np.full(len(x), x[2] - x[1])
+        mid = 0.5 * (x[1:] + x[:-1])
+        return np.concatenate((mid, [x[-1]])) - np.concatenate(([x[0]], mid))
+
+    def scale(self, scale):  # src/field.rs:93-100
+        for i, sc in enumerate(scale):
+            self.x[i] = self.x[i] * sc
+            self.dx[i] = self.dx[i] * sc
+
+    # host views of the device-resident data
+    @property
+    def v(self):
+        out = np.empty(self.space.shape_physical())
+        check(lib().b2_field_get_v_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    @v.setter
+    def v(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != tuple(self.space.shape_physical()):
+            raise B2Error(f"shape mismatch: got {a.shape}")
+        check(lib().b2_field_set_v_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    @property
+    def vhat(self):
+        shape, cx = self.space.shape(SPECTRAL)
+        out = np.empty(shape, dtype=np.complex128 if cx else np.float64)
+        check(lib().b2_field_get_vhat_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    @vhat.setter
+    def vhat(self, a):
+        shape, cx = self.space.shape(SPECTRAL)
+        a = np.ascontiguousarray(a, dtype=np.complex128 if cx else np.float64)
+        if a.shape != tuple(shape):
+            raise B2Error(f"shape mismatch: got {a.shape}, expected {tuple(shape)}")
+        check(lib().b2_field_set_vhat_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def forward(self):
+        check(lib().b2_forward(self._h))
+
+    def backward(self):
+        check(lib().b2_backward(self._h))
+
+    def to_ortho(self):
+        out = DeviceArray(self.space, ORTHO)
+        check(lib().b2_to_ortho(self._h, out._h))
+        return out
+
+    def from_ortho(self, arr):
+        check(lib().b2_from_ortho(self._h, arr._h))
+
+    def gradient(self, deriv, scale=None):
+        out = DeviceArray(self.space, ORTHO)
+        sc = None
+        if scale is not None:
+            sc = (C.c_double * 2)(float(scale[0]), float(scale[1]))
+        check(lib().b2_gradient(self._h, int(deriv[0]), int(deriv[1]), sc, out._h))
+        return out
+
+
+class _Solver:
+    def solve(self, inp, out=None, axis=0):
+        """``Solve::solve(&input, &mut output, axis)`` (src/solver.rs:59-82); ``axis`` is ignored
+        as in the reference's field solvers (src/solver/hholtz_adi.rs:120)."""
+        if isinstance(inp, np.ndarray):
+            inp = DeviceArray(self.field.space, ORTHO).set(inp)
+        if out is None:
+            out = DeviceArray(self.field.space, SPECTRAL)
+        check(lib().b2_solve(self._h, inp._h, out._h))
+        return out
+
+    solve_par = solve
+
+
+class HholtzAdi(_Solver):
+    """``HholtzAdi::new(&field, c)`` (src/solver/hholtz_adi.rs:48-76)."""
+
+    def __init__(self, field, c):
+        self.field = field
+        self._h = C.c_void_p()
+        check(lib().b2_hholtz_adi_create(field._h, float(c[0]), float(c[1]), C.byref(self._h)))
+
+
+def _eig_sorted(x):
+    """src/solver/utils.rs:67-100: LAPACK dgeev, real parts, eigenvalues sorted descending."""
+    ev, evec = np.linalg.eig(x)
+    ev, evec = ev.real, evec.real
+    perm = np.argsort(ev, kind="stable")[::-1]
+    return ev[perm], evec[:, perm]
+
+
+def poisson_eig(kind0, n0, c0, parity_split=None):
+    """Host-side setup of ``FdmaTensor::from_matrix`` (src/solver/fdma_tensor.rs:117-129) + the
+    singularity rule of ``Poisson::new`` (src/solver/poisson.rs:84-86):  X = C0^-1 A0 = Q L Q^-1,
+    returns (lam, fwd = Q^-1 C0^-1, bwd = Q).  A0 and C0 only couple indices of equal parity, so
+    for large n the two parity blocks are diagonalised separately (4x less LAPACK work; the solve
+    x = Q (..) Q^-1 C0^-1 rhs does not depend on how eigenvectors are scaled or grouped)."""
+    m = n0 - 2
+    a0 = np.zeros((m, m))
+    cm = np.zeros((m, m))
+    check(lib().b2_host_poisson_matrices(kind0, n0, float(c0), _dp(a0), _dp(cm)))
+    if parity_split is None:
+        parity_split = m > 600
+    if not parity_split:
+        cinv = np.linalg.inv(cm)
+        lam, q = _eig_sorted(cinv @ a0)
+        fwd = np.linalg.inv(q) @ cinv
+    else:
+        lam = np.zeros(m)
+        q = np.zeros((m, m))
+        fwd_p = np.zeros((m, m))
+        for par in (0, 1):
+            idx = np.arange(par, m, 2)
+            cinv = np.linalg.inv(cm[np.ix_(idx, idx)])
+            l_p, q_p = _eig_sorted(cinv @ a0[np.ix_(idx, idx)])
+            lam[idx] = l_p  # temporary slot; permuted below
+            q[np.ix_(idx, idx)] = q_p
+            fwd_p[np.ix_(idx, idx)] = np.linalg.inv(q_p) @ cinv
+        perm = np.argsort(lam, kind="stable")[::-1]
+        lam, q, fwd = lam[perm], q[:, perm], fwd_p[perm, :]
+    if abs(lam[0]) < 1e-10:
+        lam = lam - 1e-10
+    return np.ascontiguousarray(lam), np.ascontiguousarray(fwd), np.ascontiguousarray(q)
+
+
+class Poisson(_Solver):
+    """``Poisson::new(&field, c)`` (src/solver/poisson.rs:54-94)."""
+
+    def __init__(self, field, c):
+        self.field = field
+        self._h = C.c_void_p()
+        kind0, n0 = field.space.bases[0]
+        if kind0 in (CHEB_DIRICHLET, CHEB_NEUMANN):
+            lam, fwd, bwd = poisson_eig(kind0, n0, c[0])
+            check(lib().b2_poisson_create(field._h, float(c[0]), float(c[1]), _dp(lam), _dp(fwd), _dp(bwd), C.byref(self._h)))
+        else:
+            check(lib().b2_poisson_create(field._h, float(c[0]), float(c[1]), None, None, None, C.byref(self._h)))
+
+
+class _NavSpace:
+    """Space view of a field owned by the native Navier2D object."""
+
+    def __init__(self, nav, which):
+        self._nav, self._which = nav, which
+
+
+class Navier2D:
+    """``Navier2D`` (src/navier_stokes/navier.rs:49-466).  ``new_confined`` / ``new_periodic`` build
+    the same six fields, three ``HholtzAdi`` and one ``Poisson`` solver; ``update()`` advances one
+    step on the GPU."""
+
+    FIELDS = {"temp": 0, "velx": 1, "vely": 2, "pres": 3, "pseu": 4, "tempbc": 5}
+
+    def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False, ctx=None):
+        self.ctx = ctx or default_context()
+        self.nx, self.ny, self.ra, self.pr, self.dt, self.aspect = nx, ny, ra, pr, dt, aspect
+        self.periodic = periodic
+        self.scale = [aspect, 1.0]
+        self._h = C.c_void_p()
+        if periodic:
+            args = (None, None, None)
+        else:
+            lam, fwd, bwd = poisson_eig(CHEB_NEUMANN, nx, 1.0 / aspect ** 2)
+            args = (_dp(lam), _dp(fwd), _dp(bwd))
+        check(lib().b2_navier2d_create(self.ctx._h, nx, ny, ra, pr, dt, aspect, bc.encode(), int(periodic), *args, C.byref(self._h)))
+        bx = (lambda k: fourier_r2c(nx)) if periodic else (lambda k: (k, nx))
+        kinds = {"temp": (bx(CHEB_DIRICHLET if periodic else CHEB_NEUMANN), cheb_dirichlet(ny)),
+                 "velx": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)), "vely": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)),
+                 "pres": (bx(CHEBYSHEV), chebyshev(ny)), "pseu": (bx(CHEB_NEUMANN), cheb_neumann(ny)),
+                 "tempbc": (bx(CHEBYSHEV), chebyshev(ny))}
+        for name, idx in self.FIELDS.items():
+            fh = C.c_void_p()
+            check(lib().b2_navier_field(self._h, idx, C.byref(fh)))
+            sp = _BorrowedSpace(self.ctx, kinds[name], fh)
+            f = Field2(sp, handle=fh)
+            if name in ("velx", "vely", "temp", "pres"):
+                f.scale(self.scale)
+            setattr(self, name, f)
+
+    @classmethod
+    def new_confined(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None):
+        """navier.rs:215-308."""
+        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=False, ctx=ctx)
+
+    @classmethod
+    def new_periodic(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None):
+        """navier.rs:336-428."""
+        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=True, ctx=ctx)
+
+    # initial conditions: navier.rs:156-182, functions.rs:85-140
+    def _unit(self, f):
+        x, y = f.x
+        return (x - x[0]) / (x[-1] - x[0]), (y - y[0]) / (y[-1] - y[0])
+
+    def set_velocity(self, amp, m, n):
+        x, y = self._unit(self.velx)
+        self.velx.v = amp * np.outer(np.sin(np.pi * m * x), np.cos(np.pi * n * y))
+        self.velx.forward()
+        x, y = self._unit(self.vely)
+        self.vely.v = -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y))
+        self.vely.forward()
+
+    def set_temperature(self, amp, m, n):
+        x, y = self._unit(self.temp)
+        self.temp.v = -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y))
+        self.temp.forward()
+
+    def init_random(self, amp, seeds=(1, 2, 3)):
+        for f, s in zip((self.temp, self.velx, self.vely), seeds):
+            f.v = np.random.default_rng(s).uniform(-amp, amp, size=f.space.shape_physical())
+            f.forward()
+
+    # Integrate (src/lib.rs:167-178)
+    def update(self, nsteps=1):
+        check(lib().b2_navier_update(self._h, int(nsteps)))
+
+    def get_time(self):
+        t = C.c_double()
+        check(lib().b2_navier_get_time(self._h, C.byref(t)))
+        return t.value
+
+    def get_dt(self):
+        return self.dt
+
+    def div_norm(self):
+        v = C.c_double()
+        check(lib().b2_navier_div_norm(self._h, C.byref(v)))
+        return v.value
+
+    def exit(self):
+        """navier.rs:482-489: break when |div| is NaN."""
+        return bool(np.isnan(self.div_norm()))
+
+    def callback(self):
+        pass  # HDF5 snapshots / diagnostics are out of scope
+
+    def set_mode(self, fused):
+        check(lib().b2_navier_set_mode(self._h, int(fused)))
+
+    def launches_per_step(self):
+        k = C.c_longlong()
+        check(lib().b2_navier_launch_count(self._h, C.byref(k)))
+        return k.value
+
+    def state(self):
+        return {k: getattr(self, k).vhat for k in ("temp", "velx", "vely", "pres")}
+
+
+class _BorrowedSpace(Space2):
+    """Space2 facade for fields owned by a native Navier2D (no second native space is created;
+    shapes and coordinates are computed from the base kinds)."""
+
+    def __init__(self, ctx, bases, field_handle):
+        self.ctx, self.bases, self._h = ctx, bases, None
+
+    def _len(self, ax, kind):
+        k, n = self.bases[ax]
+        if kind == PHYSICAL:
+            return n
+        if k == FOURIER_R2C:
+            return n // 2 + 1
+        if kind == ORTHO or k == CHEBYSHEV:
+            return n
+        return n - 2
+
+    def shape(self, kind):
+        return (self._len(0, kind), self._len(1, kind)), (self.bases[0][0] == FOURIER_R2C and kind != PHYSICAL)
+
+    def coords(self):
+        out = []
+        for k, n in self.bases:
+            out.append(2 * np.pi * np.arange(n) / n if k == FOURIER_R2C else -np.cos(np.pi * np.arange(n) / (n - 1)))
+        return out
+
+
+def integrate(pde, max_time, save_intervall=None):
+    """``integrate`` loop (src/lib.rs:187-219): update, callback at save intervals, stop at
+    ``max_time`` or when ``exit()`` reports a NaN divergence."""
+    eps_dt = pde.get_dt() * 1e-4
+    while True:
+        pde.update()
+        t = pde.get_time()
+        if save_intervall is not None and (t + eps_dt) % save_intervall < pde.get_dt() / 2.0:
+            pde.callback()
+        if t + eps_dt >= max_time:
+            break
+        if pde.exit():
+            break

@@ -1,0 +1,1051 @@
+// b200pde: host side of the B200-native Navier2D spectral hot path + its C ABI.
+//
+// Mirrors the reference's Space / Field / Solve / Integrate surface (see include/b200pde.h for
+// the file:line of every interface replaced).  Everything numeric runs in lane_kernel.cuh;
+// this file only (a) builds the small per-axis coefficient vectors on the host exactly as
+// src/field.rs:195-249 + src/solver/*.rs define them, (b) strings lane programs together and
+// (c) owns device memory.  There is NO CPU fallback: every entry point needs a CUDA device.
+#include "lane_kernel.cuh"
+#include "../../include/b200pde.h"
+
+#ifndef B2_EMU
+#include <cublas_v2.h>
+#endif
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+#define CKB(call)                                                                                  \
+  do {                                                                                             \
+    cublasStatus_t s_ = (call);                                                                    \
+    if (s_ != CUBLAS_STATUS_SUCCESS) return fail(B2_ERR_CUDA, std::string(#call) + ": cublas error " + std::to_string((int)s_)); \
+  } while (0)
+#define RET(call)                    \
+  do {                               \
+    int r_ = (call);                 \
+    if (r_ != B2_OK) return r_;      \
+  } while (0)
+
+static inline int roundup(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------------
+// structures
+// ------------------------------------------------------------------------------------------------
+struct b2_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t blas = nullptr;
+  long long launches = 0;  // lane-kernel + helper launches (counted, for bench.py's gpu_launches)
+  // symmetric heap for nranks > 1
+  char* heap = nullptr;
+  size_t heap_bytes = 0, heap_used = 0;
+  double** d_peers = nullptr;  // device table of peer heap bases
+  void* peer_base[B2_MAXPEERS] = {nullptr};
+};
+
+struct DVecD {  // device vector of doubles
+  double* d = nullptr;
+  size_t n = 0;
+  int upload(const std::vector<double>& h) {
+    n = h.size();
+    if (n == 0) return B2_OK;
+    CK(cudaMalloc(&d, n * sizeof(double)));
+    CK(cudaMemcpy(d, h.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    return B2_OK;
+  }
+  void release() { if (d) cudaFree(d); d = nullptr; }
+};
+
+// unsweeped 4-diagonal matrix, as Fdma::from_matrix_raw (src/solver/fdma.rs:44-54)
+struct Diags {
+  int m = 0;
+  std::vector<double> low, dia, up1, up2;  // all length m (tails unused / zero)
+  explicit Diags(int m_ = 0) : m(m_), low(m_, 0.0), dia(m_, 0.0), up1(m_, 0.0), up2(m_, 0.0) {}
+};
+// LU vectors in the form the kernel wants: fl[i] = low[i-2], id[i] = 1/dia[i], u1, u2 (zero tails)
+struct LuVecs { std::vector<double> fl, id, u1, u2; };
+
+// Fdma::sweep, src/solver/fdma.rs:73-82, then repack
+static LuVecs sweep(const Diags& a) {
+  const int n = a.m;
+  std::vector<double> low = a.low, dia = a.dia, up1 = a.up1, up2 = a.up2;
+  for (int i = 2; i < n; i++) {
+    low[i - 2] /= dia[i - 2];
+    dia[i] -= low[i - 2] * up1[i - 2];
+    if (i < n - 2) up1[i] -= low[i - 2] * up2[i - 2];
+  }
+  LuVecs r;
+  r.fl.assign(n, 0.0); r.id.assign(n, 0.0); r.u1.assign(n, 0.0); r.u2.assign(n, 0.0);
+  for (int i = 0; i < n; i++) {
+    if (i >= 2) r.fl[i] = low[i - 2];
+    r.id[i] = 1.0 / dia[i];
+    if (i < n - 2) r.u1[i] = up1[i];
+    if (i < n - 4) r.u2[i] = up2[i];
+  }
+  return r;
+}
+
+struct Base1 {
+  int kind = 0, n = 0, m = 0;
+  bool cheb = false, composite = false;
+  int rows_phys = 0, rows_spec = 0, rows_ortho = 0;  // real rows along this axis (complex => 2 per mode)
+  int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
+  std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
+  DVecD d_sten2, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
+
+  // B2 = laplace_inv; pv(i, off) = (laplace_inv_eye . laplace_inv)[i, i+off]
+  double pv(int i, int off) const {
+    const int r = i + 2;
+    if (off == 0) return r == 2 ? 0.25 : 1.0 / (4.0 * r * (r - 1.0));
+    if (off == 2) return (r < n - 2) ? -1.0 / (2.0 * ((double)r * r - 1.0)) : 0.0;
+    if (off == 4) return (r < n - 4) ? 1.0 / (4.0 * r * (r + 1.0)) : 0.0;
+    return 0.0;
+  }
+  // mat_a = pinv . S and mat_b = peye . S of src/field.rs:204-208 (composite bases)
+  Diags mat_a() const {
+    Diags a(m);
+    for (int i = 0; i < m; i++) {
+      if (i >= 2) a.low[i - 2] = pv(i, 0) * s2[i - 2];
+      a.dia[i] = pv(i, 0) + pv(i, 2) * s2[i];
+      if (i + 2 < m) a.up1[i] = pv(i, 2) + pv(i, 4) * s2[i + 2];
+      if (i + 4 < m) a.up2[i] = pv(i, 4);
+    }
+    return a;
+  }
+  Diags mat_b() const {
+    Diags b(m);
+    for (int i = 0; i < m; i++) {
+      b.dia[i] = s2[i];
+      if (i + 2 < m) b.up1[i] = 1.0;
+    }
+    return b;
+  }
+  int init_host(int kind_, int n_);
+  int init(int kind_, int n_);
+  void release() {
+    DVecD* all[] = {&d_sten2, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin};
+    for (auto* v : all) v->release();
+  }
+};
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int Base1::init_host(int kind_, int n_) {
+  kind = kind_; n = n_;
+  cheb = (kind <= B2_CHEB_DIRICHLET_NEUMANN);
+  composite = (kind == B2_CHEB_DIRICHLET || kind == B2_CHEB_NEUMANN);
+  if (kind == B2_CHEB_DIRICHLET_NEUMANN || kind == B2_FOURIER_C2C)
+    return fail(B2_ERR_UNSUPPORTED, "base kind not built yet (bc=\"hc\" / c2c: SURVEY 8f)");
+  if (kind < 0 || kind > B2_FOURIER_C2C) return fail(B2_ERR_ARG, "bad base kind");
+  if (n < 5) return fail(B2_ERR_ARG, "n too small");
+  if (cheb) {
+    m = composite ? n - 2 : n;
+    rows_phys = n; rows_spec = m; rows_ortho = n; N = n - 1;
+  } else {
+    if (n % 2) return fail(B2_ERR_UNSUPPORTED, "fourier_r2c needs even n");
+    m = n / 2 + 1;
+    rows_phys = n; rows_spec = 2 * m; rows_ortho = 2 * m; N = n;
+  }
+  if (composite) {
+    s2.assign(m, 0.0);
+    for (int k = 0; k < m; k++) s2[k] = (kind == B2_CHEB_DIRICHLET) ? -1.0 : -((double)k / (k + 2.0)) * ((double)k / (k + 2.0));
+  }
+  return B2_OK;
+}
+
+int Base1::init(int kind_, int n_) {
+  RET(init_host(kind_, n_));
+  const int L = roundup(std::max(rows_phys, rows_ortho) + 8, 4) + 64;  // generous coefficient-vector length
+  if (composite) {
+    std::vector<double> sten2(L, 0.0), s2v(L, 0.0);
+    for (int i = 2; i < n; i++) sten2[i] = s2[i - 2];
+    for (int k = 0; k < m; k++) s2v[k] = s2[k];
+    RET(d_sten2.upload(sten2)); RET(d_s2.upload(s2v));
+    // from_ortho: (S^T S) c = S^T o, tridiagonal at offsets (-2,0,2)
+    Diags t(m);
+    for (int k = 0; k < m; k++) {
+      t.dia[k] = 1.0 + s2[k] * s2[k];
+      if (k + 2 < m) { t.low[k] = s2[k]; t.up1[k] = s2[k]; }
+    }
+    LuVecs lu = sweep(t);
+    lu.fl.resize(L, 0.0); lu.id.resize(L, 0.0); lu.u1.resize(L, 0.0);
+    RET(d_tfl.upload(lu.fl)); RET(d_tid.upload(lu.id)); RET(d_tu1.upload(lu.u1));
+    // MatVecFdma of the preconditioner pinv (src/solver/matvec.rs:177-203)
+    std::vector<double> bd(L, 0.0), bu1(L, 0.0), bu2(L, 0.0);
+    for (int i = 0; i < m; i++) {
+      bd[i] = pv(i, 0);
+      if (i < m - 2) bu1[i] = pv(i, 2);
+      if (i < m - 4) bu2[i] = pv(i, 4);
+    }
+    RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
+  }
+  // transform tables (only when the size is one the FFT core handles)
+  if (is_pow2(N) && N >= 64) {
+    const int M = N / 2;
+    const long double PI = 3.14159265358979323846264338327950288L;
+    std::vector<double> tw(2 * M), tw2(2 * (M + 1)), isin(M, 0.0);
+    for (int t = 0; t < M; t++) { tw[2 * t] = (double)cosl(2 * PI * t / M); tw[2 * t + 1] = (double)(-sinl(2 * PI * t / M)); }
+    for (int j = 0; j <= M; j++) { tw2[2 * j] = (double)cosl(2 * PI * j / N); tw2[2 * j + 1] = (double)(-sinl(2 * PI * j / N)); }
+    for (int k = 1; k < M; k++) isin[k] = (double)(1.0L / (4.0L * sinl(PI * k / N)));
+    RET(d_tw.upload(tw)); RET(d_tw2.upload(tw2)); RET(d_isin.upload(isin));
+  }
+  return B2_OK;
+}
+
+struct PassCfg { int in_tiles, out_tiles, LP, TPL, C, E, groups; size_t smem; };
+
+struct b2_space {
+  b2_ctx* ctx = nullptr;
+  Base1 b[2];
+  int P[2] = {0, 0};   // padded real rows along axis 0 / axis 1
+  PassCfg cfg[2];      // [0]: lanes along axis 1 (arrays stored P0 x P1); [1]: lanes along axis 0
+  bool transforms_ok = false;
+  size_t elems() const { return (size_t)P[0] * P[1]; }
+  double* tmp[6] = {nullptr};  // scratch arrays
+  int refs = 0;
+};
+
+struct b2_array {
+  b2_space* sp;
+  double* d;
+  int shape_kind;
+};
+
+struct b2_field {
+  b2_space* sp;
+  b2_array* v;
+  b2_array* vhat;
+};
+
+struct b2_solver {
+  b2_space* sp = nullptr;
+  int type = 0;  // 0 hholtz_adi, 1 poisson
+  // per axis: banded LU (Chebyshev) or reciprocal diagonal (Fourier)
+  DVecD fl[2], id[2], u1[2], u2[2], sd[2];
+  // poisson
+  bool dense = false;
+  int m0 = 0;
+  DVecD fwd, bwd;           // dense (m0 x m0) row-major
+  DVecD pfl, pid, pu1, pu2; // per-lane LU in scan layout
+  double* plain[2] = {nullptr, nullptr};
+};
+
+// ------------------------------------------------------------------------------------------------
+// helper kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t tiled_index(int r, int c, int tiles) {
+  return ((size_t)(r >> 2) * tiles + (c >> 2)) * 16 + (r & 3) * 4 + (c & 3);
+}
+// host layout (row-major real, or complex interleaved) <-> tiled real rows (complex => rows 2k / 2k+1)
+__global__ void k_host_layout(double* tiled, double* plain, int rows, int cols, int tiles, int cplx, int to_tiled) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)rows * cols;
+  if (idx >= total) return;
+  int r = (int)(idx / cols), c = (int)(idx % cols);
+  size_t p = cplx ? (((size_t)(r >> 1) * cols + c) * 2 + (r & 1)) : idx;
+  size_t t = tiled_index(r, c, tiles);
+  if (to_tiled) tiled[t] = plain[p]; else plain[p] = tiled[t];
+}
+__global__ void k_axpby(size_t n, double* __restrict__ y, double a, const double* __restrict__ x, double b) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = a * x[i] + b * y[i];
+}
+// out = (acc ? out : 0) + u * p
+__global__ void k_muladd(size_t n, double* __restrict__ out, const double* __restrict__ u, const double* __restrict__ p, int acc) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (acc ? out[i] : 0.0) + u[i] * p[i];
+}
+__global__ void k_sumsq(size_t n, const double* __restrict__ x, double* out) {
+  __shared__ double sh[32];
+  double s = 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) s += x[i] * x[i];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+static int ew_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 8); }
+
+// ------------------------------------------------------------------------------------------------
+// program builder / launcher
+// ------------------------------------------------------------------------------------------------
+static int pack_offs(int o0, int o1, int o2) { return (o0 & 0xff) | ((o1 & 0xff) << 8) | ((o2 & 0xff) << 16); }
+
+struct Prog {
+  LaneProg p;
+  int err = B2_OK;
+  Prog() { memset(&p, 0, sizeof(p)); }
+  LaneOp* add(int code) {
+    if (p.nops >= B2_MAXOPS) { err = fail(B2_ERR_ARG, "lane program too long"); return &p.ops[B2_MAXOPS - 1]; }
+    LaneOp* o = &p.ops[p.nops++];
+    memset(o, 0, sizeof(*o));
+    o->code = code; o->a = 1.0;
+    return o;
+  }
+  void load(const double* src, int len, double a = 1.0, int flags = 0) { LaneOp* o = add(OP_LOAD); o->p0 = src; o->i0 = len; o->a = a; o->i2 = flags; }
+  void store(double* dst, int len, int flags, double a = 1.0) { LaneOp* o = add(OP_STORE); o->p0 = dst; o->i0 = len; o->a = a; o->i2 = flags; }
+  void band(int len_out, int len_in, int o0, const double* c0, int o1, const double* c1, int o2 = 127, const double* c2 = nullptr) {
+    LaneOp* o = add(OP_BAND); o->i0 = len_out; o->i2 = len_in; o->i1 = pack_offs(o0, o1, o2); o->p0 = c0; o->p1 = c1; o->p2 = c2;
+  }
+  void deriv(int n, int times, double scale) { LaneOp* o = add(OP_DERIV); o->i0 = n; o->i1 = times; o->a = scale; }
+  void fdma(int len, const double* fl, const double* id, const double* u1, const double* u2, int flags) {
+    LaneOp* o = add(OP_FDMA); o->i0 = len; o->i2 = flags; o->p0 = fl; o->p1 = id; o->p2 = u1; o->p3 = u2;
+  }
+  void dct(const Base1& b, int mode) { LaneOp* o = add(OP_DCT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; o->p2 = b.d_isin.d; }
+  void rfft(const Base1& b, int mode) { LaneOp* o = add(OP_RFFT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; }
+  void fdiff(int modes, int d, double scale) { LaneOp* o = add(OP_FDIFF); o->i0 = modes; o->i1 = d; o->a = scale; }
+  void scalevec(int len, const double* v, int shift) { LaneOp* o = add(OP_SCALEVEC); o->i0 = len; o->i1 = shift; o->p0 = v; }
+  void zerotail(int from) { LaneOp* o = add(OP_ZEROTAIL); o->i0 = from; }
+  void lanemask(int from) { LaneOp* o = add(OP_LANEMASK); o->i0 = from; }
+  void zeroelem(int lane, int pos) { LaneOp* o = add(OP_ZEROELEM); o->i0 = lane; o->i1 = pos; }
+  void scale(double a) { LaneOp* o = add(OP_SCALE); o->a = a; }
+
+  // ---- per-axis operator chains (funspace semantics) ----
+  // returns the new valid length along the lane
+  int to_ortho(const Base1& b) {
+    if (b.composite) { band(b.n, b.m, 0, nullptr, -2, b.d_sten2.d); return b.n; }
+    return b.rows_ortho;
+  }
+  int from_ortho(const Base1& b) {
+    if (b.composite) {
+      band(b.m, b.n, 0, nullptr, 2, b.d_s2.d);
+      fdma(b.m, b.d_tfl.d, b.d_tid.d, b.d_tu1.d, nullptr, FD_NOU2);
+      return b.m;
+    }
+    return b.rows_spec;
+  }
+  int deriv_axis(const Base1& b, int d, double sc) {  // on ortho coefficients; sc = 1/scale^d
+    if (d == 0) { if (sc != 1.0) scale(sc); return b.rows_ortho; }
+    if (b.cheb) deriv(b.n, d, sc); else fdiff(b.m, d, sc);
+    return b.rows_ortho;
+  }
+  int backward_ortho(const Base1& b) {  // ortho coefficients -> physical values
+    if (b.cheb) dct(b, 1); else rfft(b, 1);
+    return b.rows_phys;
+  }
+  int forward_ortho(const Base1& b) {   // physical values -> ortho coefficients
+    if (b.cheb) dct(b, 0); else rfft(b, 0);
+    return b.rows_ortho;
+  }
+  int matvec(const Base1& b) {          // MatVecFdma with pinv (Chebyshev axes only)
+    if (b.composite) { band(b.m, b.n, 0, b.d_bd.d, 2, b.d_bu1.d, 4, b.d_bu2.d); return b.m; }
+    return b.rows_spec;
+  }
+};
+
+template <int E> static int launch_E(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
+  static size_t set_smem = 0;
+  if (c.smem > set_smem) {
+    CK(cudaFuncSetAttribute(lane_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    set_smem = c.smem;
+  }
+  B2_LAUNCH(lane_kernel<E>, c.groups, 4 * c.TPL, c.smem, ctx->stream, p);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+// orient 0: lanes along axis 1; orient 1: lanes along axis 0
+static int run_pass(b2_space* sp, int orient, Prog& pr) {
+  if (pr.err != B2_OK) return pr.err;
+  const PassCfg& c = sp->cfg[orient];
+  LaneProg& p = pr.p;
+  p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
+  p.group0 = 0; p.groups_per_rank = c.in_tiles; p.rank = sp->ctx->rank;
+  sp->ctx->launches++;
+  switch (c.E) {
+    case 4: return launch_E<4>(sp->ctx, c, p);
+    case 8: return launch_E<8>(sp->ctx, c, p);
+    default: return launch_E<16>(sp->ctx, c, p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context / space / arrays
+// ------------------------------------------------------------------------------------------------
+static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
+  c->in_tiles = Pl / 4; c->out_tiles = Pc / 4; c->groups = Pc / 4; c->LP = Pl;
+  const int N = lane_base.N;
+  if (is_pow2(N) && N >= 64) {
+    const int Nc = N / 2;
+    c->E = Nc >= 128 ? 16 : (Nc >= 64 ? 8 : 4);
+    c->TPL = Nc / c->E;
+  } else {  // no transform along this axis: banded ops only
+    c->E = 4;
+    int t = 8;
+    while (t * B2_CMAX < Pl) t *= 2;
+    c->TPL = t;
+  }
+  if (c->TPL > 128) return fail(B2_ERR_UNSUPPORTED, "lane longer than 4100 points: needs the 2-lane kernel variant (not built yet)");
+  c->C = (Pl + c->TPL - 1) / c->TPL;
+  if (c->C > B2_CMAX) return fail(B2_ERR_UNSUPPORTED, "lane length / thread count combination not supported");
+  c->smem = ((size_t)4 * c->LP + 32 * 12) * sizeof(double);
+  if (c->smem > 227 * 1024) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
+  return B2_OK;
+}
+
+static int alloc_zero(b2_space* sp, double** out) {
+  CK(cudaMalloc(out, sp->elems() * sizeof(double)));
+  CK(cudaMemsetAsync(*out, 0, sp->elems() * sizeof(double), sp->ctx->stream));
+  return B2_OK;
+}
+
+static int shape_of(const b2_space* sp, int shape_kind, int* rows, int* cols) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  switch (shape_kind) {
+    case B2_SHAPE_PHYSICAL: *rows = b0.rows_phys; *cols = b1.rows_phys; return B2_OK;
+    case B2_SHAPE_SPECTRAL: *rows = b0.rows_spec; *cols = b1.rows_spec; return B2_OK;
+    case B2_SHAPE_ORTHO: *rows = b0.rows_ortho; *cols = b1.rows_ortho; return B2_OK;
+  }
+  return fail(B2_ERR_ARG, "bad shape kind");
+}
+static bool shape_complex(const b2_space* sp, int shape_kind) { return !sp->b[0].cheb && shape_kind != B2_SHAPE_PHYSICAL; }
+
+// ------------------------------------------------------------------------------------------------
+// field operators (2 passes each: along y, transpose, along x, transpose back)
+// ------------------------------------------------------------------------------------------------
+static int op_forward(b2_space* sp, const double* v, double* vhat) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transforms need n-1 (Chebyshev) / n (Fourier) = 2^k >= 64");
+  Prog y; y.load(v, b1.rows_phys); y.forward_ortho(b1); int l = y.from_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_phys); x.forward_ortho(b0); l = x.from_ortho(b0); x.store(vhat, l, ST_TRANS);
+  return run_pass(sp, 1, x);
+}
+static int op_backward(b2_space* sp, const double* vhat, double* v) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transforms need n-1 (Chebyshev) / n (Fourier) = 2^k >= 64");
+  Prog y; y.load(vhat, b1.rows_spec); y.to_ortho(b1); int l = y.backward_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_spec); x.to_ortho(b0); l = x.backward_ortho(b0); x.store(v, l, ST_TRANS);
+  return run_pass(sp, 1, x);
+}
+static int op_to_ortho(b2_space* sp, const double* vhat, double* out, double alpha = 1.0, bool acc = false) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  Prog y; y.load(vhat, b1.rows_spec); int l = y.to_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_spec); l = x.to_ortho(b0); x.store(out, l, ST_TRANS | (acc ? ST_ACC : 0), alpha);
+  return run_pass(sp, 1, x);
+}
+static int op_from_ortho(b2_space* sp, const double* in, double* vhat, double alpha = 1.0, bool acc = false) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  Prog y; y.load(in, b1.rows_ortho); int l = y.from_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.from_ortho(b0); x.store(vhat, l, ST_TRANS | (acc ? ST_ACC : 0), alpha);
+  return run_pass(sp, 1, x);
+}
+static int op_gradient(b2_space* sp, const double* vhat, int d0, int d1, const double* scale, double* out, double alpha = 1.0, bool acc = false) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  double s0 = 1.0, s1 = 1.0;
+  if (scale) { s0 = 1.0 / std::pow(scale[0], d0); s1 = 1.0 / std::pow(scale[1], d1); }
+  Prog y; y.load(vhat, b1.rows_spec); y.to_ortho(b1); int l = y.deriv_axis(b1, d1, s1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_spec); x.to_ortho(b0); l = x.deriv_axis(b0, d0, s0); x.store(out, l, ST_TRANS | (acc ? ST_ACC : 0), alpha);
+  return run_pass(sp, 1, x);
+}
+// transforms of an orthonormal ("field" = ch x ch or r2c x ch) array, funspace backward_par / forward
+static int op_backward_ortho(b2_space* sp, const double* ortho, double* phys) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transform size");
+  Prog y; y.load(ortho, b1.rows_ortho); int l = y.backward_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.backward_ortho(b0); x.store(phys, l, ST_TRANS);
+  return run_pass(sp, 1, x);
+}
+// forward + dealias (src/navier_stokes/functions.rs:72-82), result scaled by alpha
+static int op_forward_ortho_dealias(b2_space* sp, const double* phys, double* ortho, bool dealias, double alpha = 1.0, bool acc = false) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transform size");
+  // bit-exact index rule: n_x = shape0*2/3, n_y = shape1*2/3 with integer division on the spectral shape
+  const int shape0 = b0.cheb ? b0.n : b0.m, shape1 = b1.cheb ? b1.n : b1.m;
+  const int cut0 = (shape0 * 2 / 3) * (b0.cheb ? 1 : 2), cut1 = (shape1 * 2 / 3) * (b1.cheb ? 1 : 2);
+  Prog y; y.load(phys, b1.rows_phys); int l = y.forward_ortho(b1); if (dealias) y.zerotail(cut1); y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_phys); l = x.forward_ortho(b0); if (dealias) x.zerotail(cut0);
+  x.store(ortho, l, ST_TRANS | (acc ? ST_ACC : 0), alpha);
+  return run_pass(sp, 1, x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// solvers
+// ------------------------------------------------------------------------------------------------
+static int upload_lu(const LuVecs& lu, int L, DVecD* fl, DVecD* id, DVecD* u1, DVecD* u2) {
+  LuVecs p = lu;
+  p.fl.resize(L, 0.0); p.id.resize(L, 0.0); p.u1.resize(L, 0.0); p.u2.resize(L, 0.0);
+  RET(fl->upload(p.fl)); RET(id->upload(p.id)); RET(u1->upload(p.u1)); RET(u2->upload(p.u2));
+  return B2_OK;
+}
+
+static int hholtz_create(b2_space* sp, double c0, double c1, b2_solver** out) {
+  b2_solver* s = new b2_solver();
+  s->sp = sp; s->type = 0;
+  const double c[2] = {c0, c1};
+  for (int ax = 0; ax < 2; ax++) {
+    const Base1& b = sp->b[ax];
+    const int L = sp->P[ax] + 64;
+    if (b.composite) {  // mat = mat_a - mat_b * c, src/solver/hholtz_adi.rs:57-63
+      Diags a = b.mat_a(), bm = b.mat_b(), mat(b.m);
+      for (int i = 0; i < b.m; i++) {
+        mat.low[i] = a.low[i] - bm.low[i] * c[ax];
+        mat.dia[i] = a.dia[i] - bm.dia[i] * c[ax];
+        mat.up1[i] = a.up1[i] - bm.up1[i] * c[ax];
+        mat.up2[i] = a.up2[i] - bm.up2[i] * c[ax];
+      }
+      RET(upload_lu(sweep(mat), L, &s->fl[ax], &s->id[ax], &s->u1[ax], &s->u2[ax]));
+    } else if (!b.cheb) {  // Sdma: dia = 1 - c * (-k^2), src/solver/sdma.rs:37-46
+      std::vector<double> sd(L, 0.0);
+      for (int k = 0; k < b.m; k++) sd[k] = 1.0 / (1.0 - (-(double)k * k) * c[ax]);
+      RET(s->sd[ax].upload(sd));
+    } else {
+      delete s;
+      return fail(B2_ERR_UNSUPPORTED, "HholtzAdi on an orthonormal Chebyshev axis is not on the Navier2D path");
+    }
+  }
+  *out = s;
+  return B2_OK;
+}
+
+// HholtzAdi::solve_par, src/solver/hholtz_adi.rs:149-169 (axis operators commute; y first here)
+static int hholtz_solve(b2_solver* s, const double* in, double* out) {
+  b2_space* sp = s->sp;
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1);
+  if (b1.composite) y.fdma(b1.m, s->fl[1].d, s->id[1].d, s->u1[1].d, s->u2[1].d, 0);
+  else y.scalevec(b1.rows_spec, s->sd[1].d, 1);
+  y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0);
+  if (b0.composite) x.fdma(b0.m, s->fl[0].d, s->id[0].d, s->u1[0].d, s->u2[0].d, 0);
+  else x.scalevec(b0.rows_spec, s->sd[0].d, 1);
+  x.store(out, l, ST_TRANS);
+  return run_pass(sp, 1, x);
+}
+
+// laplacian / mass of axis ax as in Poisson::new (src/solver/poisson.rs:65-74)
+static void poisson_axis(const Base1& b, double c, Diags* lap, Diags* mass) {
+  Diags a = b.mat_a(), bm = b.mat_b();
+  *mass = a;
+  *lap = Diags(b.m);
+  for (int i = 0; i < b.m; i++) { lap->low[i] = bm.low[i] * c; lap->dia[i] = bm.dia[i] * c; lap->up1[i] = bm.up1[i] * c; lap->up2[i] = bm.up2[i] * c; }
+}
+
+static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_in, const double* fwd, const double* bwd, b2_solver** out) {
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (!b1.composite) return fail(B2_ERR_UNSUPPORTED, "Poisson needs a composite Chebyshev axis 1");
+  b2_solver* s = new b2_solver();
+  s->sp = sp; s->type = 1;
+  std::vector<double> lam;  // one eigenvalue per real row of the axis-0-transformed array
+  int lanes;
+  if (b0.composite) {
+    if (!lam_in || !fwd || !bwd) { delete s; return fail(B2_ERR_ARG, "Poisson on a Chebyshev axis 0 needs lam/fwd/bwd (host LAPACK eig)"); }
+    s->dense = true; s->m0 = b0.m;
+    lam.assign(lam_in, lam_in + b0.m);
+    lanes = b0.m;
+    std::vector<double> f(fwd, fwd + (size_t)b0.m * b0.m), q(bwd, bwd + (size_t)b0.m * b0.m);
+    RET(s->fwd.upload(f)); RET(s->bwd.upload(q));
+    RET(alloc_zero(sp, &s->plain[0])); RET(alloc_zero(sp, &s->plain[1]));
+  } else if (!b0.cheb) {
+    // Fourier axis 0: lam = diag(laplacian) = -k^2 c0 (fdma_tensor.rs:118-121), singularity shift poisson.rs:84-86
+    lanes = 2 * b0.m;
+    lam.resize(lanes);
+    for (int k = 0; k < b0.m; k++) lam[2 * k] = lam[2 * k + 1] = -(double)k * k * c0;
+    if (std::fabs(lam[0]) < 1e-10) for (auto& v : lam) v -= 1e-10;
+  } else { delete s; return fail(B2_ERR_UNSUPPORTED, "Poisson axis-0 base"); }
+  // per-lane LU of (lap1 + lam_i mass1), src/solver/poisson.rs:222-229, in scan layout
+  Diags lap1, mass1;
+  poisson_axis(b1, c1, &lap1, &mass1);
+  const PassCfg& c = sp->cfg[0];
+  const size_t total = (size_t)c.groups * c.C * 4 * c.TPL;
+  std::vector<double> pfl(total, 0.0), pid(total, 0.0), pu1(total, 0.0), pu2(total, 0.0);
+  const int m1 = b1.m;
+  Diags mat(m1);
+  for (int lane = 0; lane < lanes; lane++) {
+    const double lm = lam[lane];
+    for (int i = 0; i < m1; i++) {
+      mat.low[i] = lap1.low[i] + mass1.low[i] * lm;
+      mat.dia[i] = lap1.dia[i] + mass1.dia[i] * lm;
+      mat.up1[i] = lap1.up1[i] + mass1.up1[i] * lm;
+      mat.up2[i] = lap1.up2[i] + mass1.up2[i] * lm;
+    }
+    LuVecs lu = sweep(mat);
+    const int g = lane / 4, l = lane % 4;
+    for (int i = 0; i < m1; i++) {
+      const int q = i / c.C, ii = i % c.C;
+      const size_t k = (((size_t)g * c.C + ii) * 4 + l) * c.TPL + q;
+      pfl[k] = lu.fl[i]; pid[k] = lu.id[i]; pu1[k] = lu.u1[i]; pu2[k] = lu.u2[i];
+    }
+  }
+  RET(s->pfl.upload(pfl)); RET(s->pid.upload(pid)); RET(s->pu1.upload(pu1)); RET(s->pu2.upload(pu2));
+  *out = s;
+  return B2_OK;
+}
+
+// Poisson::solve_par, src/solver/poisson.rs:195-236
+static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero00) {
+  b2_space* sp = s->sp;
+  b2_ctx* ctx = sp->ctx;
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  const int P0 = sp->P[0], P1 = sp->P[1];
+  if (s->dense) {
+    // matvec along y, transpose
+    Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1); y.store(sp->tmp[0], l, ST_TRANS);
+    RET(run_pass(sp, 0, y));
+    // matvec along x, keep x-lanes, write row-major for the GEMM
+    Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0); x.store(s->plain[0], l, ST_PLAIN);
+    RET(run_pass(sp, 1, x));
+    // out[j, :] = fwd . rhs[j, :]  (dense FP64 GEMM, src/solver/poisson.rs:213-219)
+    const double one = 1.0, zero = 0.0;
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->fwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    ctx->launches++;
+    Prog x2; x2.load(s->plain[1], s->m0, 1.0, LD_PLAIN); x2.store(sp->tmp[0], s->m0, ST_TRANS);
+    RET(run_pass(sp, 1, x2));
+    // per-row banded solves with (lap1 + lam_i mass1)
+    Prog y2; y2.load(sp->tmp[0], b1.m); y2.fdma(b1.m, s->pfl.d, s->pid.d, s->pu1.d, s->pu2.d, FD_PERLANE); y2.store(sp->tmp[1], b1.m, ST_TRANS);
+    RET(run_pass(sp, 0, y2));
+    Prog x3; x3.load(sp->tmp[1], s->m0); x3.store(s->plain[0], s->m0, ST_PLAIN);
+    RET(run_pass(sp, 1, x3));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->bwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    ctx->launches++;
+    Prog x4; x4.load(s->plain[1], s->m0, 1.0, LD_PLAIN);
+    if (zero00) x4.zeroelem(0, 0);
+    x4.store(out, s->m0, ST_TRANS);
+    return run_pass(sp, 1, x4);
+  }
+  Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1);
+  y.fdma(b1.m, s->pfl.d, s->pid.d, s->pu1.d, s->pu2.d, FD_PERLANE);
+  y.store(sp->tmp[0], l, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_spec);
+  if (zero00) { x.zeroelem(0, 0); x.zeroelem(0, 1); }
+  x.store(out, b0.rows_spec, ST_TRANS);
+  return run_pass(sp, 1, x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Navier2D
+// ------------------------------------------------------------------------------------------------
+struct b2_navier {
+  b2_ctx* ctx = nullptr;
+  int nx = 0, ny = 0, periodic = 0;
+  double ra = 0, pr = 0, dt = 0, nu = 0, ka = 0, time = 0, scale[2] = {1, 1};
+  // spaces: [0] velocity (cd x cd), [1] temp (cn x cd), [2] ortho "field"/pres (ch x ch), [3] pseu (cn x cn)
+  b2_space* sp_vel = nullptr; b2_space* sp_temp = nullptr; b2_space* sp_ortho = nullptr; b2_space* sp_pseu = nullptr;
+  b2_field *temp = nullptr, *velx = nullptr, *vely = nullptr, *pres = nullptr, *pseu = nullptr, *tempbc = nullptr;
+  b2_solver* hh[3] = {nullptr, nullptr, nullptr};
+  b2_solver* pois = nullptr;
+  // work arrays (ortho-sized, tiled)
+  double *that = nullptr, *tbc_ortho = nullptr, *tbc_diff = nullptr, *rhs = nullptr, *g1 = nullptr, *g2 = nullptr, *conv = nullptr, *div = nullptr, *ux = nullptr, *uy = nullptr;
+  double* d_scalar = nullptr;
+  int fused = 0;
+  long long launches_per_step = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+int b2_version(void) { return 1; }
+
+int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** out) {
+  if (!out || nranks < 1 || nranks > B2_MAXPEERS || rank < 0 || rank >= nranks) return fail(B2_ERR_ARG, "b2_ctx_create: bad arguments");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(B2_ERR_CUDA, "no CUDA device: b200pde has no CPU fallback");
+  CK(cudaSetDevice(device));
+  b2_ctx* c = new b2_ctx();
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKB(cublasCreate(&c->blas));
+  CKB(cublasSetStream(c->blas, c->stream));
+  (void)heap_bytes;
+  *out = c;
+  return B2_OK;
+}
+int b2_ctx_destroy(b2_ctx* c) {
+  if (!c) return B2_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->blas) cublasDestroy(c->blas);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return B2_OK;
+}
+int b2_ctx_sync(b2_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return B2_OK; }
+int b2_ctx_nranks(const b2_ctx* c) { return c->nranks; }
+int b2_ctx_heap_handle(b2_ctx*, void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
+int b2_ctx_attach_peers(b2_ctx*, const void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
+
+int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space** out) {
+  if (!ctx || !out) return fail(B2_ERR_ARG, "b2_space2_create: null");
+  CK(cudaSetDevice(ctx->device));
+  b2_space* sp = new b2_space();
+  sp->ctx = ctx;
+  int r = sp->b[0].init(kind0, n0);
+  if (r == B2_OK) r = sp->b[1].init(kind1, n1);
+  if (r == B2_OK && !sp->b[1].cheb) r = fail(B2_ERR_UNSUPPORTED, "axis 1 must be a Chebyshev base (Navier2D spaces)");
+  if (r != B2_OK) { delete sp; return r; }
+  for (int ax = 0; ax < 2; ax++) sp->P[ax] = roundup(std::max(sp->b[ax].rows_phys, sp->b[ax].rows_ortho), 4);
+  r = make_cfg(sp->b[1], sp->P[1], sp->P[0], &sp->cfg[0]);
+  if (r == B2_OK) r = make_cfg(sp->b[0], sp->P[0], sp->P[1], &sp->cfg[1]);
+  if (r != B2_OK) { delete sp; return r; }
+  sp->transforms_ok = sp->b[0].d_tw.d && sp->b[1].d_tw.d;
+  for (int i = 0; i < 3; i++) RET(alloc_zero(sp, &sp->tmp[i]));
+  *out = sp;
+  return B2_OK;
+}
+int b2_space_destroy(b2_space* sp) {
+  if (!sp) return B2_OK;
+  for (auto& t : sp->tmp) if (t) cudaFree(t);
+  sp->b[0].release(); sp->b[1].release();
+  delete sp;
+  return B2_OK;
+}
+int b2_space_shape(const b2_space* sp, int shape_kind, int* rows, int* cols, int* is_complex) {
+  int r, c;
+  RET(shape_of(sp, shape_kind, &r, &c));
+  bool cx = shape_complex(sp, shape_kind);
+  if (rows) *rows = cx ? r / 2 : r;
+  if (cols) *cols = c;
+  if (is_complex) *is_complex = cx;
+  return B2_OK;
+}
+int b2_space_coords(const b2_space* sp, int axis, double* x) {
+  if (axis < 0 || axis > 1) return fail(B2_ERR_ARG, "axis");
+  const Base1& b = sp->b[axis];
+  const double PI = 3.14159265358979323846;
+  for (int j = 0; j < b.n; j++) x[j] = b.cheb ? -std::cos(PI * j / (b.n - 1)) : 2.0 * PI * j / b.n;
+  return B2_OK;
+}
+
+int b2_array_create(b2_space* sp, int shape_kind, b2_array** out) {
+  int r, c;
+  RET(shape_of(sp, shape_kind, &r, &c));
+  CK(cudaSetDevice(sp->ctx->device));
+  b2_array* a = new b2_array{sp, nullptr, shape_kind};
+  RET(alloc_zero(sp, &a->d));
+  *out = a;
+  return B2_OK;
+}
+int b2_array_destroy(b2_array* a) { if (a) { cudaFree(a->d); delete a; } return B2_OK; }
+
+static int array_copy(const b2_array* a, void* buf, size_t bytes, int to_device) {
+  b2_space* sp = a->sp;
+  int r, c;
+  RET(shape_of(sp, a->shape_kind, &r, &c));
+  const size_t need = (size_t)r * c * sizeof(double);
+  if (bytes != need) return fail(B2_ERR_SHAPE, "host buffer has " + std::to_string(bytes) + " bytes, array needs " + std::to_string(need));
+  CK(cudaSetDevice(sp->ctx->device));
+  double* stage = nullptr;
+  CK(cudaMalloc(&stage, need));
+  cudaStream_t st = sp->ctx->stream;
+  const int cx = shape_complex(sp, a->shape_kind);
+  const size_t total = (size_t)r * c;
+  const int grid = (int)((total + 255) / 256);
+  if (to_device) {
+    CK(cudaMemcpyAsync(stage, buf, need, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(a->d, 0, sp->elems() * sizeof(double), st));
+    B2_LAUNCH(k_host_layout, grid, 256, 0, st, a->d, stage, r, c, sp->P[1] / 4, cx, 1);
+  } else {
+    B2_LAUNCH(k_host_layout, grid, 256, 0, st, a->d, stage, r, c, sp->P[1] / 4, cx, 0);
+    CK(cudaMemcpyAsync(buf, stage, need, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(stage));
+  return B2_OK;
+}
+int b2_array_set_host(b2_array* a, const void* buf, size_t bytes) { return array_copy(a, const_cast<void*>(buf), bytes, 1); }
+int b2_array_get_host(const b2_array* a, void* buf, size_t bytes) { return array_copy(a, buf, bytes, 0); }
+int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
+  if (y->sp->elems() != x->sp->elems()) return fail(B2_ERR_SHAPE, "axpy: different spaces");
+  const size_t n = y->sp->elems();
+  B2_LAUNCH(k_axpby, ew_grid(n), 256, 0, y->sp->ctx->stream, n, y->d, alpha, x->d, 1.0);
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+static int norm2_dev(b2_space* sp, const double* d, double* out) {
+  double* acc = nullptr;
+  CK(cudaMalloc(&acc, sizeof(double)));
+  CK(cudaMemsetAsync(acc, 0, sizeof(double), sp->ctx->stream));
+  const size_t n = sp->elems();
+  B2_LAUNCH(k_sumsq, ew_grid(n), 256, 0, sp->ctx->stream, n, d, acc);
+  CK(cudaGetLastError());
+  double h = 0;
+  CK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
+  CK(cudaStreamSynchronize(sp->ctx->stream));
+  CK(cudaFree(acc));
+  *out = std::sqrt(h);
+  return B2_OK;
+}
+int b2_array_norm2(const b2_array* a, double* out) { return norm2_dev(a->sp, a->d, out); }
+
+int b2_field_create(b2_space* sp, b2_field** out) {
+  b2_field* f = new b2_field{sp, nullptr, nullptr};
+  RET(b2_array_create(sp, B2_SHAPE_PHYSICAL, &f->v));
+  RET(b2_array_create(sp, B2_SHAPE_SPECTRAL, &f->vhat));
+  *out = f;
+  return B2_OK;
+}
+int b2_field_destroy(b2_field* f) { if (f) { b2_array_destroy(f->v); b2_array_destroy(f->vhat); delete f; } return B2_OK; }
+int b2_field_set_v_host(b2_field* f, const void* buf, size_t bytes) { return b2_array_set_host(f->v, buf, bytes); }
+int b2_field_get_v_host(const b2_field* f, void* buf, size_t bytes) { return b2_array_get_host(f->v, buf, bytes); }
+int b2_field_set_vhat_host(b2_field* f, const void* buf, size_t bytes) { return b2_array_set_host(f->vhat, buf, bytes); }
+int b2_field_get_vhat_host(const b2_field* f, void* buf, size_t bytes) { return b2_array_get_host(f->vhat, buf, bytes); }
+int b2_forward(b2_field* f) { return op_forward(f->sp, f->v->d, f->vhat->d); }
+int b2_backward(b2_field* f) { return op_backward(f->sp, f->vhat->d, f->v->d); }
+static int need_kind(const b2_array* a, int kind, const char* what) {
+  if (a->shape_kind != kind) return fail(B2_ERR_SHAPE, std::string(what) + ": array has the wrong shape kind");
+  return B2_OK;
+}
+int b2_to_ortho(const b2_field* f, b2_array* out) {
+  RET(need_kind(out, B2_SHAPE_ORTHO, "to_ortho"));
+  return op_to_ortho(f->sp, f->vhat->d, out->d);
+}
+int b2_from_ortho(b2_field* f, const b2_array* in) {
+  RET(need_kind(in, B2_SHAPE_ORTHO, "from_ortho"));
+  return op_from_ortho(f->sp, in->d, f->vhat->d);
+}
+int b2_gradient(const b2_field* f, int d0, int d1, const double* scale, b2_array* out) {
+  RET(need_kind(out, B2_SHAPE_ORTHO, "gradient"));
+  if (d0 < 0 || d1 < 0 || d0 > 3 || d1 > 3) return fail(B2_ERR_ARG, "gradient: derivative order");
+  return op_gradient(f->sp, f->vhat->d, d0, d1, scale, out->d);
+}
+
+int b2_hholtz_adi_create(const b2_field* f, double c0, double c1, b2_solver** out) { return hholtz_create(f->sp, c0, c1, out); }
+int b2_poisson_create(const b2_field* f, double c0, double c1, const double* lam, const double* fwd, const double* bwd, b2_solver** out) {
+  return poisson_create(f->sp, c0, c1, lam, fwd, bwd, out);
+}
+int b2_solver_destroy(b2_solver* s) {
+  if (!s) return B2_OK;
+  for (int ax = 0; ax < 2; ax++) { s->fl[ax].release(); s->id[ax].release(); s->u1[ax].release(); s->u2[ax].release(); s->sd[ax].release(); }
+  s->fwd.release(); s->bwd.release(); s->pfl.release(); s->pid.release(); s->pu1.release(); s->pu2.release();
+  for (auto& p : s->plain) if (p) cudaFree(p);
+  delete s;
+  return B2_OK;
+}
+int b2_solve(b2_solver* s, const b2_array* in, b2_array* out) {
+  // shape checks replace the reference's assert!/panic! (src/solver/fdma_tensor.rs:256-263)
+  RET(need_kind(in, B2_SHAPE_ORTHO, "solve input"));
+  RET(need_kind(out, B2_SHAPE_SPECTRAL, "solve output"));
+  if (in->sp != s->sp || out->sp != s->sp) return fail(B2_ERR_SHAPE, "solve: arrays belong to a different space");
+  return s->type == 0 ? hholtz_solve(s, in->d, out->d) : poisson_solve(s, in->d, out->d, false);
+}
+
+static void dense_from_diags(const Diags& d, double* out) {
+  const int m = d.m;
+  std::fill(out, out + (size_t)m * m, 0.0);
+  for (int i = 0; i < m; i++) {
+    out[(size_t)i * m + i] = d.dia[i];
+    if (i + 2 < m) { out[(size_t)(i + 2) * m + i] = d.low[i]; out[(size_t)i * m + i + 2] = d.up1[i]; }
+    if (i + 4 < m) out[(size_t)i * m + i + 4] = d.up2[i];
+  }
+}
+int b2_host_poisson_matrices(int kind0, int n0, double c0, double* a0, double* cmat0) {
+  Base1 b0;
+  RET(b0.init_host(kind0, n0));
+  if (!b0.composite) return fail(B2_ERR_ARG, "axis 0 is not a composite Chebyshev base");
+  Diags lap, mass;
+  poisson_axis(b0, c0, &lap, &mass);
+  dense_from_diags(lap, a0);
+  dense_from_diags(mass, cmat0);
+  return B2_OK;
+}
+int b2_poisson_axis0_matrices(const b2_field* f, double c0, double* a0, double* cmat0) {
+  return b2_host_poisson_matrices(f->sp->b[0].kind, f->sp->b[0].n, c0, a0, cmat0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Navier2D
+// ---------------------------------------------------------------------------------------------
+static int nav_alloc(b2_space* sp, double** p) { return alloc_zero(sp, p); }
+
+int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double dt, double aspect, const char* bc,
+                       int periodic, const double* lam, const double* fwd, const double* bwd, b2_navier** out) {
+  if (!bc || std::string(bc) != "rbc") return fail(B2_ERR_UNSUPPORTED, "only bc=\"rbc\" is built (\"hc\": SURVEY 8f item 2)");
+  b2_navier* nv = new b2_navier();
+  nv->ctx = ctx; nv->nx = nx; nv->ny = ny; nv->periodic = periodic;
+  nv->ra = ra; nv->pr = pr; nv->dt = dt; nv->scale[0] = aspect; nv->scale[1] = 1.0;
+  const double height = nv->scale[1] * 2.0;  // functions.rs:12-21
+  nv->nu = std::sqrt(pr / (ra / std::pow(height, 3.0)));
+  nv->ka = std::sqrt(1.0 / ((ra / std::pow(height, 3.0)) * pr));
+  const int kx_vel = periodic ? B2_FOURIER_R2C : B2_CHEB_DIRICHLET;
+  const int kx_temp = periodic ? B2_FOURIER_R2C : B2_CHEB_NEUMANN;
+  const int kx_ortho = periodic ? B2_FOURIER_R2C : B2_CHEBYSHEV;
+  const int kx_pseu = periodic ? B2_FOURIER_R2C : B2_CHEB_NEUMANN;
+  RET(b2_space2_create(ctx, kx_vel, nx, B2_CHEB_DIRICHLET, ny, &nv->sp_vel));     // navier.rs:235-236 / 356-357
+  RET(b2_space2_create(ctx, kx_temp, nx, B2_CHEB_DIRICHLET, ny, &nv->sp_temp));   // :240 / :361
+  RET(b2_space2_create(ctx, kx_ortho, nx, B2_CHEBYSHEV, ny, &nv->sp_ortho));      // :254,256 / :375,377
+  RET(b2_space2_create(ctx, kx_pseu, nx, B2_CHEB_NEUMANN, ny, &nv->sp_pseu));     // :255 / :376
+  RET(b2_field_create(nv->sp_vel, &nv->velx)); RET(b2_field_create(nv->sp_vel, &nv->vely));
+  RET(b2_field_create(nv->sp_temp, &nv->temp)); RET(b2_field_create(nv->sp_ortho, &nv->pres));
+  RET(b2_field_create(nv->sp_pseu, &nv->pseu)); RET(b2_field_create(nv->sp_ortho, &nv->tempbc));
+  const double sx2 = nv->scale[0] * nv->scale[0], sy2 = nv->scale[1] * nv->scale[1];
+  RET(hholtz_create(nv->sp_vel, dt * nv->nu / sx2, dt * nv->nu / sy2, &nv->hh[0]));   // navier.rs:263-274
+  RET(hholtz_create(nv->sp_vel, dt * nv->nu / sx2, dt * nv->nu / sy2, &nv->hh[1]));
+  RET(hholtz_create(nv->sp_temp, dt * nv->ka / sx2, dt * nv->ka / sy2, &nv->hh[2]));
+  RET(poisson_create(nv->sp_pseu, 1.0 / sx2, 1.0 / sy2, lam, fwd, bwd, &nv->pois)); // navier.rs:275
+  b2_space* so = nv->sp_ortho;
+  double** work[] = {&nv->that, &nv->tbc_ortho, &nv->tbc_diff, &nv->rhs, &nv->g1, &nv->g2, &nv->conv, &nv->div, &nv->ux, &nv->uy};
+  for (auto w : work) RET(nav_alloc(so, w));
+  CK(cudaMalloc(&nv->d_scalar, sizeof(double)));
+  // tempbc, src/navier_stokes/boundary_conditions.rs:18-36 / :143-161: v[i, :] = m y + n, forward, backward
+  {
+    std::vector<double> y(ny), v((size_t)nx * ny);
+    RET(b2_space_coords(so, 1, y.data()));
+    const double x1 = y[0], x2 = y[ny - 1], y1 = 0.5, y2 = -0.5;
+    const double m = (y2 - y1) / (x2 - x1), n = (y1 * x2 - y2 * x1) / (x2 - x1);
+    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) v[(size_t)i * ny + j] = m * y[j] + n;
+    RET(b2_field_set_v_host(nv->tempbc, v.data(), v.size() * sizeof(double)));
+    RET(b2_forward(nv->tempbc));
+    RET(b2_backward(nv->tempbc));
+    // constants of the step: to_ortho(tempbc) and dt*ka*(d2/dx2 + d2/dy2) tempbc (navier_eq.rs:214-218)
+    RET(op_to_ortho(so, nv->tempbc->vhat->d, nv->tbc_ortho));
+    RET(op_gradient(so, nv->tempbc->vhat->d, 2, 0, nv->scale, nv->tbc_diff, dt * nv->ka, false));
+    RET(op_gradient(so, nv->tempbc->vhat->d, 0, 2, nv->scale, nv->tbc_diff, dt * nv->ka, true));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = nv;
+  return B2_OK;
+}
+
+int b2_navier_destroy(b2_navier* nv) {
+  if (!nv) return B2_OK;
+  double* work[] = {nv->that, nv->tbc_ortho, nv->tbc_diff, nv->rhs, nv->g1, nv->g2, nv->conv, nv->div, nv->ux, nv->uy, nv->d_scalar};
+  for (auto w : work) if (w) cudaFree(w);
+  b2_field* fs[] = {nv->temp, nv->velx, nv->vely, nv->pres, nv->pseu, nv->tempbc};
+  for (auto f : fs) b2_field_destroy(f);
+  for (auto s : nv->hh) b2_solver_destroy(s);
+  b2_solver_destroy(nv->pois);
+  b2_space* sps[] = {nv->sp_vel, nv->sp_temp, nv->sp_ortho, nv->sp_pseu};
+  for (auto s : sps) b2_space_destroy(s);
+  delete nv;
+  return B2_OK;
+}
+
+int b2_navier_field(b2_navier* nv, int which, b2_field** out) {
+  b2_field* fs[] = {nv->temp, nv->velx, nv->vely, nv->pres, nv->pseu, nv->tempbc};
+  if (which < 0 || which > 5) return fail(B2_ERR_ARG, "field index");
+  *out = fs[which];
+  return B2_OK;
+}
+
+static int ew_axpby(b2_navier* nv, double* y, double a, const double* x, double b) {
+  const size_t n = nv->sp_ortho->elems();
+  B2_LAUNCH(k_axpby, ew_grid(n), 256, 0, nv->ctx->stream, n, y, a, x, b);
+  nv->ctx->launches++;
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+static int ew_muladd(b2_navier* nv, double* out, const double* u, const double* p, int acc) {
+  const size_t n = nv->sp_ortho->elems();
+  B2_LAUNCH(k_muladd, ew_grid(n), 256, 0, nv->ctx->stream, n, out, u, p, acc);
+  nv->ctx->launches++;
+  CK(cudaGetLastError());
+  return B2_OK;
+}
+
+// conv_term x2 (+ bc terms), forward, dealias: navier_eq.rs:60-101 + functions.rs:56-82.  rhs -= dt * conv
+static int nav_conv_into_rhs(b2_navier* nv, b2_field* f, bool with_bc) {
+  b2_space* so = nv->sp_ortho;
+  RET(op_gradient(f->sp, f->vhat->d, 1, 0, nv->scale, nv->g1));
+  if (with_bc) RET(op_gradient(so, nv->tempbc->vhat->d, 1, 0, nv->scale, nv->g1, 1.0, true));  // linear: u * B(g_T) + u * B(g_bc)
+  RET(op_backward_ortho(so, nv->g1, nv->g2));
+  RET(ew_muladd(nv, nv->conv, nv->ux, nv->g2, 0));
+  RET(op_gradient(f->sp, f->vhat->d, 0, 1, nv->scale, nv->g1));
+  if (with_bc) RET(op_gradient(so, nv->tempbc->vhat->d, 0, 1, nv->scale, nv->g1, 1.0, true));
+  RET(op_backward_ortho(so, nv->g1, nv->g2));
+  RET(ew_muladd(nv, nv->conv, nv->uy, nv->g2, 1));
+  return op_forward_ortho_dealias(so, nv->conv, nv->rhs, true, -nv->dt, true);
+}
+
+// one reference call = one pass pair ("unfused" mode; mirrors navier.rs:438-466 line by line)
+static int nav_update_unfused(b2_navier* nv) {
+  b2_space* so = nv->sp_ortho;
+  const double dt = nv->dt;
+  // that = temp.to_ortho() + tempbc.to_ortho()
+  RET(op_to_ortho(nv->sp_temp, nv->temp->vhat->d, nv->that));
+  RET(ew_axpby(nv, nv->that, 1.0, nv->tbc_ortho, 1.0));
+  // convection velocity
+  RET(op_backward(nv->sp_vel, nv->velx->vhat->d, nv->ux));
+  RET(op_backward(nv->sp_vel, nv->vely->vhat->d, nv->uy));
+  // solve_velx (navier_eq.rs:176-187)
+  RET(op_to_ortho(nv->sp_vel, nv->velx->vhat->d, nv->rhs));
+  RET(op_gradient(so, nv->pres->vhat->d, 1, 0, nv->scale, nv->rhs, -dt, true));
+  RET(nav_conv_into_rhs(nv, nv->velx, false));
+  RET(hholtz_solve(nv->hh[0], nv->rhs, nv->velx->vhat->d));
+  // solve_vely (navier_eq.rs:190-203)
+  RET(op_to_ortho(nv->sp_vel, nv->vely->vhat->d, nv->rhs));
+  RET(op_gradient(so, nv->pres->vhat->d, 0, 1, nv->scale, nv->rhs, -dt, true));
+  RET(ew_axpby(nv, nv->rhs, dt, nv->that, 1.0));
+  RET(nav_conv_into_rhs(nv, nv->vely, false));
+  RET(hholtz_solve(nv->hh[1], nv->rhs, nv->vely->vhat->d));
+  // div (navier_eq.rs:19-24)
+  RET(op_gradient(nv->sp_vel, nv->velx->vhat->d, 1, 0, nv->scale, nv->div));
+  RET(op_gradient(nv->sp_vel, nv->vely->vhat->d, 0, 1, nv->scale, nv->div, 1.0, true));
+  // solve_pres + remove singularity (navier_eq.rs:158-162)
+  RET(poisson_solve(nv->pois, nv->div, nv->pseu->vhat->d, true));
+  // correct_velocity(1.0) (navier_eq.rs:117-125)
+  RET(op_gradient(nv->sp_pseu, nv->pseu->vhat->d, 1, 0, nv->scale, nv->g1, -1.0));
+  RET(op_from_ortho(nv->sp_vel, nv->g1, nv->velx->vhat->d, 1.0, true));
+  RET(op_gradient(nv->sp_pseu, nv->pseu->vhat->d, 0, 1, nv->scale, nv->g1, -1.0));
+  RET(op_from_ortho(nv->sp_vel, nv->g1, nv->vely->vhat->d, 1.0, true));
+  // update_pres (navier_eq.rs:137-143)
+  RET(ew_axpby(nv, nv->pres->vhat->d, -nv->nu, nv->div, 1.0));
+  RET(op_to_ortho(nv->sp_pseu, nv->pseu->vhat->d, nv->pres->vhat->d, 1.0 / dt, true));
+  // solve_temp (navier_eq.rs:209-224)
+  RET(op_to_ortho(nv->sp_temp, nv->temp->vhat->d, nv->rhs));
+  RET(ew_axpby(nv, nv->rhs, 1.0, nv->tbc_diff, 1.0));
+  RET(nav_conv_into_rhs(nv, nv->temp, true));
+  RET(hholtz_solve(nv->hh[2], nv->rhs, nv->temp->vhat->d));
+  nv->time += dt;
+  return B2_OK;
+}
+
+int b2_navier_update(b2_navier* nv, int nsteps) {
+  CK(cudaSetDevice(nv->ctx->device));
+  for (int s = 0; s < nsteps; s++) {
+    long long l0 = nv->ctx->launches;
+    RET(nav_update_unfused(nv));
+    nv->launches_per_step = nv->ctx->launches - l0;
+  }
+  return B2_OK;
+}
+int b2_navier_div_norm(b2_navier* nv, double* out) {
+  RET(op_gradient(nv->sp_vel, nv->velx->vhat->d, 1, 0, nv->scale, nv->g1));
+  RET(op_gradient(nv->sp_vel, nv->vely->vhat->d, 0, 1, nv->scale, nv->g1, 1.0, true));
+  return norm2_dev(nv->sp_ortho, nv->g1, out);
+}
+int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
+int b2_navier_set_mode(b2_navier* nv, int fused) { nv->fused = fused; return B2_OK; }
+int b2_navier_launch_count(const b2_navier* nv, long long* k) { *k = nv->launches_per_step; return B2_OK; }
+int b2_navier_poisson_matrices(b2_navier* nv, double* a0, double* cmat0, int* m0) {
+  if (m0) *m0 = nv->sp_pseu->b[0].m;
+  if (!a0 || !cmat0) return B2_OK;
+  return b2_poisson_axis0_matrices(nv->pseu, 1.0 / (nv->scale[0] * nv->scale[0]), a0, cmat0);
+}
+
+}  // extern "C"

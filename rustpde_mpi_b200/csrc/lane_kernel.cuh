@@ -1,0 +1,691 @@
+// Lane-program kernel: the one CUDA kernel family behind every per-axis operator
+// of the Navier2D spectral hot path.
+//
+// A CTA owns one "lane group" = 4 neighbouring 1-D lanes (pencils) of a 2-D array
+// and keeps them resident in shared memory while it interprets a short program of
+// 1-D operators (load / banded mat-vec / Chebyshev recurrence / banded LU solve /
+// DCT-I / real FFT / masks / store).  Arrays live in HBM in a 4x4 micro-tiled
+// layout (128-byte tiles), so a lane group is ONE contiguous slab on the way in
+// and full 128-byte lines on the way out, whether the store keeps the orientation
+// or transposes it (that is how the x<->y pencil switch happens: every pass of a
+// 2-D operator ends in a transposing store, locally or into a peer GPU's memory).
+//
+// sm_100a only.  No CPU fallback, no library calls in here.
+#pragma once
+#ifdef B2_EMU   // tests/emu: the same source compiled for the CPU SIMT emulator (test infrastructure only)
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define B2_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define B2_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#include <stdint.h>
+
+#define B2_MAXOPS 24
+#define B2_CMAX 33        // max chunk (elements per thread per lane) for scans / banded ops
+#define B2_MAXPEERS 8
+
+enum LaneOpCode {
+  OP_LOAD = 1,     // W = [W +|*] a * src           i0=len  i2=flags(LD_*)       p0=src
+  OP_STORE = 2,    // dst = [dst +] a * W            i0=len  i2=flags(ST_*)       p0=dst  (p1=peer table)
+  OP_BAND = 3,     // y_i = sum_m c_m[i] x_{i+o_m}   i0=len_out i1=packed offs i2=len_in  p0..p2 coef (null = 1, i1 byte=127: unused)
+  OP_DERIV = 4,    // Chebyshev d/dx of i0 coeffs, i1 times, times a
+  OP_FDMA = 5,     // banded LU solve (fwd elim + back subst)  i0=len i2=flags(FD_*) p0=fl p1=inv_dia p2=u1 p3=u2
+  OP_DCT = 6,      // Chebyshev transform, i0=n (=N+1), i1: 0 fwd (values->coeffs) 1 bwd   p0=tw p1=tw2 p2=isin
+  OP_RFFT = 7,     // Fourier r2c/c2r, i0=n, i1: 0 fwd 1 bwd                              p0=tw p1=tw2
+  OP_FDIFF = 8,    // interleaved complex modes: c_k *= (i k)^{i1} * a,  i0 = number of modes
+  OP_SCALEVEC = 9, // W[e] *= p0[e >> i1] for e < i0
+  OP_ZEROTAIL = 10,// W[e] = 0 for e >= i0
+  OP_LANEMASK = 11,// lanes >= i0 zeroed
+  OP_ZEROELEM = 12,// W[lane i0][pos i1] = 0 (global lane index)
+  OP_SCALE = 13,   // W *= a
+};
+enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4 };
+enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16 };
+enum { FD_PERLANE = 1, FD_NOU2 = 2 };
+
+struct LaneOp {
+  int code, i0, i1, i2;
+  double a, b;
+  const void* p0;
+  const void* p1;
+  const void* p2;
+  const void* p3;
+};
+
+struct LaneProg {
+  int nops;
+  int LP;         // shared-memory lane pitch in doubles (multiple of 4, >= every length used)
+  int in_tiles;   // 4x4 tiles per lane of arrays in the orientation being read
+  int out_tiles;  // tiles per row of the transposed orientation (= number of lane groups)
+  int TPL;        // threads per lane (blockDim.x = 4*TPL)
+  int C;          // chunk: elements per thread per lane, C*TPL >= LP
+  int group0;     // first lane group of this launch (multi-GPU slabs)
+  int groups_per_rank;  // for ST_PEER: owner(J) = J / groups_per_rank (destination orientation)
+  int rank;       // this GPU's rank (peer table index)
+  int pad_;
+  LaneOp ops[B2_MAXOPS];
+};
+
+typedef double2 cplx;
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx cmulmi(cplx a) { return make_double2(a.y, -a.x); }  // a * (-i)
+
+// ---------------------------------------------------------------------------------------------
+// Radix-R DFT in registers (forward, e^{-2 pi i jk/R}), natural order in and out.
+// ---------------------------------------------------------------------------------------------
+template <int R> struct Dft;
+template <> struct Dft<1> { static __device__ __forceinline__ void run(cplx*) {} };
+template <> struct Dft<2> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    cplx a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+template <> struct Dft<4> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    cplx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    cplx t2 = cadd(v[1], v[3]), t3 = cmulmi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+  }
+};
+template <> struct Dft<8> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    cplx e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4>::run(e);
+    Dft<4>::run(o);
+    const double h = 0.70710678118654752440;
+    cplx t1 = make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));   // * e^{-i pi/4}
+    cplx t2 = cmulmi(o[2]);                                                 // * (-i)
+    cplx t3 = make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));  // * e^{-3i pi/4}
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], t1);   v[5] = csub(e[1], t1);
+    v[2] = cadd(e[2], t2);   v[6] = csub(e[2], t2);
+    v[3] = cadd(e[3], t3);   v[7] = csub(e[3], t3);
+  }
+};
+template <> struct Dft<16> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    cplx e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Dft<8>::run(e);
+    Dft<8>::run(o);
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    const cplx w[8] = {{1, 0}, {c1, -s1}, {h, -h}, {s1, -c1}, {0, -1}, {-s1, -c1}, {-h, -h}, {-c1, -s1}};
+    v[0] = cadd(e[0], o[0]); v[8] = csub(e[0], o[0]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+      cplx t = (k == 4) ? cmulmi(o[4]) : cmul(w[k], o[k]);
+      v[k] = cadd(e[k], t);
+      v[k + 8] = csub(e[k], t);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// shuffle helpers for small structs of doubles
+// ---------------------------------------------------------------------------------------------
+template <int K> struct DVec { double d[K]; };
+template <int K> __device__ __forceinline__ DVec<K> shfl_up(const DVec<K>& m, int delta, int width) {
+  DVec<K> r;
+#pragma unroll
+  for (int i = 0; i < K; i++) r.d[i] = __shfl_up_sync(0xffffffffu, m.d[i], delta, width);
+  return r;
+}
+template <int K> __device__ __forceinline__ DVec<K> shfl_down(const DVec<K>& m, int delta, int width) {
+  DVec<K> r;
+#pragma unroll
+  for (int i = 0; i < K; i++) r.d[i] = __shfl_down_sync(0xffffffffu, m.d[i], delta, width);
+  return r;
+}
+
+// Affine maps used by the lane recurrences.  "then(f, s)" = apply f first, then s.
+// First order, two independent parities:  y -> A y + B.      d = {A0,B0,A1,B1}
+struct Aff1 {
+  typedef DVec<4> V;
+  static __device__ __forceinline__ V identity() { V v; v.d[0] = 1; v.d[1] = 0; v.d[2] = 1; v.d[3] = 0; return v; }
+  static __device__ __forceinline__ V then(const V& f, const V& s) {
+    V r;
+    r.d[0] = s.d[0] * f.d[0]; r.d[1] = fma(s.d[0], f.d[1], s.d[1]);
+    r.d[2] = s.d[2] * f.d[2]; r.d[3] = fma(s.d[2], f.d[3], s.d[3]);
+    return r;
+  }
+};
+// Second order, two parities: state (u,w) -> P (u,w) + p.   d = {P00,P01,P10,P11,p0,p1} x 2
+struct Aff2 {
+  typedef DVec<12> V;
+  static __device__ __forceinline__ V identity() {
+    V v;
+#pragma unroll
+    for (int h = 0; h < 2; h++) { v.d[6*h+0] = 1; v.d[6*h+1] = 0; v.d[6*h+2] = 0; v.d[6*h+3] = 1; v.d[6*h+4] = 0; v.d[6*h+5] = 0; }
+    return v;
+  }
+  static __device__ __forceinline__ V then(const V& f, const V& s) {
+    V r;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const double* F = f.d + 6 * h; const double* S = s.d + 6 * h; double* R = r.d + 6 * h;
+      R[0] = S[0] * F[0] + S[1] * F[2]; R[1] = S[0] * F[1] + S[1] * F[3];
+      R[2] = S[2] * F[0] + S[3] * F[2]; R[3] = S[2] * F[1] + S[3] * F[3];
+      R[4] = S[0] * F[4] + S[1] * F[5] + S[4];
+      R[5] = S[2] * F[4] + S[3] * F[5] + S[5];
+    }
+    return r;
+  }
+};
+
+// Exclusive scan of per-thread maps across the TPL threads of one lane.
+// PREFIX: result = composition of the maps of threads q' < q (lowest applied first).
+// SUFFIX: result = composition of the maps of threads q' > q (highest applied first).
+// scratch: shared, >= 4 lanes * 8 warps entries of M::V.  All threads of the CTA must call.
+template <class M, bool SUFFIX>
+__device__ __forceinline__ typename M::V lane_scan_excl(typename M::V mine, int TPL, typename M::V* scratch) {
+  typedef typename M::V V;
+  const int tid = threadIdx.x;
+  const int q = tid % TPL, lane = tid / TPL;
+  const int width = TPL < 32 ? TPL : 32;
+  const int qi = q % width;   // position inside the shuffle segment
+  V inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    if (d < width) {
+      V o = SUFFIX ? shfl_down(inc, d, width) : shfl_up(inc, d, width);
+      bool take = SUFFIX ? (qi + d < width) : (qi >= d);
+      if (take) inc = M::then(o, inc);
+    }
+  }
+  V exc = SUFFIX ? shfl_down(inc, 1, width) : shfl_up(inc, 1, width);
+  if (SUFFIX ? (qi == width - 1) : (qi == 0)) exc = M::identity();
+  if (TPL > 32) {
+    const int nw = TPL / 32, w = q / 32;
+    if (SUFFIX ? (qi == 0) : (qi == 31)) scratch[lane * 8 + w] = inc;
+    __syncthreads();
+    V carry = M::identity();
+    if (SUFFIX) { for (int k = nw - 1; k > w; k--) carry = M::then(carry, scratch[lane * 8 + k]); }
+    else        { for (int k = 0; k < w; k++) carry = M::then(carry, scratch[lane * 8 + k]); }
+    exc = M::then(carry, exc);
+    __syncthreads();
+  }
+  return exc;
+}
+
+// sum over the TPL threads of a lane (result valid in every thread of the lane)
+__device__ __forceinline__ double lane_sum(double v, int TPL, double* scratch) {
+  const int tid = threadIdx.x, q = tid % TPL, lane = tid / TPL;
+  const int width = TPL < 32 ? TPL : 32;
+  for (int d = width >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d, width);
+  if (TPL > 32) {
+    const int nw = TPL / 32, w = q / 32;
+    if ((q & 31) == 0) scratch[lane * 8 + w] = v;
+    __syncthreads();
+    double s = 0;
+    for (int k = 0; k < nw; k++) s += scratch[lane * 8 + k];
+    __syncthreads();
+    v = s;
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ops
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl) {
+  const int T = blockDim.x, LP = P.LP;
+  const int npieces = LP * 2;  // 4 lanes * LP / 2 doubles
+  const int len = op.i0;
+  const double a = op.a;
+  const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, plain = op.i2 & LD_PLAIN;
+  const double2* src = reinterpret_cast<const double2*>(op.p0);
+  const size_t slab = (size_t)gl * P.in_tiles * 8;  // in double2 units
+  for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
+    int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (J < P.in_tiles && j0 < len) {
+      if (plain) v = src[((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1];
+      else v = src[slab + pidx];
+      v.x *= a;
+      v.y = (j0 + 1 < len) ? v.y * a : 0.0;
+    }
+    double2* w = reinterpret_cast<double2*>(W + l * LP + j0);
+    if (acc) { double2 o = *w; v.x += o.x; v.y += o.y; }
+    else if (mul) { double2 o = *w; v.x *= o.x; v.y *= o.y; }
+    *w = v;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, const double* __restrict__ W, int g, int gl) {
+  const int T = blockDim.x, LP = P.LP;
+  const int npieces = P.in_tiles * 8;
+  const int len = op.i0;
+  const double a = op.a;
+  const int flags = op.i2;
+  double2* dst = reinterpret_cast<double2*>(const_cast<void*>(op.p0));
+  if (flags & ST_TRANS) {
+    double* const* peers = reinterpret_cast<double* const*>(op.p1);
+    for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
+      int J = pidx >> 3, jl = (pidx & 7) >> 1, l0 = (pidx & 1) * 2, j = 4 * J + jl;
+      double2 v = make_double2(0.0, 0.0);
+      if (j < len) { v.x = a * W[l0 * LP + j]; v.y = a * W[(l0 + 1) * LP + j]; }
+      double2* d = dst;
+      int Jl = J;
+      if (flags & ST_PEER) {  // row block J of the transposed array lives on rank J / groups_per_rank
+        int owner = J / P.groups_per_rank;
+        Jl = J - owner * P.groups_per_rank;
+        d = reinterpret_cast<double2*>(reinterpret_cast<char*>(peers[owner]) +
+                                       (reinterpret_cast<const char*>(op.p0) - reinterpret_cast<const char*>(peers[P.rank])));
+      }
+      size_t idx = (((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + l0) >> 1;
+      if (flags & ST_ACC) { double2 o = d[idx]; v.x += o.x; v.y += o.y; }
+      d[idx] = v;
+    }
+  } else {
+    const size_t slab = (size_t)gl * P.in_tiles * 8;
+    for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
+      int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      double2 v = make_double2(0.0, 0.0);
+      if (j0 < len) {
+        double2 w = *reinterpret_cast<const double2*>(W + l * LP + j0);
+        v.x = a * w.x;
+        v.y = (j0 + 1 < len) ? a * w.y : 0.0;
+      }
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1) : (slab + pidx);
+      if (flags & ST_ACC) { double2 o = dst[idx]; v.x += o.x; v.y += o.y; }
+      dst[idx] = v;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void op_band(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  const int TPL = P.TPL, C = P.C, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int len_out = op.i0, len_in = op.i2;
+  const int o0 = (int)(signed char)(op.i1 & 0xff), o1 = (int)(signed char)((op.i1 >> 8) & 0xff), o2 = (int)(signed char)((op.i1 >> 16) & 0xff);
+  const double* c0 = (const double*)op.p0; const double* c1 = (const double*)op.p1; const double* c2 = (const double*)op.p2;
+  const double* w = W + l * LP;
+  double y[B2_CMAX];
+  const int base = q * C;
+#pragma unroll
+  for (int ii = 0; ii < B2_CMAX; ii++) {
+    int i = base + ii;
+    double acc = 0.0;
+    if (ii < C && i < len_out) {
+      if (o0 != 127) { int j = i + o0; if (j >= 0 && j < len_in) acc = (c0 ? c0[i] : 1.0) * w[j]; }
+      if (o1 != 127) { int j = i + o1; if (j >= 0 && j < len_in) acc = fma(c1 ? c1[i] : 1.0, w[j], acc); }
+      if (o2 != 127) { int j = i + o2; if (j >= 0 && j < len_in) acc = fma(c2 ? c2[i] : 1.0, w[j], acc); }
+    }
+    y[ii] = acc;
+  }
+  __syncthreads();
+  double* wo = W + l * LP;
+#pragma unroll
+  for (int ii = 0; ii < B2_CMAX; ii++) {
+    int i = base + ii;
+    if (ii < C && i < LP) wo[i] = y[ii];
+  }
+  __syncthreads();
+}
+
+// Chebyshev derivative: b_k = S_{k+1},  S_m = 2 m a_m + S_{m+2};  b_0 *= 1/2;  result * scale
+__device__ __forceinline__ void op_deriv(const LaneProg& P, const LaneOp& op, double* __restrict__ W, void* scratch) {
+  const int TPL = P.TPL, C = P.C, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int n = op.i0;
+  double* w = W + l * LP;
+  const int base = q * C;
+  for (int rep = 0; rep < op.i1; rep++) {
+    // pass 1: chunk totals per parity
+    double tot0 = 0.0, tot1 = 0.0;
+#pragma unroll
+    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
+      int i = base + ii;
+      if (ii < C && i < n) { double t = 2.0 * i * w[i]; if (i & 1) tot1 += t; else tot0 += t; }
+    }
+    Aff1::V m; m.d[0] = 1; m.d[1] = tot0; m.d[2] = 1; m.d[3] = tot1;
+    Aff1::V inc = lane_scan_excl<Aff1, true>(m, TPL, (Aff1::V*)scratch);
+    double s0 = inc.d[1], s1 = inc.d[3];
+    double y[B2_CMAX];
+#pragma unroll
+    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
+      int i = base + ii;
+      double v = 0.0;
+      if (ii < C && i < LP) {
+        double t = (i < n) ? 2.0 * i * w[i] : 0.0;
+        if (i & 1) { s1 += t; v = s1; } else { s0 += t; v = s0; }
+      }
+      y[ii] = v;   // = S_i
+    }
+    __syncthreads();
+    const double sc = (rep == op.i1 - 1) ? op.a : 1.0;
+#pragma unroll
+    for (int ii = 0; ii < B2_CMAX; ii++) {
+      int i = base + ii;
+      if (ii < C && i < LP && i >= 1) w[i - 1] = y[ii] * (i == 1 ? 0.5 * sc : sc);
+    }
+    if (q == TPL - 1) w[LP - 1] = 0.0;
+    __syncthreads();
+  }
+}
+
+// Coefficient access for the banded LU solve: shared vectors (index i) or per-lane arrays in
+// "scan layout"  ((g*C + ii)*4 + l)*TPL + q  (coalesced across the CTA at every step).
+struct FdCoef {
+  const double* fl; const double* id; const double* u1; const double* u2;
+  bool perlane; size_t pbase; int stride;
+  __device__ __forceinline__ size_t ix(int i, int ii) const { return perlane ? pbase + (size_t)ii * stride : (size_t)i; }
+};
+
+// In-place solve of the LU-factored 4-diagonal (-2,0,+2,+4) system (reference: src/solver/fdma.rs:101-118):
+//   forward:  x_i -= fl_i x_{i-2}                     (fl_i = swept low_{i-2})
+//   backward: x_i = (x_i - u1_i x_{i+2} - u2_i x_{i+4}) * id_i
+// Each thread owns a chunk; chunk maps are combined with an exclusive scan over the lane.
+__device__ __forceinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, void* scratch) {
+  const int TPL = P.TPL, C = P.C, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int n = op.i0;
+  double* w = W + l * LP;
+  const int base = q * C;
+  FdCoef cf;
+  cf.fl = (const double*)op.p0; cf.id = (const double*)op.p1; cf.u1 = (const double*)op.p2; cf.u2 = (const double*)op.p3;
+  cf.perlane = op.i2 & FD_PERLANE;
+  cf.stride = 4 * TPL;
+  cf.pbase = ((size_t)gl * C * 4 + l) * TPL + q;
+  const bool nou2 = op.i2 & FD_NOU2;
+  // ---- forward elimination (first order, prefix) ----
+  {
+    Aff1::V m = Aff1::identity();
+#pragma unroll
+    for (int ii = 0; ii < B2_CMAX; ii++) {
+      int i = base + ii;
+      if (ii < C && i < n) {
+        double a = -cf.fl[cf.ix(i, ii)], b = w[i];
+        int h = (i & 1) * 2;
+        m.d[h + 1] = fma(a, m.d[h + 1], b);
+        m.d[h] *= a;
+      }
+    }
+    Aff1::V inc = lane_scan_excl<Aff1, false>(m, TPL, (Aff1::V*)scratch);
+    double y0 = inc.d[1], y1 = inc.d[3];  // x of the last even / odd element before this chunk (start state is 0)
+#pragma unroll
+    for (int ii = 0; ii < B2_CMAX; ii++) {
+      int i = base + ii;
+      if (ii < C && i < n) {
+        double a = -cf.fl[cf.ix(i, ii)];
+        if (i & 1) { y1 = fma(a, y1, w[i]); w[i] = y1; } else { y0 = fma(a, y0, w[i]); w[i] = y0; }
+      }
+    }
+  }
+  // no sync needed: every thread only touches its own chunk
+  // ---- back substitution (second order, suffix) ----
+  {
+    Aff2::V m = Aff2::identity();
+#pragma unroll
+    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
+      int i = base + ii;
+      if (ii < C && i < n) {
+        size_t k = cf.ix(i, ii);
+        double idv = cf.id[k];
+        double m0 = -cf.u1[k] * idv, m1 = nou2 ? 0.0 : -cf.u2[k] * idv, v0 = w[i] * idv;
+        double* M = m.d + 6 * (i & 1);
+        double r0 = m0 * M[0] + m1 * M[2], r1 = m0 * M[1] + m1 * M[3], rp = m0 * M[4] + m1 * M[5] + v0;
+        M[2] = M[0]; M[3] = M[1]; M[5] = M[4];
+        M[0] = r0; M[1] = r1; M[4] = rp;
+      }
+    }
+    Aff2::V inc = lane_scan_excl<Aff2, true>(m, TPL, (Aff2::V*)scratch);
+    // incoming state (x_{i+2}, x_{i+4}) per parity; the far-end state is (0,0) so only the offsets matter
+    double s[4] = {inc.d[4], inc.d[5], inc.d[10], inc.d[11]};
+#pragma unroll
+    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
+      int i = base + ii;
+      if (ii < C && i < n) {
+        size_t k = cf.ix(i, ii);
+        double idv = cf.id[k];
+        double* st = s + 2 * (i & 1);
+        double x = w[i] - cf.u1[k] * st[0];
+        if (!nou2) x -= cf.u2[k] * st[1];
+        x *= idv;
+        st[1] = st[0]; st[0] = x;
+        w[i] = x;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// complex FFT of Nc points per lane, in place in shared memory (Stockham autosort, register-staged:
+// every thread reads its E points, the CTA syncs, then everything is written back).
+// tw[t] = exp(-2 pi i t / Nc)
+// ---------------------------------------------------------------------------------------------
+template <int E, int R>
+__device__ __forceinline__ void fft_stage(double* __restrict__ wl, int Nc, int Ns, int q, int TPL, const cplx* __restrict__ tw) {
+  constexpr int NB = E / R;
+  cplx v[E];
+  const int stride = Nc / R;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    int j = q + b * TPL;
+#pragma unroll
+    for (int r = 0; r < R; r++) v[b * R + r] = *reinterpret_cast<const cplx*>(wl + 2 * (j + r * stride));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    int j = q + b * TPL;
+    int k = j % Ns;
+    if (Ns > 1) {
+      int tstep = k * (Nc / (Ns * R));
+#pragma unroll
+      for (int r = 1; r < R; r++) v[b * R + r] = cmul(v[b * R + r], tw[r * tstep]);
+    }
+    Dft<R>::run(v + b * R);
+    int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; r++) *reinterpret_cast<cplx*>(wl + 2 * (j0 + r * Ns)) = v[b * R + r];
+  }
+  __syncthreads();
+}
+
+template <int E>
+__device__ __forceinline__ void lane_fft(double* __restrict__ W, int LP, int Nc, int TPL, const cplx* __restrict__ tw) {
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  double* wl = W + l * LP;
+  int Ns = 1;
+  // radix plan: as many radix-E passes as fit, then one pass with the remainder (1, 2, 4 or 8)
+  while (Nc / Ns >= E) { fft_stage<E, E>(wl, Nc, Ns, q, TPL, tw); Ns *= E; }
+  const int rem = Nc / Ns;
+  if constexpr (E >= 16) { if (rem == 8) fft_stage<E, 8>(wl, Nc, Ns, q, TPL, tw); }
+  if constexpr (E >= 8) { if (rem == 4) fft_stage<E, 4>(wl, Nc, Ns, q, TPL, tw); }
+  if (rem == 2) fft_stage<E, 2>(wl, Nc, Ns, q, TPL, tw);
+}
+
+// Chebyshev transform (DCT-I of n = N+1 points on Gauss-Lobatto nodes x_j = -cos(pi j/N)) through ONE
+// complex FFT of N/2 points:
+//   mode 0 (forward):  c_k = (-1)^k X_k / N, c_0 and c_N halved,  X = DCT-I(v)
+//   mode 1 (backward): v = DCT-I(y)/2, y_k = (-1)^k c_k, y_0 and y_N doubled
+// tw: exp(-2 pi i t/(N/2)), tw2[j] = exp(-2 pi i j/N) (j <= N/2), isin[k] = 1/(4 sin(pi k/N))
+template <int E>
+__device__ __forceinline__ void op_dct(const LaneProg& P, const LaneOp& op, double* __restrict__ W, double* scratch) {
+  const int TPL = P.TPL, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int N = op.i0 - 1, M = N >> 1, mode = op.i1;
+  const cplx* tw = (const cplx*)op.p0; const cplx* tw2 = (const cplx*)op.p1; const double* isin = (const double*)op.p2;
+  double* w = W + l * LP;
+  constexpr int NP = E / 2 + 1;
+  // ---- pre: x -> g (N/2 complex), pairs (j, M-j) ----
+  cplx gj[NP], gm[NP];
+  double r0 = 0.0;
+  auto xin = [&](int i) -> double {  // input sample with the backward-mode pre-scaling folded in
+    double v = w[i];
+    if (mode == 1) { if (i & 1) v = -v; if (i == 0 || i == N) v *= 2.0; }
+    return v;
+  };
+#pragma unroll
+  for (int pi = 0; pi < NP; pi++) {
+    int j = q + pi * TPL;
+    gj[pi] = make_double2(0, 0); gm[pi] = make_double2(0, 0);
+    if (j <= M / 2) {
+      int jm = M - j;
+      double xo_p = xin(2 * j + 1);                       // x_{2j+1}
+      double xo_m = (j == 0) ? xo_p : xin(2 * j - 1);     // x_{2j-1}, x_{-1} = x_1
+      double xm_m = xin(2 * jm - 1);                      // x_{2jm-1}
+      double xm_p = (jm == M) ? xm_m : xin(2 * jm + 1);   // x_{2jm+1}, x_{N+1} = x_{N-1}
+      cplx zj = make_double2(xin(2 * j), xo_p - xo_m);
+      cplx zmc = make_double2(xin(2 * jm), -(xm_p - xm_m));  // conj(z_{M-j})
+      cplx e = cadd(zj, zmc), d = cmul(csub(zj, zmc), tw2[j]);
+      gj[pi] = make_double2(e.x - d.y, e.y + d.x);           // e + i d
+      gm[pi] = make_double2(e.x + d.y, -e.y + d.x);          // conj(e) + i conj(d)
+      if (j < M / 2) r0 += xo_p + xm_m;
+    }
+  }
+  r0 = 2.0 * lane_sum(r0, TPL, scratch);   // R_0 = 2 * sum of odd samples
+  __syncthreads();
+#pragma unroll
+  for (int pi = 0; pi < NP; pi++) {
+    int j = q + pi * TPL;
+    if (j <= M / 2) {
+      *reinterpret_cast<cplx*>(w + 2 * j) = gj[pi];
+      if (j > 0 && j < M / 2) *reinterpret_cast<cplx*>(w + 2 * (M - j)) = gm[pi];
+    }
+  }
+  __syncthreads();
+  lane_fft<E>(W, LP, M, TPL, tw);
+  // ---- post: Z (N reals) -> X (N+1), pairs (k, N-k) ----
+  const double fs = (mode == 0) ? 1.0 / N : 0.5;
+  for (int k = q; k <= M; k += TPL) {
+    double xk, xn;
+    if (k == 0) { double z0 = w[0]; xk = z0 + r0; xn = z0 - r0; if (mode == 0) { xk *= 0.5; xn *= 0.5; } }
+    else if (k == M) { xk = w[M]; xn = xk; }
+    else {
+      double zk = w[k], zn = w[N - k];
+      double A = 0.5 * (zk + zn), R = (zn - zk) * isin[k];
+      xk = A + R; xn = A - R;
+    }
+    double sk = fs, sn = fs;
+    if (mode == 0) { if (k & 1) sk = -fs; if ((N - k) & 1) sn = -fs; }
+    w[k] = xk * sk;
+    if (k != M) w[N - k] = xn * sn;
+  }
+  __syncthreads();
+}
+
+// Real FFT of n points along the lane (Fourier axis): forward r2c is unnormalised,
+// n/2+1 interleaved complex modes; backward c2r carries 1/n and ignores Im of the k=0 and k=n/2 modes.
+template <int E>
+__device__ __forceinline__ void op_rfft(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  const int TPL = P.TPL, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int n = op.i0, M = n >> 1, mode = op.i1;
+  const cplx* tw = (const cplx*)op.p0; const cplx* tw2 = (const cplx*)op.p1;
+  double* w = W + l * LP;
+  if (mode == 0) {
+    lane_fft<E>(W, LP, M, TPL, tw);
+    for (int k = q; k <= M / 2; k += TPL) {
+      if (k == 0) {
+        cplx z = *reinterpret_cast<cplx*>(w);
+        *reinterpret_cast<cplx*>(w) = make_double2(z.x + z.y, 0.0);
+        *reinterpret_cast<cplx*>(w + 2 * M) = make_double2(z.x - z.y, 0.0);
+      } else {
+        cplx zk = *reinterpret_cast<cplx*>(w + 2 * k), zm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
+        cplx S = cadd(zk, zm), D = cmul(tw2[k], csub(zk, zm));   // w_k D
+        // X_k = (S - i wD)/2 ; X_{M-k} = conj((S + i wD)/2)
+        *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
+        if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int k = q; k <= M / 2; k += TPL) {
+      if (k == 0) {
+        double x0 = w[0], xm = w[2 * M];
+        // Zc_0 = ((x0+xm) + i(x0-xm))/2 ; FFT input is conj(Zc)
+        *reinterpret_cast<cplx*>(w) = make_double2(0.5 * (x0 + xm), -0.5 * (x0 - xm));
+      } else {
+        cplx xk = *reinterpret_cast<cplx*>(w + 2 * k), xm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
+        cplx S = cadd(xk, xm), D = cmul(cconj(tw2[k]), csub(xk, xm));  // conj(w_k) D'
+        // Zc_k = (S + i cD)/2 ; Zc_{M-k} = conj((S - i cD)/2); store conjugates
+        *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
+        if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
+      }
+    }
+    __syncthreads();
+    lane_fft<E>(W, LP, M, TPL, tw);
+    const double s = 1.0 / M;
+    for (int e = q; e < LP; e += TPL) {
+      double v = w[e];
+      w[e] = (e < n) ? ((e & 1) ? -v * s : v * s) : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int g) {
+  const int TPL = P.TPL, LP = P.LP;
+  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  double* w = W + l * LP;
+  switch (op.code) {
+    case OP_FDIFF: {   // interleaved complex: (re, im) *= (i k)^d * a
+      const int m = op.i0, d = op.i1 & 3;
+      for (int k = q; k < m; k += TPL) {
+        cplx c = *reinterpret_cast<cplx*>(w + 2 * k);
+        double f = op.a;
+        for (int t = 0; t < op.i1; t++) f *= (double)k;
+        cplx r;
+        if (d == 0) r = make_double2(c.x * f, c.y * f);
+        else if (d == 1) r = make_double2(-c.y * f, c.x * f);
+        else if (d == 2) r = make_double2(-c.x * f, -c.y * f);
+        else r = make_double2(c.y * f, -c.x * f);
+        *reinterpret_cast<cplx*>(w + 2 * k) = r;
+      }
+    } break;
+    case OP_SCALEVEC: {
+      const double* v = (const double*)op.p0;
+      for (int e = q; e < op.i0; e += TPL) w[e] *= v[e >> op.i1];
+    } break;
+    case OP_ZEROTAIL:
+      for (int e = op.i0 + q; e < LP; e += TPL) w[e] = 0.0;
+      break;
+    case OP_LANEMASK:
+      if (4 * g + l >= op.i0) for (int e = q; e < LP; e += TPL) w[e] = 0.0;
+      break;
+    case OP_ZEROELEM:
+      if (4 * g + l == op.i0 && q == 0) w[op.i1] = 0.0;
+      break;
+    case OP_SCALE:
+      for (int e = q; e < LP; e += TPL) w[e] *= op.a;
+      break;
+  }
+  __syncthreads();
+}
+
+template <int E>
+__global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg P) {
+  B2_DYN_SMEM(double, smem);
+  double* W = smem;                       // [4][LP]
+  void* scratch = smem + 4 * P.LP;        // 32 * sizeof(DVec<12>) = 3 KB
+  const int gl = blockIdx.x;              // local lane group (addresses this GPU's slab)
+  const int g = P.group0 + gl;            // global lane group (mode indices, transposed stores)
+  for (int o = 0; o < P.nops; o++) {
+    const LaneOp& op = P.ops[o];
+    switch (op.code) {
+      case OP_LOAD: op_load(P, op, W, gl); break;
+      case OP_STORE: op_store(P, op, W, g, gl); break;
+      case OP_BAND: op_band(P, op, W); break;
+      case OP_DERIV: op_deriv(P, op, W, scratch); break;
+      case OP_FDMA: op_fdma(P, op, W, gl, scratch); break;
+      case OP_DCT: op_dct<E>(P, op, W, (double*)scratch); break;
+      case OP_RFFT: op_rfft<E>(P, op, W); break;
+      default: op_pointwise(P, op, W, g); break;
+    }
+  }
+}

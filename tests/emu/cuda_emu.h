@@ -1,0 +1,206 @@
+// SIMT emulator -- TEST INFRASTRUCTURE ONLY (never part of the product, never loaded by
+// rustpde_mpi_b200 itself).  It lets the CPU-only test suite compile the *same* kernel and host
+// sources (lane_kernel.cuh, b200pde.cu) with g++ and run every CUDA thread of a block as an OS
+// thread, so that host logic, lane programs and the per-thread index algebra of the kernels can be
+// checked against the oracle without a GPU.  Build: tests/emu/build_emu.py -> tests/emu/libb200pde_emu.so
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
+#define __shared__ static
+
+struct alignas(16) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+using std::fma;
+
+namespace emu {
+struct Dim3 { int x = 1, y = 1, z = 1; };
+
+class Barrier {
+ public:
+  void reset(int n) { n_ = n; count_ = 0; gen_ = 0; }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const uint64_t g = gen_;
+    if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+    else cv_.wait(lk, [&] { return gen_ != g; });
+  }
+ private:
+  std::mutex m_; std::condition_variable cv_; int n_ = 1, count_ = 0; uint64_t gen_ = 0;
+};
+
+struct Warp { double buf[32]; Barrier bar; };
+
+struct Block {
+  Barrier bar;
+  std::vector<Warp> warps{32};
+  std::vector<char> dyn;
+};
+
+inline Block& block() { static Block b; return b; }
+inline thread_local Dim3 t_threadIdx, t_blockIdx;
+inline Dim3 g_blockDim, g_gridDim;
+inline std::mutex g_atomic_mutex;
+
+// persistent worker pool: worker i runs CUDA thread i of the current block
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+  void run_block(int T, const std::function<void()>& fn) {
+    ensure(T);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn; active_ = T; done_ = 0; gen_++;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return done_ == active_; });
+  }
+ private:
+  void ensure(int T) {
+    while ((int)workers_.size() < T) {
+      int id = (int)workers_.size();
+      workers_.emplace_back([this, id] { loop(id); });
+      workers_.back().detach();
+    }
+  }
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void()>* fn;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (id >= active_) continue;
+        fn = fn_;
+      }
+      t_threadIdx.x = id;
+      (*fn)();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        done_++;
+      }
+      cv_done_.notify_one();
+    }
+  }
+  std::mutex m_; std::condition_variable cv_, cv_done_;
+  std::vector<std::thread> workers_;
+  const std::function<void()>* fn_ = nullptr;
+  int active_ = 0, done_ = 0; uint64_t gen_ = 0;
+};
+
+template <class F> inline void launch(int grid, int blockdim, size_t smem, F&& body) {
+  Block& b = block();
+  g_blockDim.x = blockdim; g_gridDim.x = grid;
+  b.dyn.assign(smem + 64, 0);
+  b.bar.reset(blockdim);
+  const int nw = (blockdim + 31) / 32;
+  for (int w = 0; w < nw; w++) b.warps[w].bar.reset(std::min(32, blockdim - 32 * w));
+  for (int bl = 0; bl < grid; bl++) {
+    std::function<void()> fn = [&, bl] { t_blockIdx.x = bl; body(); };
+    Pool::get().run_block(blockdim, fn);
+  }
+}
+
+inline double shfl(double v, int src_lane) {
+  Warp& w = block().warps[t_threadIdx.x / 32];
+  const int lane = t_threadIdx.x % 32;
+  w.buf[lane] = v;
+  w.bar.wait();
+  double r = w.buf[src_lane];
+  w.bar.wait();
+  return r;
+}
+}  // namespace emu
+
+#define threadIdx emu::t_threadIdx
+#define blockIdx emu::t_blockIdx
+#define blockDim emu::g_blockDim
+#define gridDim emu::g_gridDim
+
+static inline void __syncthreads() { emu::block().bar.wait(); }
+static inline double __shfl_up_sync(unsigned, double v, int d, int width = 32) {
+  const int lane = threadIdx.x % 32;
+  return emu::shfl(v, (lane % width) >= d ? lane - d : lane);
+}
+static inline double __shfl_down_sync(unsigned, double v, int d, int width = 32) {
+  const int lane = threadIdx.x % 32;
+  return emu::shfl(v, (lane % width) + d < width ? lane + d : lane);
+}
+static inline double __shfl_xor_sync(unsigned, double v, int d, int width = 32) {
+  const int lane = threadIdx.x % 32;
+  const int src = lane ^ d;
+  return emu::shfl(v, (src / width == lane / width) ? src : lane);
+}
+static inline double atomicAdd(double* p, double v) {
+  std::lock_guard<std::mutex> lk(emu::g_atomic_mutex);
+  double o = *p; *p = o + v; return o;
+}
+
+// ---- CUDA runtime subset used by the host code ----
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)aligned_alloc(256, (n + 255) / 256 * 256); return *p ? 0 : 1; }
+static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+
+// ---- cuBLAS subset ----
+typedef void* cublasHandle_t;
+typedef int cublasStatus_t;
+enum { CUBLAS_STATUS_SUCCESS = 0 };
+enum cublasOperation_t { CUBLAS_OP_N, CUBLAS_OP_T };
+static inline cublasStatus_t cublasCreate(cublasHandle_t* h) { *h = nullptr; return 0; }
+static inline cublasStatus_t cublasDestroy(cublasHandle_t) { return 0; }
+static inline cublasStatus_t cublasSetStream(cublasHandle_t, cudaStream_t) { return 0; }
+// column-major C(m x n) = alpha op(A) op(B) + beta C   (only the op combinations the host code uses)
+static inline cublasStatus_t cublasDgemm(cublasHandle_t, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k,
+                                         const double* alpha, const double* A, int lda, const double* B, int ldb,
+                                         const double* beta, double* C, int ldc) {
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < m; i++) {
+      double s = 0;
+      for (int p = 0; p < k; p++) {
+        double a = (ta == CUBLAS_OP_N) ? A[(size_t)p * lda + i] : A[(size_t)i * lda + p];
+        double b = (tb == CUBLAS_OP_N) ? B[(size_t)j * ldb + p] : B[(size_t)p * ldb + j];
+        s += a * b;
+      }
+      C[(size_t)j * ldc + i] = *alpha * s + (*beta == 0.0 ? 0.0 : *beta * C[(size_t)j * ldc + i]);
+    }
+  return 0;
+}
+
+#define B2_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::block().dyn.data()) + 15) & ~uintptr_t(15))
+#define B2_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
