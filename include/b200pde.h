@@ -50,6 +50,12 @@ int b2_version(void);
 int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** out);
 int b2_ctx_destroy(b2_ctx* ctx);
 int b2_ctx_sync(b2_ctx* ctx);
+/* device-side timing on the ctx stream (CUDA events): bench.py's timed region */
+int b2_ctx_timer_start(b2_ctx* ctx);
+int b2_ctx_timer_stop(b2_ctx* ctx, double* ms);
+int b2_ctx_launch_count(const b2_ctx* ctx, long long* kernels_launched);
+/* read (and reset) the time spent in the dense Poisson GEMMs since profiling was switched on */
+int b2_ctx_profile(b2_ctx* ctx, int on, double* gemm_ms);
 int b2_ctx_heap_handle(b2_ctx* ctx, void* handle64 /* 64 bytes out */);
 int b2_ctx_attach_peers(b2_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order */);
 /* cross-rank barrier hooks: the host (torch.distributed / MPI) calls these around its barrier */

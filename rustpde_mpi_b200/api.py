@@ -46,6 +46,25 @@ class Context:
     def sync(self):
         check(lib().b2_ctx_sync(self._h))
 
+    def timer_start(self):
+        check(lib().b2_ctx_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(lib().b2_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_longlong()
+        check(lib().b2_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def profile(self, on):
+        """Switch GEMM timing on/off; returns the GEMM milliseconds accumulated since the last call."""
+        ms = C.c_double()
+        check(lib().b2_ctx_profile(self._h, int(on), C.byref(ms)))
+        return ms.value
+
 
 _default_ctx = None
 

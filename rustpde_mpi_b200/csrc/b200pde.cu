@@ -50,6 +50,10 @@ struct b2_ctx {
   cudaStream_t stream = nullptr;
   cublasHandle_t blas = nullptr;
   long long launches = 0;  // lane-kernel + helper launches (counted, for bench.py's gpu_launches)
+  double* stage = nullptr; size_t stage_bytes = 0;   // host<->device staging (plain layout)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // b2_ctx_timer_*
+  bool profile = false;                              // time the GEMM launches separately
+  std::vector<cudaEvent_t> gemm_events;
   // symmetric heap for nranks > 1
   char* heap = nullptr;
   size_t heap_bytes = 0, heap_used = 0;
@@ -602,6 +606,15 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
   return B2_OK;
 }
 
+static int gemm_mark(b2_ctx* ctx) {
+  if (!ctx->profile) return B2_OK;
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(e, ctx->stream));
+  ctx->gemm_events.push_back(e);
+  return B2_OK;
+}
+
 // Poisson::solve_par, src/solver/poisson.rs:195-236
 static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero00) {
   b2_space* sp = s->sp;
@@ -617,7 +630,9 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
     RET(run_pass(sp, 1, x));
     // out[j, :] = fwd . rhs[j, :]  (dense FP64 GEMM, src/solver/poisson.rs:213-219)
     const double one = 1.0, zero = 0.0;
+    RET(gemm_mark(ctx));
     CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->fwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x2; x2.load(s->plain[1], s->m0, 1.0, LD_PLAIN); x2.store(sp->tmp[0], s->m0, ST_TRANS);
     RET(run_pass(sp, 1, x2));
@@ -626,7 +641,9 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
     RET(run_pass(sp, 0, y2));
     Prog x3; x3.load(sp->tmp[1], s->m0); x3.store(s->plain[0], s->m0, ST_PLAIN);
     RET(run_pass(sp, 1, x3));
+    RET(gemm_mark(ctx));
     CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->bwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x4; x4.load(s->plain[1], s->m0, 1.0, LD_PLAIN);
     if (zero00) x4.zeroelem(0, 0);
@@ -695,6 +712,35 @@ int b2_ctx_destroy(b2_ctx* c) {
   return B2_OK;
 }
 int b2_ctx_sync(b2_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return B2_OK; }
+int b2_ctx_timer_start(b2_ctx* c) {
+  if (!c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  return B2_OK;
+}
+int b2_ctx_timer_stop(b2_ctx* c, double* ms) {
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  *ms = f;
+  return B2_OK;
+}
+int b2_ctx_launch_count(const b2_ctx* c, long long* n) { *n = c->launches; return B2_OK; }
+int b2_ctx_profile(b2_ctx* c, int on, double* gemm_ms) {
+  CK(cudaStreamSynchronize(c->stream));
+  double tot = 0;
+  for (size_t i = 0; i + 1 < c->gemm_events.size(); i += 2) {
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->gemm_events[i], c->gemm_events[i + 1]));
+    tot += f;
+  }
+  for (auto e : c->gemm_events) cudaEventDestroy(e);
+  c->gemm_events.clear();
+  if (gemm_ms) *gemm_ms = tot;
+  c->profile = on != 0;
+  return B2_OK;
+}
 int b2_ctx_nranks(const b2_ctx* c) { return c->nranks; }
 int b2_ctx_heap_handle(b2_ctx*, void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
 int b2_ctx_attach_peers(b2_ctx*, const void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
@@ -759,8 +805,13 @@ static int array_copy(const b2_array* a, void* buf, size_t bytes, int to_device)
   const size_t need = (size_t)r * c * sizeof(double);
   if (bytes != need) return fail(B2_ERR_SHAPE, "host buffer has " + std::to_string(bytes) + " bytes, array needs " + std::to_string(need));
   CK(cudaSetDevice(sp->ctx->device));
-  double* stage = nullptr;
-  CK(cudaMalloc(&stage, need));
+  b2_ctx* ctx = sp->ctx;
+  if (ctx->stage_bytes < need) {
+    if (ctx->stage) CK(cudaFree(ctx->stage));
+    CK(cudaMalloc(&ctx->stage, need));
+    ctx->stage_bytes = need;
+  }
+  double* stage = ctx->stage;
   cudaStream_t st = sp->ctx->stream;
   const int cx = shape_complex(sp, a->shape_kind);
   const size_t total = (size_t)r * c;
@@ -774,8 +825,8 @@ static int array_copy(const b2_array* a, void* buf, size_t bytes, int to_device)
     CK(cudaMemcpyAsync(buf, stage, need, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaGetLastError());
+  ctx->launches++;
   CK(cudaStreamSynchronize(st));
-  CK(cudaFree(stage));
   return B2_OK;
 }
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes) { return array_copy(a, const_cast<void*>(buf), bytes, 1); }

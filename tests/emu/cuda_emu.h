@@ -55,7 +55,7 @@ struct Block {
   std::vector<char> dyn;
 };
 
-inline Block& block() { static Block b; return b; }
+inline Block& block() { static Block* b = new Block; return *b; }
 inline thread_local Dim3 t_threadIdx, t_blockIdx;
 inline Dim3 g_blockDim, g_gridDim;
 inline std::mutex g_atomic_mutex;
@@ -63,7 +63,7 @@ inline std::mutex g_atomic_mutex;
 // persistent worker pool: worker i runs CUDA thread i of the current block
 class Pool {
  public:
-  static Pool& get() { static Pool p; return p; }
+  static Pool& get() { static Pool* p = new Pool; return *p; }  // leaked on purpose: workers are detached
   void run_block(int T, const std::function<void()>& fn) {
     ensure(T);
     {
@@ -175,6 +175,12 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+typedef void* cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(8); return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
 // ---- cuBLAS subset ----

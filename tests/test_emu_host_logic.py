@@ -1,0 +1,67 @@
+"""Host logic on CPU: the SAME sources (lane_kernel.cuh + b200pde.cu) compiled with g++ against the
+SIMT emulator of tests/emu (every CUDA thread = one OS thread) and compared with the oracle.
+This covers lane-program construction, coefficient vectors, thread/chunk index algebra and the
+reference's golden vectors through the C ABI -- it is NOT a product path (the package never
+loads the emulator build) and says nothing about GPU results; `-m gpu` does that."""
+import subprocess
+import sys
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# run in a subprocess: the emulator build replaces the library for the whole process
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %r)
+from tests import emu
+emu.activate()
+import numpy as np
+import rustpde_mpi_b200 as b2
+from tests import gpu_checks as g
+from oracle import rustpde_oracle as o
+
+case = sys.argv[1]
+if case == "ops":
+    for sp in [(1, 65, 2, 65), (4, 64, 1, 65)]:
+        for fn in (g.check_roundtrip_layout, g.check_to_ortho, g.check_from_ortho, g.check_backward, g.check_forward, g.check_hholtz):
+            e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
+        for d in ((1, 0), (0, 2)):
+            e = g.check_gradient(*sp, d); assert e < g.TOL, ("gradient", sp, d, e)
+elif case == "poisson":
+    for sp in [(2, 65, 2, 65), (4, 64, 2, 65)]:
+        e = g.check_poisson(*sp); assert e < g.TOL, (sp, e)
+elif case == "golden":
+    # reference goldens through the C ABI: src/solver/hholtz_adi.rs:215-246 and poisson.rs:295-325
+    f = b2.Field2(b2.Space2(b2.cheb_dirichlet(7), b2.cheb_dirichlet(7)))
+    x = b2.HholtzAdi(f, [1.0, 1.0]).solve(np.tile(np.arange(1.0, 8.0), (7, 1))).get()
+    y = np.array([[-7.083e-03, -9.025e-03, -5.210e-03, 4.146e-03, 3.520e-03],
+                  [5.809e-04, 7.402e-04, 4.273e-04, -3.401e-04, -2.887e-04],
+                  [1.699e-04, 2.165e-04, 1.250e-04, -9.951e-05, -8.447e-05],
+                  [-1.007e-03, -1.283e-03, -7.406e-04, 5.895e-04, 5.004e-04],
+                  [-6.775e-04, -8.632e-04, -4.983e-04, 3.966e-04, 3.366e-04]])
+    np.testing.assert_allclose(x, y, rtol=6e-4, atol=1e-7)
+    f = b2.Field2(b2.Space2(b2.cheb_dirichlet(8), b2.cheb_dirichlet(7)))
+    x = b2.Poisson(f, [1.0, 1.0]).solve(np.tile(np.arange(1.0, 8.0), (8, 1))).get()
+    from tests.test_oracle_golden import GOLD_P2D
+    np.testing.assert_allclose(x, GOLD_P2D, atol=1.5e-6)
+    # shape errors replace the reference's panics
+    try:
+        b2.DeviceArray(f.space, b2.ORTHO).set(np.zeros((3, 3)))
+        raise SystemExit("expected a shape error")
+    except b2.B2Error:
+        pass
+elif case == "navier":
+    errs = g.check_navier(65, 65, 2)
+    assert max(errs.values()) < g.TOL, errs
+    errs = g.check_navier(64, 65, 2, True)
+    assert max(errs.values()) < g.TOL, errs
+print("ok")
+''' % ROOT
+
+
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier"])
+def test_emulated_host_logic(case):
+    r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
