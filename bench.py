@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- Navier2D timesteps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W [--config C2|C3|C4|C1] [--impl reference]
+
+A "step" is one `Navier2D::update()` (src/navier_stokes/navier.rs:438-466) on synthetic fields:
+constructor defaults, physical fields U(-0.1, 0.1) from numpy default_rng(1/2/3), forward().
+N = 1 workload: BASELINE configs[1] = confined 1025 x 1025 Chebyshev x Chebyshev, Ra 1e7, dt 1e-3.
+
+value  : steps/s with state resident in HBM, CUDA events on the library's stream, max over ranks.
+e2e    : the same step through the public API with HOST state: every step uploads the four
+         spectral state arrays from pinned host memory, steps, and downloads them again.
+roofline: HBM-bound lane kernels: algorithmic bytes per step (728 N) / time in lane kernels.
+cpu_baseline / --impl reference: the numpy oracle port of the reference's update() timed on the
+         host cores (the Rust reference cannot be built in this image: no cargo/rustc).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (nx, ny, ra, dt, periodic)
+    "C1": (129, 129, 1e5, 1e-2, False),
+    "C2": (1025, 1025, 1e7, 1e-3, False),
+    "C3": (2048, 1025, 1e7, 1e-3, True),
+    "C4": (4097, 4097, 1e9, 1e-4, False),
+}
+
+
+def workload_name(cfg):
+    nx, ny, ra, dt, per = CONFIGS[cfg]
+    return f"Navier2D {'periodic' if per else 'confined'} {nx}x{ny} {'Fourier' if per else 'Cheb'}xCheb Ra={ra:g} dt={dt:g}"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_steps(cfg, steps, eig=None):
+    """Time `steps` updates of the oracle port on the host.  Returns (steps/s, seconds, cores)."""
+    import numpy as np  # noqa: F401
+
+    from oracle import rustpde_oracle as o
+
+    nx, ny, ra, dt, per = CONFIGS[cfg]
+    nav = o.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, pois_eig=eig)
+    nav.init_random(0.1)
+    nav.update()  # warm-up (allocations, FFT plans)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nav.update()
+    t = time.perf_counter() - t0
+    return steps / t, t, os.cpu_count()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.config
+    n_steps = max(1, min(args.steps, 3 if cfg in ("C2", "C3") else (1 if cfg == "C4" else 20)))
+    v, t, cores = cpu_oracle_steps(cfg, n_steps)
+    line = {
+        "impl": "reference", "metric": "Navier2D timesteps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": n_steps, "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "config": cfg},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_steps} update() steps of the numpy oracle port (reference Rust toolchain absent)"},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", type=int, default=1, help="1 fused+graph (default), 3 fused without graph, 0 one pass pair per reference call")
+    args = ap.parse_args()
+    if args.config is None:
+        args.config = "C2" if args.gpus == 1 else "C4"
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+
+    import rustpde_mpi_b200 as b2
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if world > 1:
+        raise SystemExit("multi-GPU bench: see bench_multi path (not built in this revision)")
+
+    cfg = args.config
+    nx, ny, ra, dt, per = CONFIGS[cfg]
+    torch.cuda.set_device(local)
+    ctx = b2.Context(local)
+    t_setup = time.perf_counter()
+    nav = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, ctx=ctx)
+    nav.init_random(0.1)
+    nav.set_mode(args.mode)
+    setup_s = time.perf_counter() - t_setup
+    N = nx * ny
+
+    # ---- device-resident timing ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    nav.update(args.warmup)
+    ctx.sync()
+    l0 = ctx.launch_count()
+    t_a = time.time()
+    ctx.timer_start()
+    nav.update(args.steps)
+    ms = ctx.timer_stop()
+    t_b = time.time()
+    launches = ctx.launch_count() - l0
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    # keep the same loop running until nvidia-smi (100 ms period) has seen >= 1.5 s of it
+    n_more = 0
+    while time.time() - t_a < 1.5:
+        nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
+    clocks = sampler.stop()
+    clocks["note"] = f"sampled every 100 ms from warm-up through the timed region ({(t_b - t_a) * 1e3:.0f} ms) and {n_more} continuation bursts of the same loop"
+    # GEMM share of the step (separate short pass: event pairs around the two cuBLAS calls, no graph replay)
+    n_prof = max(2, min(args.steps, 10))
+    ctx.profile(True)
+    nav.update(n_prof)
+    gemm_ms = ctx.profile(False) / n_prof * args.steps
+    div = nav.div_norm()
+    assert np.isfinite(div), "NaN divergence"
+
+    # ---- roofline of the HBM-bound lane kernels (SURVEY 8d work model) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    lane_ms = (ms - gemm_ms) / args.steps
+    alg_bytes = 728.0 * N
+    achieved = alg_bytes / (lane_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
+    except Exception:  # noqa: BLE001
+        pass
+    gemm_flop = 0 if per else 4.0 * (nx - 2) ** 2 * (ny - 2)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "kernel": "lane_kernel (all per-axis passes of one step)", "alg_bytes_per_step": alg_bytes,
+                "lane_ms_per_step": lane_ms, "gemm_ms_per_step": gemm_ms / args.steps,
+                "gemm_tflops": (gemm_flop / (gemm_ms / args.steps * 1e-3) / 1e12) if gemm_ms > 0 else None}
+
+    # ---- end to end with host-resident state (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        names = ("temp", "velx", "vely", "pres")
+        host = {}
+        for k in names:
+            a = getattr(nav, k).vhat
+            t = torch.from_numpy(a.view(np.float64) if a.dtype == np.complex128 else a).clone().pin_memory()
+            host[k] = (t, a.dtype, a.shape)
+        nbytes = sum(t.numel() * 8 for t, _, _ in host.values())
+        k_e2e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            for k in names:
+                t, dt_, sh = host[k]
+                arr = t.numpy().view(dt_).reshape(sh)
+                getattr(nav, k).vhat = arr
+            nav.update(1)
+            for k in names:
+                t, dt_, sh = host[k]
+                t.numpy().view(dt_).reshape(sh)[...] = getattr(nav, k).vhat
+
+        e2e_step()
+        ctx.timer_start()
+        for _ in range(k_e2e):
+            e2e_step()
+        ms2 = ctx.timer_stop()
+        e2e = {"value": 1e3 / (ms2 / k_e2e), "unit": "steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps": k_e2e}
+
+    # ---- CPU baseline (oracle port), bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_cpu = 2 if cfg in ("C2", "C3") else (1 if cfg == "C4" else 10)
+        eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
+        v, t, cores = cpu_oracle_steps(cfg, n_cpu, eig)
+        cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} update() steps of the numpy oracle port at the same config ({t:.1f} s)"}
+
+    line = {
+        "metric": "Navier2D timesteps/sec", "value": value, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "config": cfg, "parallelism": "1 GPU",
+                   "l2": "per-step working set (~30 arrays x 8N bytes) exceeds the 126 MB L2; no explicit flush" if N > 600000 else "fits L2",
+                   "schedule": {1: "fused, CUDA-graph replay", 3: "fused, no graph", 0: "one pass pair per reference call"}.get(args.mode, str(args.mode)),
+                   "launches_per_step": nav.launches_per_step()},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "setup_s": setup_s, "div_norm": div,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,7 +118,7 @@ int b2_navier_field(b2_navier* nav, int which, b2_field** out);
 int b2_navier_update(b2_navier* nav, int nsteps);            /* Integrate::update, navier.rs:438-466 */
 int b2_navier_div_norm(b2_navier* nav, double* out);         /* navier_eq.rs:32-49 (exit() NaN guard) */
 int b2_navier_get_time(const b2_navier* nav, double* t);
-int b2_navier_set_mode(b2_navier* nav, int fused);           /* 0: one pass pair per reference call; 1: fused schedule */
+int b2_navier_set_mode(b2_navier* nav, int mode);            /* bit0: fused schedule (default on); bit1: no CUDA-graph replay */
 int b2_navier_launch_count(const b2_navier* nav, long long* kernels_per_step);
 int b2_navier_poisson_matrices(b2_navier* nav, double* a0, double* cmat0, int* m0);
 

@@ -12,6 +12,7 @@
 #include <cublas_v2.h>
 #endif
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -51,6 +52,7 @@ struct b2_ctx {
   cublasHandle_t blas = nullptr;
   long long launches = 0;  // lane-kernel + helper launches (counted, for bench.py's gpu_launches)
   double* stage = nullptr; size_t stage_bytes = 0;   // host<->device staging (plain layout)
+  void* blas_ws = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // b2_ctx_timer_*
   bool profile = false;                              // time the GEMM launches separately
   std::vector<cudaEvent_t> gemm_events;
@@ -354,6 +356,12 @@ struct Prog {
     if (b.cheb) dct(b, 0); else rfft(b, 0);
     return b.rows_ortho;
   }
+  void load_stencil(const double* src, const Base1& b, double a, bool acc) {  // W [+]= a * to_ortho(src) along the lane
+    LaneOp* o = add(OP_LOAD); o->p0 = src; o->a = a;
+    o->i0 = b.rows_ortho;
+    o->i2 = (acc ? LD_ACC : 0) | (b.composite ? LD_STENCIL : 0);
+    o->p1 = b.d_sten2.d;
+  }
   int matvec(const Base1& b) {          // MatVecFdma with pinv (Chebyshev axes only)
     if (b.composite) { band(b.m, b.n, 0, b.d_bd.d, 2, b.d_bu1.d, 4, b.d_bu2.d); return b.m; }
     return b.rows_spec;
@@ -395,6 +403,10 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   if (is_pow2(N) && N >= 64) {
     const int Nc = N / 2;
     c->E = Nc >= 128 ? 16 : (Nc >= 64 ? 8 : 4);
+    if (const char* e = getenv("B2_E")) {   // tuning knob: FFT points per thread (4, 8, 16)
+      int ev = atoi(e);
+      if ((ev == 4 || ev == 8 || ev == 16) && Nc / ev >= 8 && Nc / ev <= 128) c->E = ev;
+    }
     c->TPL = Nc / c->E;
   } else {  // no transform along this axis: banded ops only
     c->E = 4;
@@ -660,6 +672,14 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
   return run_pass(sp, 1, x);
 }
 
+// one axis of HholtzAdi: precondition (MatVecFdma) + banded / diagonal solve
+static void emit_hh_axis(Prog& p, const b2_solver* s, int ax) {
+  const Base1& b = s->sp->b[ax];
+  p.matvec(b);
+  if (b.composite) p.fdma(b.m, s->fl[ax].d, s->id[ax].d, s->u1[ax].d, s->u2[ax].d, 0);
+  else p.scalevec(b.rows_spec, s->sd[ax].d, 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Navier2D
 // ------------------------------------------------------------------------------------------------
@@ -675,8 +695,17 @@ struct b2_navier {
   // work arrays (ortho-sized, tiled)
   double *that = nullptr, *tbc_ortho = nullptr, *tbc_diff = nullptr, *rhs = nullptr, *g1 = nullptr, *g2 = nullptr, *conv = nullptr, *div = nullptr, *ux = nullptr, *uy = nullptr;
   double* d_scalar = nullptr;
-  int fused = 0;
+  // fused schedule: intermediates (suffix T = stored in the transposed orientation)
+  double *Pf[3] = {nullptr}, *Qf[3] = {nullptr}, *V1[3] = {nullptr}, *Cx[3] = {nullptr}, *Zf[3] = {nullptr};
+  double *VTv = nullptr, *uxT = nullptr, *uyT = nullptr, *cv = nullptr, *PH = nullptr, *PHy = nullptr, *F1 = nullptr, *F2 = nullptr, *R0 = nullptr;
+  double *G0 = nullptr, *G1 = nullptr, *U1 = nullptr, *U2 = nullptr, *U3 = nullptr;
+  double *GxT = nullptr, *GyT = nullptr, *KbT = nullptr, *KTT = nullptr;   // constants of the step
+  int fused = 1;
   long long launches_per_step = 0;
+#ifndef B2_EMU
+  cudaGraphExec_t graph = nullptr;
+#endif
+  int use_graph = 1, warm_steps = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -698,6 +727,10 @@ int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** 
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CKB(cublasCreate(&c->blas));
   CKB(cublasSetStream(c->blas, c->stream));
+#ifndef B2_EMU
+  CK(cudaMalloc(&c->blas_ws, (size_t)64 << 20));   // fixed workspace so that the GEMMs can live inside a CUDA graph
+  CKB(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)64 << 20));
+#endif
   (void)heap_bytes;
   *out = c;
   return B2_OK;
@@ -978,6 +1011,27 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
     RET(op_gradient(so, nv->tempbc->vhat->d, 2, 0, nv->scale, nv->tbc_diff, dt * nv->ka, false));
     RET(op_gradient(so, nv->tempbc->vhat->d, 0, 2, nv->scale, nv->tbc_diff, dt * nv->ka, true));
   }
+  // ---- fused schedule: work arrays and the constants that never change during a run ----
+  {
+    double** fw[] = {&nv->VTv, &nv->uxT, &nv->uyT, &nv->cv, &nv->PH, &nv->PHy, &nv->F1, &nv->F2, &nv->R0, &nv->G0, &nv->G1,
+                     &nv->U1, &nv->U2, &nv->U3, &nv->GxT, &nv->GyT, &nv->KbT, &nv->KTT};
+    for (auto w : fw) RET(nav_alloc(so, w));
+    for (int i = 0; i < 3; i++) { RET(nav_alloc(so, &nv->Pf[i])); RET(nav_alloc(so, &nv->Qf[i])); RET(nav_alloc(so, &nv->V1[i])); RET(nav_alloc(so, &nv->Cx[i])); RET(nav_alloc(so, &nv->Zf[i])); }
+    const Base1& bxo = so->b[0]; const Base1& byo = so->b[1];
+    // GxT / GyT = backward(d/dx tempbc), backward(d/dy tempbc): physical values, kept in x-lane orientation
+    for (int d = 0; d < 2; d++) {
+      RET(op_gradient(so, nv->tempbc->vhat->d, d == 0, d == 1, nv->scale, nv->g1));
+      Prog y; y.load(nv->g1, byo.rows_ortho); int l = y.backward_ortho(byo); y.store(so->tmp[0], l, ST_TRANS);
+      RET(run_pass(so, 0, y));
+      Prog x; x.load(so->tmp[0], bxo.rows_ortho); l = x.backward_ortho(bxo); x.store(d == 0 ? nv->GxT : nv->GyT, l, 0);
+      RET(run_pass(so, 1, x));
+    }
+    // KbT = dt * Hholtz_vely(to_ortho(tempbc)); KTT = Hholtz_temp(dt ka lap tempbc); both transposed
+    RET(hholtz_solve(nv->hh[1], nv->tbc_ortho, nv->g1));
+    { Prog y; y.load(nv->g1, so->P[1], dt); y.store(nv->KbT, so->P[1], ST_TRANS); RET(run_pass(so, 0, y)); }
+    RET(hholtz_solve(nv->hh[2], nv->tbc_diff, nv->g1));
+    { Prog y; y.load(nv->g1, so->P[1]); y.store(nv->KTT, so->P[1], ST_TRANS); RET(run_pass(so, 0, y)); }
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   *out = nv;
   return B2_OK;
@@ -987,8 +1041,15 @@ int b2_navier_destroy(b2_navier* nv) {
   if (!nv) return B2_OK;
   double* work[] = {nv->that, nv->tbc_ortho, nv->tbc_diff, nv->rhs, nv->g1, nv->g2, nv->conv, nv->div, nv->ux, nv->uy, nv->d_scalar};
   for (auto w : work) if (w) cudaFree(w);
+  double* fw[] = {nv->VTv, nv->uxT, nv->uyT, nv->cv, nv->PH, nv->PHy, nv->F1, nv->F2, nv->R0, nv->G0, nv->G1, nv->U1, nv->U2, nv->U3,
+                  nv->GxT, nv->GyT, nv->KbT, nv->KTT};
+  for (auto w : fw) if (w) cudaFree(w);
+  for (int i = 0; i < 3; i++) { cudaFree(nv->Pf[i]); cudaFree(nv->Qf[i]); cudaFree(nv->V1[i]); cudaFree(nv->Cx[i]); cudaFree(nv->Zf[i]); }
   b2_field* fs[] = {nv->temp, nv->velx, nv->vely, nv->pres, nv->pseu, nv->tempbc};
   for (auto f : fs) b2_field_destroy(f);
+#ifndef B2_EMU
+  if (nv->graph) cudaGraphExecDestroy(nv->graph);
+#endif
   for (auto s : nv->hh) b2_solver_destroy(s);
   b2_solver_destroy(nv->pois);
   b2_space* sps[] = {nv->sp_vel, nv->sp_temp, nv->sp_ortho, nv->sp_pseu};
@@ -1076,12 +1137,196 @@ static int nav_update_unfused(b2_navier* nv) {
   return B2_OK;
 }
 
+// Fused schedule: the same algebra as navier.rs:438-466 (all operators are tensor products, so the
+// per-axis factors can be regrouped freely), organised as 23 lane passes + 2 GEMMs per step with
+// ~91 array touches (SURVEY 8d work model) instead of one pass pair per reference call.
+static int nav_update_fused(b2_navier* nv) {
+  b2_space* so = nv->sp_ortho;
+  b2_ctx* ctx = nv->ctx;
+  const double dt = nv->dt, sx = 1.0 / nv->scale[0], sy = 1.0 / nv->scale[1];
+  const Base1& bxo = so->b[0]; const Base1& byo = so->b[1];
+  const Base1& bxp = nv->sp_pseu->b[0]; const Base1& byp = nv->sp_pseu->b[1];
+  b2_field* fld[3] = {nv->velx, nv->vely, nv->temp};
+  // dealias cuts, functions.rs:72-82 (integer division on the spectral shape of `field`)
+  const int shape0 = bxo.cheb ? bxo.n : bxo.m, shape1 = byo.n;
+  const int cut0 = (shape0 * 2 / 3) * (bxo.cheb ? 1 : 2), cut1 = shape1 * 2 / 3;
+  const int P0 = so->P[0], P1 = so->P[1];
+
+  // ---- A: along y on the three advected fields: values, d/dy values, Helmholtz-y of the old field ----
+  for (int i = 0; i < 3; i++) {
+    const b2_field* f = fld[i];
+    const Base1& by = f->sp->b[1];
+    const double* src = f->vhat->d;
+    Prog y;
+    y.load(src, by.rows_spec); y.to_ortho(by); int l = y.backward_ortho(by); y.store(nv->Pf[i], l, ST_TRANS);
+    y.load(src, by.rows_spec); y.to_ortho(by); y.deriv_axis(by, 1, sy); l = y.backward_ortho(by); y.store(nv->Qf[i], l, ST_TRANS);
+    y.load(src, by.rows_spec); y.to_ortho(by); emit_hh_axis(y, nv->hh[i], 1); y.store(nv->V1[i], by.m, ST_TRANS);
+    if (i == 2) { y.load(src, by.rows_spec); y.to_ortho(by); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->VTv, by.m, ST_TRANS); }
+    RET(run_pass(so, 0, y));
+  }
+  // ---- A-x: convection velocities ux, uy (physical, x-lane orientation) ----
+  for (int i = 0; i < 2; i++) {
+    const Base1& bx = fld[i]->sp->b[0];
+    Prog x; x.load(nv->Pf[i], bx.rows_spec); x.to_ortho(bx); int l = x.backward_ortho(bx); x.store(i == 0 ? nv->uxT : nv->uyT, l, 0);
+    RET(run_pass(so, 1, x));
+  }
+  // ---- B: u . grad f in physical space, forward transform along x, dealias rows ----
+  for (int i = 0; i < 3; i++) {
+    const Base1& bx = fld[i]->sp->b[0];
+    Prog x;
+    x.load(nv->Pf[i], bx.rows_spec); x.to_ortho(bx); x.deriv_axis(bx, 1, sx); int l = x.backward_ortho(bx);
+    if (i == 2) x.load(nv->GxT, l, 1.0, LD_ACC);
+    x.load(nv->uxT, l, 1.0, LD_MUL);
+    x.store(nv->cv, l, 0);
+    x.load(nv->Qf[i], bx.rows_spec); x.to_ortho(bx); l = x.backward_ortho(bx);
+    if (i == 2) x.load(nv->GyT, l, 1.0, LD_ACC);
+    x.load(nv->uyT, l, 1.0, LD_MUL);
+    x.load(nv->cv, l, 1.0, LD_ACC);
+    l = x.forward_ortho(bxo); x.zerotail(cut0);
+    x.store(nv->Cx[i], l, ST_TRANS);
+    RET(run_pass(so, 1, x));
+  }
+  // ---- C-y: forward along y, dealias columns, -dt, Helmholtz-y ----
+  for (int i = 0; i < 3; i++) {
+    Prog y; y.load(nv->Cx[i], byo.rows_phys, -dt); y.forward_ortho(byo); y.zerotail(cut1);
+    emit_hh_axis(y, nv->hh[i], 1); y.store(nv->Zf[i], fld[i]->sp->b[1].m, ST_TRANS);
+    RET(run_pass(so, 0, y));
+  }
+  {  // pressure gradient terms: Helmholtz-y of pres and of d/dy pres
+    Prog y;
+    y.load(nv->pres->vhat->d, byo.rows_ortho); emit_hh_axis(y, nv->hh[0], 1); y.store(nv->PH, nv->sp_vel->b[1].m, ST_TRANS);
+    y.load(nv->pres->vhat->d, byo.rows_ortho); y.deriv_axis(byo, 1, sy); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->PHy, nv->sp_vel->b[1].m, ST_TRANS);
+    RET(run_pass(so, 0, y));
+  }
+  // ---- C-x: assemble rhs along x and finish the three Helmholtz solves ----
+  {
+    const Base1& bxv = nv->sp_vel->b[0]; const Base1& bxT = nv->sp_temp->b[0];
+    Prog x;  // velx
+    x.load(nv->PH, bxo.rows_ortho, -dt); x.deriv_axis(bxo, 1, sx);
+    x.load(nv->Zf[0], bxo.rows_ortho, 1.0, LD_ACC);
+    x.load_stencil(nv->V1[0], bxv, 1.0, true);
+    emit_hh_axis(x, nv->hh[0], 0);
+    x.store(nv->velx->vhat->d, bxv.rows_spec, ST_TRANS);
+    RET(run_pass(so, 1, x));
+    Prog v;  // vely (+ buoyancy dt * (to_ortho(temp) + to_ortho(tempbc)))
+    v.load(nv->PHy, bxo.rows_ortho, -dt);
+    v.load(nv->Zf[1], bxo.rows_ortho, 1.0, LD_ACC);
+    v.load_stencil(nv->V1[1], bxv, 1.0, true);
+    v.load_stencil(nv->VTv, bxT, dt, true);
+    emit_hh_axis(v, nv->hh[1], 0);
+    v.load(nv->KbT, bxv.rows_spec, 1.0, LD_ACC);
+    v.store(nv->vely->vhat->d, bxv.rows_spec, ST_TRANS);
+    RET(run_pass(so, 1, v));
+  }
+  // ---- D: divergence of the intermediate velocity, pressure update part 1, Poisson rhs ----
+  {
+    const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
+    Prog y;
+    y.load(nv->velx->vhat->d, byv.rows_spec); int l = y.to_ortho(byv); y.store(nv->F1, l, ST_TRANS);
+    y.load(nv->vely->vhat->d, byv.rows_spec); y.to_ortho(byv); l = y.deriv_axis(byv, 1, sy); y.store(nv->F2, l, ST_TRANS);
+    RET(run_pass(so, 0, y));
+    Prog x;
+    x.load(nv->F1, bxv.rows_spec); x.to_ortho(bxv); x.deriv_axis(bxv, 1, sx);
+    x.load_stencil(nv->F2, bxv, 1.0, true);
+    x.store(nv->pres->vhat->d, bxo.rows_ortho, ST_TRANS | ST_ACC, -nv->nu);   // pres += -nu div (navier_eq.rs:137-143)
+    x.matvec(bxp);
+    x.store(nv->R0, bxp.rows_spec, ST_TRANS);
+    RET(run_pass(so, 1, x));
+  }
+  // temperature Helmholtz can go any time after B (it only needs the old fields)
+  {
+    const Base1& bxT = nv->sp_temp->b[0];
+    Prog t;
+    t.load(nv->Zf[2], bxo.rows_ortho);
+    t.load_stencil(nv->V1[2], bxT, 1.0, true);
+    emit_hh_axis(t, nv->hh[2], 0);
+    t.load(nv->KTT, bxT.rows_spec, 1.0, LD_ACC);
+    t.store(nv->temp->vhat->d, bxT.rows_spec, ST_TRANS);
+    RET(run_pass(so, 1, t));
+  }
+  // ---- Poisson (src/solver/poisson.rs:195-236) ----
+  b2_solver* ps = nv->pois;
+  const double* pseu_src; int pseu_flags;
+  if (ps->dense) {
+    const double one = 1.0, zero = 0.0;
+    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN);
+    RET(run_pass(so, 0, y));
+    RET(gemm_mark(ctx));   // G1[i', j] = sum_i fwd[i', i] G0[i, j]   (row-major views)
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ps->m0, ps->m0, &one, nv->G0, P1, ps->fwd.d, ps->m0, &zero, nv->G1, P1));
+    RET(gemm_mark(ctx)); ctx->launches++;
+    Prog y2; y2.load(nv->G1, byp.m, 1.0, LD_PLAIN); y2.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_PLAIN);
+    RET(run_pass(so, 0, y2));
+    RET(gemm_mark(ctx));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ps->m0, ps->m0, &one, nv->G0, P1, ps->bwd.d, ps->m0, &zero, nv->G1, P1));
+    RET(gemm_mark(ctx)); ctx->launches++;
+    pseu_src = nv->G1; pseu_flags = LD_PLAIN;
+  } else {
+    Prog y; y.load(nv->R0, byo.rows_ortho); y.matvec(byp);
+    y.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE);
+    y.zeroelem(0, 0); y.zeroelem(1, 0);
+    y.store(nv->pseu->vhat->d, byp.m, 0);
+    RET(run_pass(so, 0, y));
+    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
+  }
+  // ---- E: velocity correction and pressure update part 2 (navier_eq.rs:117-143) ----
+  {
+    const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
+    Prog y;
+    for (int k = 0; k < 3; k++) {
+      y.load(pseu_src, byp.m, 1.0, pseu_flags);
+      if (ps->dense) y.zeroelem(0, 0);
+      if (k == 0 && ps->dense) y.store(nv->pseu->vhat->d, byp.m, 0);
+      y.to_ortho(byp);
+      if (k == 1) y.deriv_axis(byo, 1, sy);
+      int l = byo.rows_ortho;
+      if (k < 2) l = y.from_ortho(byv);
+      y.store(k == 0 ? nv->U1 : (k == 1 ? nv->U2 : nv->U3), l, ST_TRANS);
+    }
+    RET(run_pass(so, 0, y));
+    Prog x1; x1.load(nv->U1, bxp.rows_spec); x1.to_ortho(bxp); x1.deriv_axis(bxo, 1, sx); int l = x1.from_ortho(bxv);
+    x1.store(nv->velx->vhat->d, l, ST_TRANS | ST_ACC, -1.0);
+    RET(run_pass(so, 1, x1));
+    Prog x2; x2.load(nv->U2, bxp.rows_spec); x2.to_ortho(bxp); l = x2.from_ortho(bxv);
+    x2.store(nv->vely->vhat->d, l, ST_TRANS | ST_ACC, -1.0);
+    RET(run_pass(so, 1, x2));
+    Prog x3; x3.load(nv->U3, bxp.rows_spec); l = x3.to_ortho(bxp);
+    x3.store(nv->pres->vhat->d, l, ST_TRANS | ST_ACC, 1.0 / dt);
+    RET(run_pass(so, 1, x3));
+  }
+  nv->time += dt;
+  return B2_OK;
+}
+
 int b2_navier_update(b2_navier* nv, int nsteps) {
   CK(cudaSetDevice(nv->ctx->device));
+  b2_ctx* ctx = nv->ctx;
   for (int s = 0; s < nsteps; s++) {
-    long long l0 = nv->ctx->launches;
-    RET(nav_update_unfused(nv));
-    nv->launches_per_step = nv->ctx->launches - l0;
+#ifndef B2_EMU
+    // the fused step is a fixed launch sequence: capture it once into a CUDA graph and replay it
+    if (nv->fused && nv->use_graph && !ctx->profile && nv->warm_steps >= 1) {
+      if (!nv->graph) {
+        cudaGraph_t g = nullptr;
+        const long long l0 = ctx->launches;
+        const double t0 = nv->time;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int r = nav_update_fused(nv);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->launches = l0; nv->time = t0;
+        if (r != B2_OK) return r;
+        CK(e);
+        CK(cudaGraphInstantiate(&nv->graph, g, 0));
+        CK(cudaGraphDestroy(g));
+      }
+      CK(cudaGraphLaunch(nv->graph, ctx->stream));
+      ctx->launches += nv->launches_per_step;
+      nv->time += nv->dt;
+      continue;
+    }
+#endif
+    long long l0 = ctx->launches;
+    RET(nv->fused ? nav_update_fused(nv) : nav_update_unfused(nv));
+    nv->launches_per_step = ctx->launches - l0;
+    nv->warm_steps++;
   }
   return B2_OK;
 }
@@ -1091,7 +1336,14 @@ int b2_navier_div_norm(b2_navier* nv, double* out) {
   return norm2_dev(nv->sp_ortho, nv->g1, out);
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
-int b2_navier_set_mode(b2_navier* nv, int fused) { nv->fused = fused; return B2_OK; }
+int b2_navier_set_mode(b2_navier* nv, int mode) {
+  // bit 0: fused schedule; bit 1: disable CUDA-graph replay
+  nv->fused = mode & 1; nv->use_graph = !(mode & 2); nv->warm_steps = 0;
+#ifndef B2_EMU
+  if (nv->graph) { cudaGraphExecDestroy(nv->graph); nv->graph = nullptr; }
+#endif
+  return B2_OK;
+}
 int b2_navier_launch_count(const b2_navier* nv, long long* k) { *k = nv->launches_per_step; return B2_OK; }
 int b2_navier_poisson_matrices(b2_navier* nv, double* a0, double* cmat0, int* m0) {
   if (m0) *m0 = nv->sp_pseu->b[0].m;

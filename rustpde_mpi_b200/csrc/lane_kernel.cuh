@@ -26,7 +26,7 @@
 #define B2_MAXPEERS 8
 
 enum LaneOpCode {
-  OP_LOAD = 1,     // W = [W +|*] a * src           i0=len  i2=flags(LD_*)       p0=src
+  OP_LOAD = 1,     // W = [W +|*] a * src           i0=len  i2=flags(LD_*)       p0=src (p1 = stencil coefficients)
   OP_STORE = 2,    // dst = [dst +] a * W            i0=len  i2=flags(ST_*)       p0=dst  (p1=peer table)
   OP_BAND = 3,     // y_i = sum_m c_m[i] x_{i+o_m}   i0=len_out i1=packed offs i2=len_in  p0..p2 coef (null = 1, i1 byte=127: unused)
   OP_DERIV = 4,    // Chebyshev d/dx of i0 coeffs, i1 times, times a
@@ -40,7 +40,7 @@ enum LaneOpCode {
   OP_ZEROELEM = 12,// W[lane i0][pos i1] = 0 (global lane index)
   OP_SCALE = 13,   // W *= a
 };
-enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4 };
+enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8 };  // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
 enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16 };
 enum { FD_PERLANE = 1, FD_NOU2 = 2 };
 
@@ -245,19 +245,38 @@ __device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, dou
   const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, plain = op.i2 & LD_PLAIN;
   const double2* src = reinterpret_cast<const double2*>(op.p0);
   const size_t slab = (size_t)gl * P.in_tiles * 8;  // in double2 units
-  for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
-    int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (J < P.in_tiles && j0 < len) {
-      if (plain) v = src[((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1];
-      else v = src[slab + pidx];
-      v.x *= a;
-      v.y = (j0 + 1 < len) ? v.y * a : 0.0;
+  const double* sc = reinterpret_cast<const double*>(op.p1);
+  const bool sten = op.i2 & LD_STENCIL;
+  constexpr int U = 8;   // loads in flight per thread: all U global loads are issued before the first use
+  for (int p0 = threadIdx.x; p0 < npieces; p0 += U * T) {
+    double2 v[U], u[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int pidx = p0 + k * T;
+      const int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      v[k] = make_double2(0.0, 0.0); u[k] = make_double2(0.0, 0.0);
+      if (pidx < npieces && J < P.in_tiles && j0 < len) {
+        v[k] = plain ? src[((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1] : src[slab + pidx];
+        if (sten && j0 >= 2) {   // composite -> orthonormal on the fly: + p1[j] * src[j-2]  (tiled sources only)
+          const int jm = j0 - 2;
+          u[k] = src[slab + ((size_t)(jm >> 2) * 16 + l * 4 + (jm & 3)) / 2];
+        }
+      }
     }
-    double2* w = reinterpret_cast<double2*>(W + l * LP + j0);
-    if (acc) { double2 o = *w; v.x += o.x; v.y += o.y; }
-    else if (mul) { double2 o = *w; v.x *= o.x; v.y *= o.y; }
-    *w = v;
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int pidx = p0 + k * T;
+      if (pidx >= npieces) break;
+      const int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      double2 x = v[k];
+      if (sten && j0 >= 2 && j0 < len) { x.x = fma(sc[j0], u[k].x, x.x); x.y = fma(sc[j0 + 1], u[k].y, x.y); }
+      x.x *= a;
+      x.y = (j0 + 1 < len) ? x.y * a : 0.0;
+      double2* w = reinterpret_cast<double2*>(W + l * LP + j0);
+      if (acc) { double2 o = *w; x.x += o.x; x.y += o.y; }
+      else if (mul) { double2 o = *w; x.x *= o.x; x.y *= o.y; }
+      *w = x;
+    }
   }
   __syncthreads();
 }
