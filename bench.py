@@ -137,16 +137,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    if world > 1:
-        raise SystemExit("multi-GPU bench: see bench_multi path (not built in this revision)")
-
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     cfg = args.config
     nx, ny, ra, dt, per = CONFIGS[cfg]
     torch.cuda.set_device(local)
-    ctx = b2.Context(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl")
+        heap = (110 * (nx + 64) * (ny + 64) * 8) // world + (64 << 20)
+        ctx = b2.Context.distributed(local, heap)
+    else:
+        ctx = b2.Context(local)
+
+    def fence():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     t_setup = time.perf_counter()
     nav = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, ctx=ctx)
     nav.init_random(0.1)
@@ -159,19 +169,29 @@ def main():
     sampler.start()
     nav.update(args.warmup)
     ctx.sync()
+    fence()
     l0 = ctx.launch_count()
     t_a = time.time()
     ctx.timer_start()
     nav.update(args.steps)
     ms = ctx.timer_stop()
+    fence()
     t_b = time.time()
+    if dist is not None:  # device time of the slowest rank
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     launches = ctx.launch_count() - l0
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
     # keep the same loop running until nvidia-smi (100 ms period) has seen >= 1.5 s of it
     n_more = 0
-    while time.time() - t_a < 1.5:
+    n_target = 0 if dist is not None else 10 ** 9   # multi-rank: every rank must issue the same number of steps
+    while n_more < n_target and time.time() - t_a < 1.5:
         nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
+    if dist is not None:
+        for _ in range(4):
+            nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
     clocks = sampler.stop()
     clocks["note"] = f"sampled every 100 ms from warm-up through the timed region ({(t_b - t_a) * 1e3:.0f} ms) and {n_more} continuation bursts of the same loop"
     # GEMM share of the step (separate short pass: event pairs around the two cuBLAS calls, no graph replay)
@@ -190,14 +210,14 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     lane_ms = (ms - gemm_ms) / args.steps
-    alg_bytes = 728.0 * N
+    alg_bytes = 728.0 * N / world   # per GPU
     achieved = alg_bytes / (lane_ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg)
     except Exception:  # noqa: BLE001
         pass
-    gemm_flop = 0 if per else 4.0 * (nx - 2) ** 2 * (ny - 2)
+    gemm_flop = 0 if per else 4.0 * (nx - 2) ** 2 * (ny - 2) / world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "kernel": "lane_kernel (all per-axis passes of one step)", "alg_bytes_per_step": alg_bytes,
@@ -227,16 +247,24 @@ def main():
                 t.numpy().view(dt_).reshape(sh)[...] = getattr(nav, k).vhat
 
         e2e_step()
+        fence()
         ctx.timer_start()
         for _ in range(k_e2e):
             e2e_step()
         ms2 = ctx.timer_stop()
+        fence()
+        if dist is not None:
+            t = torch.tensor([ms2, float(nbytes)], dtype=torch.float64)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms2, nbytes = float(tm[0]), int(t[1])
         e2e = {"value": 1e3 / (ms2 / k_e2e), "unit": "steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": k_e2e}
 
     # ---- CPU baseline (oracle port), bounded sample ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         n_cpu = 2 if cfg in ("C2", "C3") else (1 if cfg == "C4" else 10)
         eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
         v, t, cores = cpu_oracle_steps(cfg, n_cpu, eig)
@@ -244,17 +272,21 @@ def main():
                "sample": f"{n_cpu} update() steps of the numpy oracle port at the same config ({t:.1f} s)"}
 
     line = {
-        "metric": "Navier2D timesteps/sec", "value": value, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+        "metric": "Navier2D timesteps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "config": cfg, "parallelism": "1 GPU",
+        "config": {"workload": workload_name(cfg), "config": cfg, "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, slab decomposition, peer-store transposes over NVLink",
                    "l2": "per-step working set (~30 arrays x 8N bytes) exceeds the 126 MB L2; no explicit flush" if N > 600000 else "fits L2",
                    "schedule": {1: "fused, CUDA-graph replay", 3: "fused, no graph", 0: "one pass pair per reference call"}.get(args.mode, str(args.mode)),
                    "launches_per_step": nav.launches_per_step()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "setup_s": setup_s, "div_norm": div,
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

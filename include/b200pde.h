@@ -60,6 +60,7 @@ int b2_ctx_heap_handle(b2_ctx* ctx, void* handle64 /* 64 bytes out */);
 int b2_ctx_attach_peers(b2_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order */);
 /* cross-rank barrier hooks: the host (torch.distributed / MPI) calls these around its barrier */
 int b2_ctx_nranks(const b2_ctx* ctx);
+int b2_ctx_barrier(b2_ctx* ctx);   /* all-ranks barrier on the ctx stream (peer flags over NVLink) */
 
 /* ---- Space2 (funspace Space2::new(&base0,&base1); src/bases.rs:11-19, src/field.rs:81-90) ---- */
 int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space** out);
@@ -71,6 +72,11 @@ int b2_space_coords(const b2_space* sp, int axis, double* x_host /* n values */)
 /* ---- device arrays (the `Array2<T>` values that flow between Field and Solve calls) ---- */
 int b2_array_create(b2_space* sp, int shape_kind, b2_array** out);
 int b2_array_destroy(b2_array* a);
+/* slab decomposition (funspace Decomp2d y-pencil, src/field_mpi.rs:130-134): axis 0 is split in
+ * contiguous blocks of P0/nranks rows (P0 = rows padded to 4*nranks); with one rank this is the
+ * whole array.  Host buffers of set/get hold exactly these rows (modes for complex arrays). */
+int b2_array_local_rows(const b2_array* a, int* row_start, int* row_count);
+int b2_array_sumsq_local(const b2_array* a, double* out);
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes);
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes);
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x); /* y += alpha x (same shape kind) */
@@ -83,6 +89,7 @@ int b2_field_set_v_host(b2_field* f, const void* buf, size_t bytes);  /* field.v
 int b2_field_get_v_host(const b2_field* f, void* buf, size_t bytes);
 int b2_field_set_vhat_host(b2_field* f, const void* buf, size_t bytes);
 int b2_field_get_vhat_host(const b2_field* f, void* buf, size_t bytes);
+int b2_field_local_rows(const b2_field* f, int shape_kind, int* row_start, int* row_count);
 int b2_forward(b2_field* f);                                          /* field.rs:103-105 */
 int b2_backward(b2_field* f);                                         /* field.rs:108-110 */
 int b2_to_ortho(const b2_field* f, b2_array* out /* ORTHO */);        /* field.rs:113-115 */

@@ -29,12 +29,15 @@ SYMBOLS = {
     "b2_ctx_heap_handle": (_I, [_P, _P]),
     "b2_ctx_attach_peers": (_I, [_P, _P]),
     "b2_ctx_nranks": (_I, [_P]),
+    "b2_ctx_barrier": (_I, [_P]),
     "b2_space2_create": (_I, [_P, _I, _I, _I, _I, _PP]),
     "b2_space_destroy": (_I, [_P]),
     "b2_space_shape": (_I, [_P, _I, _IP, _IP, _IP]),
     "b2_space_coords": (_I, [_P, _I, _DP]),
     "b2_array_create": (_I, [_P, _I, _PP]),
     "b2_array_destroy": (_I, [_P]),
+    "b2_array_local_rows": (_I, [_P, _IP, _IP]),
+    "b2_array_sumsq_local": (_I, [_P, _DP]),
     "b2_array_set_host": (_I, [_P, _P, _SZ]),
     "b2_array_get_host": (_I, [_P, _P, _SZ]),
     "b2_array_axpy": (_I, [_P, _D, _P]),
@@ -45,6 +48,7 @@ SYMBOLS = {
     "b2_field_get_v_host": (_I, [_P, _P, _SZ]),
     "b2_field_set_vhat_host": (_I, [_P, _P, _SZ]),
     "b2_field_get_vhat_host": (_I, [_P, _P, _SZ]),
+    "b2_field_local_rows": (_I, [_P, _I, _IP, _IP]),
     "b2_forward": (_I, [_P]),
     "b2_backward": (_I, [_P]),
     "b2_to_ortho": (_I, [_P, _P]),

@@ -43,6 +43,50 @@ class Context:
         check(lib().b2_ctx_create(device, rank, nranks, heap_bytes, C.byref(self._h)))
         self.device, self.rank, self.nranks = device, rank, nranks
 
+    @classmethod
+    def distributed(cls, device, heap_bytes):
+        """One context per rank of an initialised ``torch.distributed`` group (one process per GPU).
+        The ranks exchange the CUDA-IPC handle of their symmetric heap so that every pencil transpose
+        is a peer store inside the producing kernel (replaces funspace ``Decomp2d::transpose_*`` /
+        MPI_Alltoallv, src/field_mpi.rs:456-477)."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ctx = cls(device, rank, world, heap_bytes)
+        if world > 1:
+            h = C.create_string_buffer(64)
+            check(lib().b2_ctx_heap_handle(ctx._h, h))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h.raw))
+            check(lib().b2_ctx_attach_peers(ctx._h, b"".join(handles)))
+            dist.barrier()
+        return ctx
+
+    def all_reduce_sum(self, x):
+        if self.nranks == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(self.device)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def all_gather_rows(self, a):
+        """Concatenate the ranks' row slabs (gather(local) == global)."""
+        if self.nranks == 1:
+            return a
+        import torch.distributed as dist
+
+        parts = [None] * self.nranks
+        dist.all_gather_object(parts, a)
+        return np.concatenate([p for p in parts if p.shape[0] > 0], axis=0)
+
+    def barrier(self):
+        check(lib().b2_ctx_barrier(self._h))
+
     def sync(self):
         check(lib().b2_ctx_sync(self._h))
 
@@ -124,18 +168,29 @@ class DeviceArray:
         else:
             self._h = handle
 
-    def set(self, a):
+    def local_rows(self):
+        """(first row, number of rows) of this rank's slab (axis 0 split; whole array with one rank)."""
+        r0, cnt = C.c_int(), C.c_int()
+        check(lib().b2_array_local_rows(self._h, C.byref(r0), C.byref(cnt)))
+        return r0.value, cnt.value
+
+    def local_shape(self):
         shape, _ = self.space.shape(self.kind)
+        return (self.local_rows()[1], shape[1])
+
+    def set(self, a):
+        shape = self.local_shape()
         a = np.ascontiguousarray(a, dtype=_host_dtype(self.space, self.kind))
         if a.shape != tuple(shape):
             raise B2Error(f"shape mismatch: got {a.shape}, expected {tuple(shape)}")  # reference: panic
-        check(lib().b2_array_set_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        if a.size:
+            check(lib().b2_array_set_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
         return self
 
     def get(self):
-        shape, _ = self.space.shape(self.kind)
-        out = np.empty(shape, dtype=_host_dtype(self.space, self.kind))
-        check(lib().b2_array_get_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        out = np.empty(self.local_shape(), dtype=_host_dtype(self.space, self.kind))
+        if out.size:
+            check(lib().b2_array_get_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
     def axpy(self, alpha, x):
@@ -175,34 +230,49 @@ class Field2:
             self.x[i] = self.x[i] * sc
             self.dx[i] = self.dx[i] * sc
 
-    # host views of the device-resident data
+    def local_rows(self, kind):
+        """(first row, count) of this rank's slab of ``v`` (PHYSICAL) or ``vhat`` (SPECTRAL): axis 0 is
+        split in contiguous blocks (y-pencil of src/field_mpi.rs:71-88); one rank owns everything."""
+        r0, cnt = C.c_int(), C.c_int()
+        check(lib().b2_field_local_rows(self._h, kind, C.byref(r0), C.byref(cnt)))
+        return r0.value, cnt.value
+
+    def local_slice(self, kind):
+        r0, cnt = self.local_rows(kind)
+        return slice(r0, r0 + cnt)
+
+    # host views of the device-resident data (this rank's rows)
     @property
     def v(self):
-        out = np.empty(self.space.shape_physical())
-        check(lib().b2_field_get_v_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        out = np.empty((self.local_rows(PHYSICAL)[1], self.space.shape_physical()[1]))
+        if out.size:
+            check(lib().b2_field_get_v_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
     @v.setter
     def v(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
-        if a.shape != tuple(self.space.shape_physical()):
+        if a.shape != (self.local_rows(PHYSICAL)[1], self.space.shape_physical()[1]):
             raise B2Error(f"shape mismatch: got {a.shape}")
-        check(lib().b2_field_set_v_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        if a.size:
+            check(lib().b2_field_set_v_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
 
     @property
     def vhat(self):
         shape, cx = self.space.shape(SPECTRAL)
-        out = np.empty(shape, dtype=np.complex128 if cx else np.float64)
-        check(lib().b2_field_get_vhat_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        out = np.empty((self.local_rows(SPECTRAL)[1], shape[1]), dtype=np.complex128 if cx else np.float64)
+        if out.size:
+            check(lib().b2_field_get_vhat_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
     @vhat.setter
     def vhat(self, a):
         shape, cx = self.space.shape(SPECTRAL)
         a = np.ascontiguousarray(a, dtype=np.complex128 if cx else np.float64)
-        if a.shape != tuple(shape):
-            raise B2Error(f"shape mismatch: got {a.shape}, expected {tuple(shape)}")
-        check(lib().b2_field_set_vhat_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        if a.shape != (self.local_rows(SPECTRAL)[1], shape[1]):
+            raise B2Error(f"shape mismatch: got {a.shape}, expected {(self.local_rows(SPECTRAL)[1], shape[1])}")
+        if a.size:
+            check(lib().b2_field_set_vhat_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
 
     def forward(self):
         check(lib().b2_forward(self._h))
@@ -337,6 +407,7 @@ class Navier2D:
                  "velx": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)), "vely": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)),
                  "pres": (bx(CHEBYSHEV), chebyshev(ny)), "pseu": (bx(CHEB_NEUMANN), cheb_neumann(ny)),
                  "tempbc": (bx(CHEBYSHEV), chebyshev(ny))}
+        self.nranks = self.ctx.nranks
         for name, idx in self.FIELDS.items():
             fh = C.c_void_p()
             check(lib().b2_navier_field(self._h, idx, C.byref(fh)))
@@ -363,20 +434,24 @@ class Navier2D:
 
     def set_velocity(self, amp, m, n):
         x, y = self._unit(self.velx)
-        self.velx.v = amp * np.outer(np.sin(np.pi * m * x), np.cos(np.pi * n * y))
+        self.velx.v = (amp * np.outer(np.sin(np.pi * m * x), np.cos(np.pi * n * y)))[self.velx.local_slice(PHYSICAL)]
         self.velx.forward()
         x, y = self._unit(self.vely)
-        self.vely.v = -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y))
+        self.vely.v = (-amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y)))[self.vely.local_slice(PHYSICAL)]
         self.vely.forward()
 
     def set_temperature(self, amp, m, n):
         x, y = self._unit(self.temp)
-        self.temp.v = -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y))
+        self.temp.v = (-amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y)))[self.temp.local_slice(PHYSICAL)]
         self.temp.forward()
 
     def init_random(self, amp, seeds=(1, 2, 3)):
+        """U(-amp, amp) physical fields, then forward (navier.rs:171-182).  With several ranks every rank
+        draws the same global field and keeps its rows (the reference draws on rank 0 and scatters,
+        src/navier_stokes_mpi/functions.rs:269-286)."""
         for f, s in zip((self.temp, self.velx, self.vely), seeds):
-            f.v = np.random.default_rng(s).uniform(-amp, amp, size=f.space.shape_physical())
+            full = np.random.default_rng(s).uniform(-amp, amp, size=f.space.shape_physical())
+            f.v = full[f.local_slice(PHYSICAL)]
             f.forward()
 
     # Integrate (src/lib.rs:167-178)
@@ -394,6 +469,8 @@ class Navier2D:
     def div_norm(self):
         v = C.c_double()
         check(lib().b2_navier_div_norm(self._h, C.byref(v)))
+        if self.ctx.nranks > 1:  # the library returns the local sum of squares; all_gather_sum of navier_eq.rs:51,64
+            return float(np.sqrt(self.ctx.all_reduce_sum(v.value)))
         return v.value
 
     def exit(self):
@@ -412,7 +489,12 @@ class Navier2D:
         return k.value
 
     def state(self):
+        """This rank's slabs of the four spectral state arrays."""
         return {k: getattr(self, k).vhat for k in ("temp", "velx", "vely", "pres")}
+
+    def gather_state(self):
+        """Global state arrays on every rank (gather_spectral of src/field_mpi.rs:363-376)."""
+        return {k: self.ctx.all_gather_rows(v) for k, v in self.state().items()}
 
 
 class _BorrowedSpace(Space2):

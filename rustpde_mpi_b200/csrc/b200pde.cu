@@ -56,12 +56,51 @@ struct b2_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // b2_ctx_timer_*
   bool profile = false;                              // time the GEMM launches separately
   std::vector<cudaEvent_t> gemm_events;
-  // symmetric heap for nranks > 1
+  // symmetric heap for nranks > 1: every rank allocates the same arrays in the same order, so an
+  // array has the same offset on every GPU and a peer's copy is peer_base[r] + offset
   char* heap = nullptr;
   size_t heap_bytes = 0, heap_used = 0;
   double** d_peers = nullptr;  // device table of peer heap bases
   void* peer_base[B2_MAXPEERS] = {nullptr};
+  bool attached = false;
+  long long barriers = 0;
 };
+static const size_t B2_HEAP_RESERVED = 4096;  // flags[0..nranks) + epoch counter live at the start of the heap
+
+static int ctx_alloc(b2_ctx* c, size_t bytes, double** out) {
+  if (c->nranks == 1) { CK(cudaMalloc(out, bytes)); return B2_OK; }
+  const size_t need = (bytes + 255) / 256 * 256;
+  if (c->heap_used + need > c->heap_bytes) return fail(B2_ERR_ARG, "symmetric heap exhausted: pass a larger heap_bytes to b2_ctx_create");
+  *out = reinterpret_cast<double*>(c->heap + c->heap_used);
+  c->heap_used += need;
+  return B2_OK;
+}
+static void ctx_free(b2_ctx* c, void* p) { if (p && c->nranks == 1) cudaFree(p); }
+
+// all-ranks barrier on the stream: signal every peer's flag slot, then wait for every peer's signal
+__global__ void k_barrier(unsigned long long* const* peers, int rank, int nranks) {
+  unsigned long long* mine = peers[rank];
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) epoch = mine[B2_MAXPEERS] + 1;
+  __syncthreads();
+  const unsigned long long e = epoch;
+  __threadfence_system();
+  if ((int)threadIdx.x < nranks) {
+    *reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + rank) = e;
+    __threadfence_system();
+    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) {}
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mine[B2_MAXPEERS] = e;
+}
+static int ctx_barrier(b2_ctx* c) {
+  if (c->nranks == 1) return B2_OK;
+  if (!c->attached) return fail(B2_ERR_ARG, "b2_ctx_attach_peers has not been called");
+  B2_LAUNCH(k_barrier, 1, 32, 0, c->stream, reinterpret_cast<unsigned long long* const*>(c->d_peers), c->rank, c->nranks);
+  CK(cudaGetLastError());
+  c->barriers++;
+  return B2_OK;
+}
 
 struct DVecD {  // device vector of doubles
   double* d = nullptr;
@@ -111,7 +150,7 @@ struct Base1 {
   int rows_phys = 0, rows_spec = 0, rows_ortho = 0;  // real rows along this axis (complex => 2 per mode)
   int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
-  DVecD d_sten2, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
+  DVecD d_sten2, d_sten2s, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
 
   // B2 = laplace_inv; pv(i, off) = (laplace_inv_eye . laplace_inv)[i, i+off]
   double pv(int i, int off) const {
@@ -141,9 +180,20 @@ struct Base1 {
     return b;
   }
   int init_host(int kind_, int n_);
-  int init(int kind_, int n_);
+  int init(int C, int TPL);   // device vectors; (C, TPL) = chunking of the passes whose lanes run along this axis
+  int lay_C = 1, lay_TPL = 1;
+  // chunk-transposed copy of a coefficient vector: out[ii*TPL + q] = v[q*C + ii]
+  std::vector<double> scan_layout(const std::vector<double>& v) const {
+    std::vector<double> o((size_t)lay_C * lay_TPL, 0.0);
+    for (int q = 0; q < lay_TPL; q++)
+      for (int ii = 0; ii < lay_C; ii++) {
+        const size_t i = (size_t)q * lay_C + ii;
+        if (i < v.size()) o[(size_t)ii * lay_TPL + q] = v[i];
+      }
+    return o;
+  }
   void release() {
-    DVecD* all[] = {&d_sten2, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin};
+    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin};
     for (auto* v : all) v->release();
   }
 };
@@ -173,14 +223,14 @@ int Base1::init_host(int kind_, int n_) {
   return B2_OK;
 }
 
-int Base1::init(int kind_, int n_) {
-  RET(init_host(kind_, n_));
+int Base1::init(int C, int TPL) {
+  lay_C = C; lay_TPL = TPL;
   const int L = roundup(std::max(rows_phys, rows_ortho) + 8, 4) + 64;  // generous coefficient-vector length
   if (composite) {
     std::vector<double> sten2(L, 0.0), s2v(L, 0.0);
     for (int i = 2; i < n; i++) sten2[i] = s2[i - 2];
     for (int k = 0; k < m; k++) s2v[k] = s2[k];
-    RET(d_sten2.upload(sten2)); RET(d_s2.upload(s2v));
+    RET(d_sten2.upload(sten2)); RET(d_sten2s.upload(scan_layout(sten2))); RET(d_s2.upload(scan_layout(s2v)));
     // from_ortho: (S^T S) c = S^T o, tridiagonal at offsets (-2,0,2)
     Diags t(m);
     for (int k = 0; k < m; k++) {
@@ -189,7 +239,7 @@ int Base1::init(int kind_, int n_) {
     }
     LuVecs lu = sweep(t);
     lu.fl.resize(L, 0.0); lu.id.resize(L, 0.0); lu.u1.resize(L, 0.0);
-    RET(d_tfl.upload(lu.fl)); RET(d_tid.upload(lu.id)); RET(d_tu1.upload(lu.u1));
+    RET(d_tfl.upload(scan_layout(lu.fl))); RET(d_tid.upload(scan_layout(lu.id))); RET(d_tu1.upload(scan_layout(lu.u1)));
     // MatVecFdma of the preconditioner pinv (src/solver/matvec.rs:177-203)
     std::vector<double> bd(L, 0.0), bu1(L, 0.0), bu2(L, 0.0);
     for (int i = 0; i < m; i++) {
@@ -197,7 +247,7 @@ int Base1::init(int kind_, int n_) {
       if (i < m - 2) bu1[i] = pv(i, 2);
       if (i < m - 4) bu2[i] = pv(i, 4);
     }
-    RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
+    RET(d_bd.upload(scan_layout(bd))); RET(d_bu1.upload(scan_layout(bu1))); RET(d_bu2.upload(scan_layout(bu2)));
   }
   // transform tables (only when the size is one the FFT core handles)
   if (is_pow2(N) && N >= 64) {
@@ -220,7 +270,7 @@ struct b2_space {
   int P[2] = {0, 0};   // padded real rows along axis 0 / axis 1
   PassCfg cfg[2];      // [0]: lanes along axis 1 (arrays stored P0 x P1); [1]: lanes along axis 0
   bool transforms_ok = false;
-  size_t elems() const { return (size_t)P[0] * P[1]; }
+  size_t elems() const { return (size_t)P[0] * P[1] / ctx->nranks; }   // local slab
   double* tmp[6] = {nullptr};  // scratch arrays
   int refs = 0;
 };
@@ -332,7 +382,7 @@ struct Prog {
   // ---- per-axis operator chains (funspace semantics) ----
   // returns the new valid length along the lane
   int to_ortho(const Base1& b) {
-    if (b.composite) { band(b.n, b.m, 0, nullptr, -2, b.d_sten2.d); return b.n; }
+    if (b.composite) { band(b.n, b.m, 0, nullptr, -2, b.d_sten2s.d); return b.n; }
     return b.rows_ortho;
   }
   int from_ortho(const Base1& b) {
@@ -374,7 +424,7 @@ template <int E> static int launch_E(b2_ctx* ctx, const PassCfg& c, const LanePr
     CK(cudaFuncSetAttribute(lane_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     set_smem = c.smem;
   }
-  B2_LAUNCH(lane_kernel<E>, c.groups, 4 * c.TPL, c.smem, ctx->stream, p);
+  B2_LAUNCH(lane_kernel<E>, c.groups / ctx->nranks, 4 * c.TPL, c.smem, ctx->stream, p);
   CK(cudaGetLastError());
   return B2_OK;
 }
@@ -384,14 +434,23 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   if (pr.err != B2_OK) return pr.err;
   const PassCfg& c = sp->cfg[orient];
   LaneProg& p = pr.p;
+  b2_ctx* ctx = sp->ctx;
   p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
-  p.group0 = 0; p.groups_per_rank = c.in_tiles; p.rank = sp->ctx->rank;
-  sp->ctx->launches++;
-  switch (c.E) {
-    case 4: return launch_E<4>(sp->ctx, c, p);
-    case 8: return launch_E<8>(sp->ctx, c, p);
-    default: return launch_E<16>(sp->ctx, c, p);
+  p.group0 = ctx->rank * (c.groups / ctx->nranks); p.groups_per_rank = c.in_tiles / ctx->nranks; p.rank = ctx->rank;
+  bool exchange = false;
+  if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
+    for (int i = 0; i < p.nops; i++)
+      if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
   }
+  ctx->launches++;
+  int r;
+  switch (c.E) {
+    case 4: r = launch_E<4>(ctx, c, p); break;
+    case 8: r = launch_E<8>(ctx, c, p); break;
+    default: r = launch_E<16>(ctx, c, p); break;
+  }
+  if (r != B2_OK) return r;
+  return exchange ? ctx_barrier(ctx) : B2_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,7 +482,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
 }
 
 static int alloc_zero(b2_space* sp, double** out) {
-  CK(cudaMalloc(out, sp->elems() * sizeof(double)));
+  RET(ctx_alloc(sp->ctx, sp->elems() * sizeof(double), out));
   CK(cudaMemsetAsync(*out, 0, sp->elems() * sizeof(double), sp->ctx->stream));
   return B2_OK;
 }
@@ -507,10 +566,9 @@ static int op_forward_ortho_dealias(b2_space* sp, const double* phys, double* or
 // ------------------------------------------------------------------------------------------------
 // solvers
 // ------------------------------------------------------------------------------------------------
-static int upload_lu(const LuVecs& lu, int L, DVecD* fl, DVecD* id, DVecD* u1, DVecD* u2) {
-  LuVecs p = lu;
-  p.fl.resize(L, 0.0); p.id.resize(L, 0.0); p.u1.resize(L, 0.0); p.u2.resize(L, 0.0);
-  RET(fl->upload(p.fl)); RET(id->upload(p.id)); RET(u1->upload(p.u1)); RET(u2->upload(p.u2));
+static int upload_lu(const LuVecs& lu, const Base1& b, DVecD* fl, DVecD* id, DVecD* u1, DVecD* u2) {
+  RET(fl->upload(b.scan_layout(lu.fl))); RET(id->upload(b.scan_layout(lu.id)));
+  RET(u1->upload(b.scan_layout(lu.u1))); RET(u2->upload(b.scan_layout(lu.u2)));
   return B2_OK;
 }
 
@@ -529,7 +587,7 @@ static int hholtz_create(b2_space* sp, double c0, double c1, b2_solver** out) {
         mat.up1[i] = a.up1[i] - bm.up1[i] * c[ax];
         mat.up2[i] = a.up2[i] - bm.up2[i] * c[ax];
       }
-      RET(upload_lu(sweep(mat), L, &s->fl[ax], &s->id[ax], &s->u1[ax], &s->u2[ax]));
+      RET(upload_lu(sweep(mat), b, &s->fl[ax], &s->id[ax], &s->u1[ax], &s->u2[ax]));
     } else if (!b.cheb) {  // Sdma: dia = 1 - c * (-k^2), src/solver/sdma.rs:37-46
       std::vector<double> sd(L, 0.0);
       for (int k = 0; k < b.m; k++) sd[k] = 1.0 / (1.0 - (-(double)k * k) * c[ax]);
@@ -593,11 +651,12 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
   Diags lap1, mass1;
   poisson_axis(b1, c1, &lap1, &mass1);
   const PassCfg& c = sp->cfg[0];
-  const size_t total = (size_t)c.groups * c.C * 4 * c.TPL;
+  const int nr = sp->ctx->nranks, lane0 = sp->ctx->rank * (c.groups / nr) * 4, lane1 = lane0 + (c.groups / nr) * 4;
+  const size_t total = (size_t)(c.groups / nr) * c.C * 4 * c.TPL;
   std::vector<double> pfl(total, 0.0), pid(total, 0.0), pu1(total, 0.0), pu2(total, 0.0);
   const int m1 = b1.m;
   Diags mat(m1);
-  for (int lane = 0; lane < lanes; lane++) {
+  for (int lane = lane0; lane < std::min(lanes, lane1); lane++) {
     const double lm = lam[lane];
     for (int i = 0; i < m1; i++) {
       mat.low[i] = lap1.low[i] + mass1.low[i] * lm;
@@ -606,7 +665,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
       mat.up2[i] = lap1.up2[i] + mass1.up2[i] * lm;
     }
     LuVecs lu = sweep(mat);
-    const int g = lane / 4, l = lane % 4;
+    const int g = (lane - lane0) / 4, l = lane % 4;
     for (int i = 0; i < m1; i++) {
       const int q = i / c.C, ii = i % c.C;
       const size_t k = (((size_t)g * c.C + ii) * 4 + l) * c.TPL + q;
@@ -643,7 +702,7 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
     // out[j, :] = fwd . rhs[j, :]  (dense FP64 GEMM, src/solver/poisson.rs:213-219)
     const double one = 1.0, zero = 0.0;
     RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->fwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1 / ctx->nranks, s->m0, &one, s->fwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
     RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x2; x2.load(s->plain[1], s->m0, 1.0, LD_PLAIN); x2.store(sp->tmp[0], s->m0, ST_TRANS);
@@ -654,7 +713,7 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
     Prog x3; x3.load(sp->tmp[1], s->m0); x3.store(s->plain[0], s->m0, ST_PLAIN);
     RET(run_pass(sp, 1, x3));
     RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1, s->m0, &one, s->bwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1 / ctx->nranks, s->m0, &one, s->bwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
     RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x4; x4.load(s->plain[1], s->m0, 1.0, LD_PLAIN);
@@ -708,6 +767,10 @@ struct b2_navier {
   int use_graph = 1, warm_steps = 0;
 };
 
+#ifndef B2_EMU
+static int b2_heap_malloc(void** p, size_t bytes) { CK(cudaMalloc(p, bytes)); return B2_OK; }
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -731,7 +794,14 @@ int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** 
   CK(cudaMalloc(&c->blas_ws, (size_t)64 << 20));   // fixed workspace so that the GEMMs can live inside a CUDA graph
   CKB(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)64 << 20));
 #endif
-  (void)heap_bytes;
+  if (nranks > 1) {
+    if (heap_bytes < (1u << 20)) return fail(B2_ERR_ARG, "nranks > 1 needs a symmetric heap (heap_bytes)");
+    c->heap_bytes = heap_bytes;
+    RET(b2_heap_malloc(reinterpret_cast<void**>(&c->heap), heap_bytes));
+    CK(cudaMemset(c->heap, 0, heap_bytes));
+    c->heap_used = B2_HEAP_RESERVED;
+    c->peer_base[rank] = c->heap;
+  }
   *out = c;
   return B2_OK;
 }
@@ -775,21 +845,45 @@ int b2_ctx_profile(b2_ctx* c, int on, double* gemm_ms) {
   return B2_OK;
 }
 int b2_ctx_nranks(const b2_ctx* c) { return c->nranks; }
-int b2_ctx_heap_handle(b2_ctx*, void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
-int b2_ctx_attach_peers(b2_ctx*, const void*) { return fail(B2_ERR_UNSUPPORTED, "multi-GPU heap not built yet"); }
+int b2_ctx_heap_handle(b2_ctx* c, void* handle64) {
+  if (c->nranks == 1) return fail(B2_ERR_ARG, "single-rank context has no heap");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->heap));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return B2_OK;
+}
+int b2_ctx_attach_peers(b2_ctx* c, const void* handles) {
+  if (c->nranks == 1) return B2_OK;
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+    CK(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  CK(cudaMalloc(&c->d_peers, B2_MAXPEERS * sizeof(double*)));
+  CK(cudaMemcpy(c->d_peers, c->peer_base, B2_MAXPEERS * sizeof(double*), cudaMemcpyHostToDevice));
+  c->attached = true;
+  return B2_OK;
+}
+int b2_ctx_barrier(b2_ctx* c) { return ctx_barrier(c); }
 
 int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space** out) {
   if (!ctx || !out) return fail(B2_ERR_ARG, "b2_space2_create: null");
   CK(cudaSetDevice(ctx->device));
   b2_space* sp = new b2_space();
   sp->ctx = ctx;
-  int r = sp->b[0].init(kind0, n0);
-  if (r == B2_OK) r = sp->b[1].init(kind1, n1);
+  int r = sp->b[0].init_host(kind0, n0);
+  if (r == B2_OK) r = sp->b[1].init_host(kind1, n1);
   if (r == B2_OK && !sp->b[1].cheb) r = fail(B2_ERR_UNSUPPORTED, "axis 1 must be a Chebyshev base (Navier2D spaces)");
   if (r != B2_OK) { delete sp; return r; }
-  for (int ax = 0; ax < 2; ax++) sp->P[ax] = roundup(std::max(sp->b[ax].rows_phys, sp->b[ax].rows_ortho), 4);
+  // padded so that the 4-row lane groups split evenly over the ranks (slab decomposition)
+  for (int ax = 0; ax < 2; ax++) sp->P[ax] = roundup(std::max(sp->b[ax].rows_phys, sp->b[ax].rows_ortho), 4 * ctx->nranks);
   r = make_cfg(sp->b[1], sp->P[1], sp->P[0], &sp->cfg[0]);
   if (r == B2_OK) r = make_cfg(sp->b[0], sp->P[0], sp->P[1], &sp->cfg[1]);
+  if (r == B2_OK) r = sp->b[1].init(sp->cfg[0].C, sp->cfg[0].TPL);   // cfg[0]: lanes along axis 1
+  if (r == B2_OK) r = sp->b[0].init(sp->cfg[1].C, sp->cfg[1].TPL);
   if (r != B2_OK) { delete sp; return r; }
   sp->transforms_ok = sp->b[0].d_tw.d && sp->b[1].d_tw.d;
   for (int i = 0; i < 3; i++) RET(alloc_zero(sp, &sp->tmp[i]));
@@ -798,7 +892,7 @@ int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space
 }
 int b2_space_destroy(b2_space* sp) {
   if (!sp) return B2_OK;
-  for (auto& t : sp->tmp) if (t) cudaFree(t);
+  for (auto& t : sp->tmp) ctx_free(sp->ctx, t);
   sp->b[0].release(); sp->b[1].release();
   delete sp;
   return B2_OK;
@@ -829,12 +923,21 @@ int b2_array_create(b2_space* sp, int shape_kind, b2_array** out) {
   *out = a;
   return B2_OK;
 }
-int b2_array_destroy(b2_array* a) { if (a) { cudaFree(a->d); delete a; } return B2_OK; }
+int b2_array_destroy(b2_array* a) { if (a) { ctx_free(a->sp->ctx, a->d); delete a; } return B2_OK; }
+
+// rows of the logical (real-row) array that live on this rank: [row0, row0 + count)
+static void local_rows(const b2_space* sp, int rows_total, int* row0, int* count) {
+  const int per = sp->P[0] / sp->ctx->nranks;
+  *row0 = sp->ctx->rank * per;
+  *count = std::max(0, std::min(per, rows_total - *row0));
+}
 
 static int array_copy(const b2_array* a, void* buf, size_t bytes, int to_device) {
   b2_space* sp = a->sp;
   int r, c;
   RET(shape_of(sp, a->shape_kind, &r, &c));
+  { int row0; local_rows(sp, r, &row0, &r); }   // multi-rank: the host buffer is this rank's slab of rows
+  if (r == 0) return bytes == 0 ? B2_OK : fail(B2_ERR_SHAPE, "this rank owns no rows of the array");
   const size_t need = (size_t)r * c * sizeof(double);
   if (bytes != need) return fail(B2_ERR_SHAPE, "host buffer has " + std::to_string(bytes) + " bytes, array needs " + std::to_string(need));
   CK(cudaSetDevice(sp->ctx->device));
@@ -862,6 +965,15 @@ static int array_copy(const b2_array* a, void* buf, size_t bytes, int to_device)
   CK(cudaStreamSynchronize(st));
   return B2_OK;
 }
+int b2_array_local_rows(const b2_array* a, int* row_start, int* row_count) {
+  int r, c, row0, cnt;
+  RET(shape_of(a->sp, a->shape_kind, &r, &c));
+  local_rows(a->sp, r, &row0, &cnt);
+  const int div = shape_complex(a->sp, a->shape_kind) ? 2 : 1;
+  if (row_start) *row_start = row0 / div;
+  if (row_count) *row_count = cnt / div;
+  return B2_OK;
+}
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes) { return array_copy(a, const_cast<void*>(buf), bytes, 1); }
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes) { return array_copy(a, buf, bytes, 0); }
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
@@ -882,10 +994,16 @@ static int norm2_dev(b2_space* sp, const double* d, double* out) {
   CK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
   CK(cudaStreamSynchronize(sp->ctx->stream));
   CK(cudaFree(acc));
-  *out = std::sqrt(h);
+  *out = h;
   return B2_OK;
 }
-int b2_array_norm2(const b2_array* a, double* out) { return norm2_dev(a->sp, a->d, out); }
+// sum |a|^2 over this rank's slab; with one rank b2_array_norm2 = sqrt of it (functions.rs:24-35)
+int b2_array_sumsq_local(const b2_array* a, double* out) { return norm2_dev(a->sp, a->d, out); }
+int b2_array_norm2(const b2_array* a, double* out) {
+  RET(norm2_dev(a->sp, a->d, out));
+  *out = std::sqrt(*out);
+  return B2_OK;
+}
 
 int b2_field_create(b2_space* sp, b2_field** out) {
   b2_field* f = new b2_field{sp, nullptr, nullptr};
@@ -899,6 +1017,9 @@ int b2_field_set_v_host(b2_field* f, const void* buf, size_t bytes) { return b2_
 int b2_field_get_v_host(const b2_field* f, void* buf, size_t bytes) { return b2_array_get_host(f->v, buf, bytes); }
 int b2_field_set_vhat_host(b2_field* f, const void* buf, size_t bytes) { return b2_array_set_host(f->vhat, buf, bytes); }
 int b2_field_get_vhat_host(const b2_field* f, void* buf, size_t bytes) { return b2_array_get_host(f->vhat, buf, bytes); }
+int b2_field_local_rows(const b2_field* f, int shape_kind, int* row_start, int* row_count) {
+  return b2_array_local_rows(shape_kind == B2_SHAPE_PHYSICAL ? f->v : f->vhat, row_start, row_count);
+}
 int b2_forward(b2_field* f) { return op_forward(f->sp, f->v->d, f->vhat->d); }
 int b2_backward(b2_field* f) { return op_backward(f->sp, f->vhat->d, f->v->d); }
 static int need_kind(const b2_array* a, int kind, const char* what) {
@@ -927,7 +1048,7 @@ int b2_solver_destroy(b2_solver* s) {
   if (!s) return B2_OK;
   for (int ax = 0; ax < 2; ax++) { s->fl[ax].release(); s->id[ax].release(); s->u1[ax].release(); s->u2[ax].release(); s->sd[ax].release(); }
   s->fwd.release(); s->bwd.release(); s->pfl.release(); s->pid.release(); s->pu1.release(); s->pu2.release();
-  for (auto& p : s->plain) if (p) cudaFree(p);
+  for (auto& p : s->plain) ctx_free(s->sp->ctx, p);
   delete s;
   return B2_OK;
 }
@@ -1003,7 +1124,9 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
     const double x1 = y[0], x2 = y[ny - 1], y1 = 0.5, y2 = -0.5;
     const double m = (y2 - y1) / (x2 - x1), n = (y1 * x2 - y2 * x1) / (x2 - x1);
     for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) v[(size_t)i * ny + j] = m * y[j] + n;
-    RET(b2_field_set_v_host(nv->tempbc, v.data(), v.size() * sizeof(double)));
+    int row0 = 0, cnt = nx;
+    RET(b2_field_local_rows(nv->tempbc, B2_SHAPE_PHYSICAL, &row0, &cnt));   // every row is the same profile
+    RET(b2_field_set_v_host(nv->tempbc, v.data(), (size_t)cnt * ny * sizeof(double)));
     RET(b2_forward(nv->tempbc));
     RET(b2_backward(nv->tempbc));
     // constants of the step: to_ortho(tempbc) and dt*ka*(d2/dx2 + d2/dy2) tempbc (navier_eq.rs:214-218)
@@ -1039,12 +1162,13 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
 
 int b2_navier_destroy(b2_navier* nv) {
   if (!nv) return B2_OK;
-  double* work[] = {nv->that, nv->tbc_ortho, nv->tbc_diff, nv->rhs, nv->g1, nv->g2, nv->conv, nv->div, nv->ux, nv->uy, nv->d_scalar};
-  for (auto w : work) if (w) cudaFree(w);
+  double* work[] = {nv->that, nv->tbc_ortho, nv->tbc_diff, nv->rhs, nv->g1, nv->g2, nv->conv, nv->div, nv->ux, nv->uy};
+  for (auto w : work) ctx_free(nv->ctx, w);
+  if (nv->d_scalar) cudaFree(nv->d_scalar);
   double* fw[] = {nv->VTv, nv->uxT, nv->uyT, nv->cv, nv->PH, nv->PHy, nv->F1, nv->F2, nv->R0, nv->G0, nv->G1, nv->U1, nv->U2, nv->U3,
                   nv->GxT, nv->GyT, nv->KbT, nv->KTT};
-  for (auto w : fw) if (w) cudaFree(w);
-  for (int i = 0; i < 3; i++) { cudaFree(nv->Pf[i]); cudaFree(nv->Qf[i]); cudaFree(nv->V1[i]); cudaFree(nv->Cx[i]); cudaFree(nv->Zf[i]); }
+  for (auto w : fw) ctx_free(nv->ctx, w);
+  for (int i = 0; i < 3; i++) { ctx_free(nv->ctx, nv->Pf[i]); ctx_free(nv->ctx, nv->Qf[i]); ctx_free(nv->ctx, nv->V1[i]); ctx_free(nv->ctx, nv->Cx[i]); ctx_free(nv->ctx, nv->Zf[i]); }
   b2_field* fs[] = {nv->temp, nv->velx, nv->vely, nv->pres, nv->pseu, nv->tempbc};
   for (auto f : fs) b2_field_destroy(f);
 #ifndef B2_EMU
@@ -1247,7 +1371,24 @@ static int nav_update_fused(b2_navier* nv) {
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
   const double* pseu_src; int pseu_flags;
-  if (ps->dense) {
+  if (ps->dense && ctx->nranks > 1) {
+    // slabs: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y, row-major)
+    const double one = 1.0, zero = 0.0;
+    const int P1loc = P1 / ctx->nranks;
+    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_TRANS | ST_PLAIN);
+    RET(run_pass(so, 0, y));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->fwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
+    ctx->launches++;
+    Prog x; x.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x.store(nv->U1, ps->m0, ST_TRANS);
+    RET(run_pass(so, 1, x));
+    Prog y2; y2.load(nv->U1, byp.m); y2.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_TRANS | ST_PLAIN);
+    RET(run_pass(so, 0, y2));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->bwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
+    ctx->launches++;
+    Prog x2; x2.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, ps->m0, ST_TRANS);
+    RET(run_pass(so, 1, x2));
+    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
+  } else if (ps->dense) {
     const double one = 1.0, zero = 0.0;
     Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN);
     RET(run_pass(so, 0, y));
@@ -1274,8 +1415,10 @@ static int nav_update_fused(b2_navier* nv) {
     Prog y;
     for (int k = 0; k < 3; k++) {
       y.load(pseu_src, byp.m, 1.0, pseu_flags);
-      if (ps->dense) y.zeroelem(0, 0);
-      if (k == 0 && ps->dense) y.store(nv->pseu->vhat->d, byp.m, 0);
+      if (pseu_flags & LD_PLAIN) {   // single-GPU dense path: pseu still sits in the GEMM's row-major buffer
+        y.zeroelem(0, 0);
+        if (k == 0) y.store(nv->pseu->vhat->d, byp.m, 0);
+      }
       y.to_ortho(byp);
       if (k == 1) y.deriv_axis(byo, 1, sy);
       int l = byo.rows_ortho;
@@ -1333,7 +1476,9 @@ int b2_navier_update(b2_navier* nv, int nsteps) {
 int b2_navier_div_norm(b2_navier* nv, double* out) {
   RET(op_gradient(nv->sp_vel, nv->velx->vhat->d, 1, 0, nv->scale, nv->g1));
   RET(op_gradient(nv->sp_vel, nv->vely->vhat->d, 0, 1, nv->scale, nv->g1, 1.0, true));
-  return norm2_dev(nv->sp_ortho, nv->g1, out);
+  RET(norm2_dev(nv->sp_ortho, nv->g1, out));   // multi-rank: local sum of squares; the host all-reduces
+  if (nv->ctx->nranks == 1) *out = std::sqrt(*out);
+  return B2_OK;
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
 int b2_navier_set_mode(b2_navier* nv, int mode) {

@@ -302,7 +302,9 @@ __device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, co
         d = reinterpret_cast<double2*>(reinterpret_cast<char*>(peers[owner]) +
                                        (reinterpret_cast<const char*>(op.p0) - reinterpret_cast<const char*>(peers[P.rank])));
       }
-      size_t idx = (((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + l0) >> 1;
+      // tiled: tile (Jl, g) holds [jl][l];  row-major ("plain", for the GEMM): row 4*Jl+jl, columns 4g+l
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + l0) >> 1)
+                                      : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + l0) >> 1);
       if (flags & ST_ACC) { double2 o = d[idx]; v.x += o.x; v.y += o.y; }
       d[idx] = v;
     }
@@ -338,9 +340,10 @@ __device__ __forceinline__ void op_band(const LaneProg& P, const LaneOp& op, dou
     int i = base + ii;
     double acc = 0.0;
     if (ii < C && i < len_out) {
-      if (o0 != 127) { int j = i + o0; if (j >= 0 && j < len_in) acc = (c0 ? c0[i] : 1.0) * w[j]; }
-      if (o1 != 127) { int j = i + o1; if (j >= 0 && j < len_in) acc = fma(c1 ? c1[i] : 1.0, w[j], acc); }
-      if (o2 != 127) { int j = i + o2; if (j >= 0 && j < len_in) acc = fma(c2 ? c2[i] : 1.0, w[j], acc); }
+      const int k = ii * TPL + q;   // coefficient vectors are stored chunk-transposed: coalesced across the lane's threads
+      if (o0 != 127) { int j = i + o0; if (j >= 0 && j < len_in) acc = (c0 ? c0[k] : 1.0) * w[j]; }
+      if (o1 != 127) { int j = i + o1; if (j >= 0 && j < len_in) acc = fma(c1 ? c1[k] : 1.0, w[j], acc); }
+      if (o2 != 127) { int j = i + o2; if (j >= 0 && j < len_in) acc = fma(c2 ? c2[k] : 1.0, w[j], acc); }
     }
     y[ii] = acc;
   }
@@ -395,12 +398,12 @@ __device__ __forceinline__ void op_deriv(const LaneProg& P, const LaneOp& op, do
   }
 }
 
-// Coefficient access for the banded LU solve: shared vectors (index i) or per-lane arrays in
-// "scan layout"  ((g*C + ii)*4 + l)*TPL + q  (coalesced across the CTA at every step).
+// Coefficient access for the banded LU solve: shared vectors in chunk-transposed order (ii*TPL + q) or
+// per-lane arrays in "scan layout" ((g*C + ii)*4 + l)*TPL + q: coalesced across the CTA at every step.
 struct FdCoef {
   const double* fl; const double* id; const double* u1; const double* u2;
-  bool perlane; size_t pbase; int stride;
-  __device__ __forceinline__ size_t ix(int i, int ii) const { return perlane ? pbase + (size_t)ii * stride : (size_t)i; }
+  size_t pbase; int stride;
+  __device__ __forceinline__ size_t ix(int, int ii) const { return pbase + (size_t)ii * stride; }
 };
 
 // In-place solve of the LU-factored 4-diagonal (-2,0,+2,+4) system (reference: src/solver/fdma.rs:101-118):
@@ -415,9 +418,9 @@ __device__ __forceinline__ void op_fdma(const LaneProg& P, const LaneOp& op, dou
   const int base = q * C;
   FdCoef cf;
   cf.fl = (const double*)op.p0; cf.id = (const double*)op.p1; cf.u1 = (const double*)op.p2; cf.u2 = (const double*)op.p3;
-  cf.perlane = op.i2 & FD_PERLANE;
-  cf.stride = 4 * TPL;
-  cf.pbase = ((size_t)gl * C * 4 + l) * TPL + q;
+  // shared vectors: chunk-transposed [ii][q]; per-lane arrays: [group][ii][lane][q]  -- both coalesced
+  if (op.i2 & FD_PERLANE) { cf.stride = 4 * TPL; cf.pbase = ((size_t)gl * C * 4 + l) * TPL + q; }
+  else { cf.stride = TPL; cf.pbase = q; }
   const bool nou2 = op.i2 & FD_NOU2;
   // ---- forward elimination (first order, prefix) ----
   {

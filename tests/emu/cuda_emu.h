@@ -16,6 +16,10 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #define __global__
 #define __device__
@@ -175,6 +179,44 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+// CUDA IPC emulated with POSIX shared memory (multi-rank tests: one process per "GPU", gloo for the handles)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+namespace emu {
+struct Shm { void* p; size_t n; char name[48]; };
+inline std::vector<Shm>& shms() { static std::vector<Shm>* v = new std::vector<Shm>; return *v; }
+inline void unlink_all() { for (auto& s : shms()) shm_unlink(s.name); }
+}  // namespace emu
+static inline int b2_heap_malloc(void** p, size_t bytes) {
+  static int counter = 0;
+  emu::Shm s;
+  snprintf(s.name, sizeof(s.name), "/b2emu_%d_%d", (int)getpid(), counter++);
+  int fd = shm_open(s.name, O_CREAT | O_RDWR, 0600);
+  if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) return 2;
+  s.p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (s.p == MAP_FAILED) return 2;
+  s.n = bytes;
+  if (emu::shms().empty()) atexit(emu::unlink_all);
+  emu::shms().push_back(s);
+  *p = s.p;
+  return 0;
+}
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* ptr) {
+  for (auto& s : emu::shms())
+    if (s.p == ptr) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, s.name, sizeof(s.name)); memcpy(h->reserved + 48, &s.n, sizeof(size_t)); return 0; }
+  return 1;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, int) {
+  size_t n; memcpy(&n, h.reserved + 48, sizeof(size_t));
+  int fd = shm_open(h.reserved, O_RDWR, 0600);
+  if (fd < 0) return 1;
+  *p = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  return *p == MAP_FAILED ? 1 : 0;
+}
 typedef void* cudaEvent_t;
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(8); return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
