@@ -103,6 +103,14 @@ class Context:
         check(lib().b2_ctx_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def opprof(self, on):
+        """Per-op cycle counters of the lane kernel: {op name: (cycles, calls)} since the last call."""
+        buf = (C.c_ulonglong * 64)()
+        check(lib().b2_ctx_opprof(self._h, int(on), buf))
+        names = {1: "load", 2: "store", 3: "band", 4: "deriv", 5: "fdma", 6: "dct", 7: "rfft", 8: "fdiff", 9: "scalevec",
+                 10: "zerotail", 11: "lanemask", 12: "zeroelem", 13: "scale"}
+        return {names[c]: (buf[c], buf[32 + c]) for c in names if buf[32 + c]}
+
     def profile(self, on):
         """Switch GEMM timing on/off; returns the GEMM milliseconds accumulated since the last call."""
         ms = C.c_double()

@@ -64,6 +64,7 @@ struct b2_ctx {
   void* peer_base[B2_MAXPEERS] = {nullptr};
   bool attached = false;
   long long barriers = 0;
+  unsigned long long* d_prof = nullptr;   // per-op cycle counters (debug/profiling)
 };
 static const size_t B2_HEAP_RESERVED = 4096;  // flags[0..nranks) + epoch counter live at the start of the heap
 
@@ -182,13 +183,14 @@ struct Base1 {
   int init_host(int kind_, int n_);
   int init(int C, int TPL);   // device vectors; (C, TPL) = chunking of the passes whose lanes run along this axis
   int lay_C = 1, lay_TPL = 1;
-  // chunk-transposed copy of a coefficient vector: out[ii*TPL + q] = v[q*C + ii]
+  // pair/scan order of a coefficient vector: double2 slot [t*TPL + q] = (v[2p], v[2p+1]), p = q*CP + t
   std::vector<double> scan_layout(const std::vector<double>& v) const {
-    std::vector<double> o((size_t)lay_C * lay_TPL, 0.0);
+    std::vector<double> o((size_t)2 * lay_C * lay_TPL, 0.0);
     for (int q = 0; q < lay_TPL; q++)
-      for (int ii = 0; ii < lay_C; ii++) {
-        const size_t i = (size_t)q * lay_C + ii;
-        if (i < v.size()) o[(size_t)ii * lay_TPL + q] = v[i];
+      for (int t = 0; t < lay_C; t++) {
+        const size_t p = (size_t)q * lay_C + t, k = (size_t)t * lay_TPL + q;
+        if (2 * p < v.size()) o[2 * k] = v[2 * p];
+        if (2 * p + 1 < v.size()) o[2 * k + 1] = v[2 * p + 1];
       }
     return o;
   }
@@ -230,7 +232,7 @@ int Base1::init(int C, int TPL) {
     std::vector<double> sten2(L, 0.0), s2v(L, 0.0);
     for (int i = 2; i < n; i++) sten2[i] = s2[i - 2];
     for (int k = 0; k < m; k++) s2v[k] = s2[k];
-    RET(d_sten2.upload(sten2)); RET(d_sten2s.upload(scan_layout(sten2))); RET(d_s2.upload(scan_layout(s2v)));
+    RET(d_sten2.upload(sten2)); RET(d_sten2s.upload(sten2)); RET(d_s2.upload(s2v));   // banded mat-vec coefficients: natural order
     // from_ortho: (S^T S) c = S^T o, tridiagonal at offsets (-2,0,2)
     Diags t(m);
     for (int k = 0; k < m; k++) {
@@ -247,7 +249,7 @@ int Base1::init(int C, int TPL) {
       if (i < m - 2) bu1[i] = pv(i, 2);
       if (i < m - 4) bu2[i] = pv(i, 4);
     }
-    RET(d_bd.upload(scan_layout(bd))); RET(d_bu1.upload(scan_layout(bu1))); RET(d_bu2.upload(scan_layout(bu2)));
+    RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
   }
   // transform tables (only when the size is one the FFT core handles)
   if (is_pow2(N) && N >= 64) {
@@ -262,7 +264,7 @@ int Base1::init(int C, int TPL) {
   return B2_OK;
 }
 
-struct PassCfg { int in_tiles, out_tiles, LP, TPL, C, E, groups; size_t smem; };
+struct PassCfg { int in_tiles, out_tiles, LP, TPL, C, E, groups, LN; size_t smem; };
 
 struct b2_space {
   b2_ctx* ctx = nullptr;
@@ -424,7 +426,7 @@ template <int E> static int launch_E(b2_ctx* ctx, const PassCfg& c, const LanePr
     CK(cudaFuncSetAttribute(lane_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     set_smem = c.smem;
   }
-  B2_LAUNCH(lane_kernel<E>, c.groups / ctx->nranks, 4 * c.TPL, c.smem, ctx->stream, p);
+  B2_LAUNCH(lane_kernel<E>, (c.groups / ctx->nranks) * (4 / c.LN), c.LN * c.TPL, c.smem, ctx->stream, p);
   CK(cudaGetLastError());
   return B2_OK;
 }
@@ -437,6 +439,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   b2_ctx* ctx = sp->ctx;
   p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
   p.group0 = ctx->rank * (c.groups / ctx->nranks); p.groups_per_rank = c.in_tiles / ctx->nranks; p.rank = ctx->rank;
+  p.prof = ctx->d_prof; p.LN = c.LN;
   bool exchange = false;
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
@@ -459,24 +462,40 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
 static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   c->in_tiles = Pl / 4; c->out_tiles = Pc / 4; c->groups = Pc / 4; c->LP = Pl;
   const int N = lane_base.N;
+  // E = FFT points per thread; a thread also owns CP = E+1 element pairs of the lane for the banded ops,
+  // so the lane (LP doubles) must fit in 2*CP*TPL.  LN = lanes per CTA (4 = whole lane group, 2 = half).
+  int ln_want = 4;
+  if (const char* e = getenv("B2_LN")) { if (atoi(e) == 2) ln_want = 2; }
+  auto pick = [&](int LN, int want) -> bool {
+    const int Nc = N / 2;
+    for (int e = want; e >= 4; e /= 2) {
+      const int tpl = Nc / e;
+      if (tpl >= 8 && tpl * LN <= 512 && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
+    }
+    return false;
+  };
   if (is_pow2(N) && N >= 64) {
     const int Nc = N / 2;
-    c->E = Nc >= 128 ? 16 : (Nc >= 64 ? 8 : 4);
-    if (const char* e = getenv("B2_E")) {   // tuning knob: FFT points per thread (4, 8, 16)
+    int want = Nc >= 128 ? 16 : (Nc >= 64 ? 8 : 4);
+    if (const char* e = getenv("B2_E")) {   // tuning knob
       int ev = atoi(e);
-      if ((ev == 4 || ev == 8 || ev == 16) && Nc / ev >= 8 && Nc / ev <= 128) c->E = ev;
+      if (ev == 4 || ev == 8 || ev == 16) want = ev;
     }
-    c->TPL = Nc / c->E;
+    c->E = 0;
+    const size_t smem4 = ((size_t)4 * Pl + 32 * 12) * sizeof(double);
+    bool ok = false;
+    if (ln_want == 4 && smem4 <= 227 * 1024) ok = pick(4, want) || pick(4, 16);
+    if (!ok) ok = pick(2, want) || pick(2, 16);
+    if (!ok) return fail(B2_ERR_UNSUPPORTED, "lane of " + std::to_string(Pl) + " points: no supported thread layout");
   } else {  // no transform along this axis: banded ops only
-    c->E = 4;
+    c->E = 16; c->LN = 4;
     int t = 8;
-    while (t * B2_CMAX < Pl) t *= 2;
+    while (2 * 17 * t < Pl) t *= 2;
     c->TPL = t;
+    if (t > 128) return fail(B2_ERR_UNSUPPORTED, "lane too long");
   }
-  if (c->TPL > 128) return fail(B2_ERR_UNSUPPORTED, "lane longer than 4100 points: needs the 2-lane kernel variant (not built yet)");
-  c->C = (Pl + c->TPL - 1) / c->TPL;
-  if (c->C > B2_CMAX) return fail(B2_ERR_UNSUPPORTED, "lane length / thread count combination not supported");
-  c->smem = ((size_t)4 * c->LP + 32 * 12) * sizeof(double);
+  c->C = c->E + 1;
+  c->smem = ((size_t)c->LN * c->LP + 32 * 12) * sizeof(double);
   if (c->smem > 227 * 1024) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
   return B2_OK;
 }
@@ -652,7 +671,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
   poisson_axis(b1, c1, &lap1, &mass1);
   const PassCfg& c = sp->cfg[0];
   const int nr = sp->ctx->nranks, lane0 = sp->ctx->rank * (c.groups / nr) * 4, lane1 = lane0 + (c.groups / nr) * 4;
-  const size_t total = (size_t)(c.groups / nr) * c.C * 4 * c.TPL;
+  const size_t total = (size_t)(c.groups / nr) * c.C * 4 * c.TPL * 2;
   std::vector<double> pfl(total, 0.0), pid(total, 0.0), pu1(total, 0.0), pu2(total, 0.0);
   const int m1 = b1.m;
   Diags mat(m1);
@@ -667,8 +686,8 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     LuVecs lu = sweep(mat);
     const int g = (lane - lane0) / 4, l = lane % 4;
     for (int i = 0; i < m1; i++) {
-      const int q = i / c.C, ii = i % c.C;
-      const size_t k = (((size_t)g * c.C + ii) * 4 + l) * c.TPL + q;
+      const int pr = i / 2, q = pr / c.C, t = pr % c.C;
+      const size_t k = ((((size_t)g * c.C + t) * 4 + l) * c.TPL + q) * 2 + (i & 1);
       pfl[k] = lu.fl[i]; pid[k] = lu.id[i]; pu1[k] = lu.u1[i]; pu2[k] = lu.u2[i];
     }
   }
@@ -830,6 +849,15 @@ int b2_ctx_timer_stop(b2_ctx* c, double* ms) {
   return B2_OK;
 }
 int b2_ctx_launch_count(const b2_ctx* c, long long* n) { *n = c->launches; return B2_OK; }
+// per-op cycle counters of the lane kernel (thread 0 of every CTA): out[code] = cycles, out[32+code] = count
+int b2_ctx_opprof(b2_ctx* c, int on, unsigned long long* out64) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_prof && out64) CK(cudaMemcpy(out64, c->d_prof, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (on && !c->d_prof) CK(cudaMalloc(&c->d_prof, 64 * sizeof(unsigned long long)));
+  if (c->d_prof) CK(cudaMemset(c->d_prof, 0, 64 * sizeof(unsigned long long)));
+  if (!on && c->d_prof) { CK(cudaFree(c->d_prof)); c->d_prof = nullptr; }
+  return B2_OK;
+}
 int b2_ctx_profile(b2_ctx* c, int on, double* gemm_ms) {
   CK(cudaStreamSynchronize(c->stream));
   double tot = 0;

@@ -22,7 +22,6 @@
 #include <stdint.h>
 
 #define B2_MAXOPS 24
-#define B2_CMAX 33        // max chunk (elements per thread per lane) for scans / banded ops
 #define B2_MAXPEERS 8
 
 enum LaneOpCode {
@@ -59,14 +58,22 @@ struct LaneProg {
   int in_tiles;   // 4x4 tiles per lane of arrays in the orientation being read
   int out_tiles;  // tiles per row of the transposed orientation (= number of lane groups)
   int TPL;        // threads per lane (blockDim.x = 4*TPL)
-  int C;          // chunk: elements per thread per lane, C*TPL >= LP
+  int C;          // pairs per thread per lane (= E+1 of the kernel instance), 2*C*TPL >= LP
   int group0;     // first lane group of this launch (multi-GPU slabs)
   int groups_per_rank;  // for ST_PEER: owner(J) = J / groups_per_rank (destination orientation)
   int rank;       // this GPU's rank (peer table index)
   int pad_;
+  unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
+  int LN;         // lanes per CTA: 4 (a whole lane group) or 2 (half a group; grid = 2 x groups)
+  int pad2_;
   LaneOp ops[B2_MAXOPS];
 };
 
+#ifdef B2_EMU
+template <class T> static inline T ldg(const T* p) { return *p; }
+#else
+template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }   // LDG.CONSTANT: read-only tables / coefficients
+#endif
 typedef double2 cplx;
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -237,9 +244,11 @@ __device__ __forceinline__ double lane_sum(double v, int TPL, double* scratch) {
 // ---------------------------------------------------------------------------------------------
 // ops
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl) {
+__device__ __noinline__ void op_load(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl) {
   const int T = blockDim.x, LP = P.LP;
-  const int npieces = LP * 2;  // 4 lanes * LP / 2 doubles
+  const int LN = P.LN, psh = LN == 4 ? 3 : 2, pm = 2 * LN - 1;   // 2*LN 16-byte pieces per tile belong to this CTA
+  const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;             // first lane of the group handled by this CTA
+  const int npieces = LN * LP / 2;
   const int len = op.i0;
   const double a = op.a;
   const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, plain = op.i2 & LD_PLAIN;
@@ -253,13 +262,14 @@ __device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, dou
 #pragma unroll
     for (int k = 0; k < U; k++) {
       const int pidx = p0 + k * T;
-      const int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      const int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
       v[k] = make_double2(0.0, 0.0); u[k] = make_double2(0.0, 0.0);
       if (pidx < npieces && J < P.in_tiles && j0 < len) {
-        v[k] = plain ? src[((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1] : src[slab + pidx];
+        v[k] = plain ? src[((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1]
+                     : src[slab + (size_t)J * 8 + (lb + l) * 2 + (pidx & 1)];
         if (sten && j0 >= 2) {   // composite -> orthonormal on the fly: + p1[j] * src[j-2]  (tiled sources only)
           const int jm = j0 - 2;
-          u[k] = src[slab + ((size_t)(jm >> 2) * 16 + l * 4 + (jm & 3)) / 2];
+          u[k] = src[slab + ((size_t)(jm >> 2) * 16 + (lb + l) * 4 + (jm & 3)) / 2];
         }
       }
     }
@@ -267,7 +277,7 @@ __device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, dou
     for (int k = 0; k < U; k++) {
       const int pidx = p0 + k * T;
       if (pidx >= npieces) break;
-      const int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      const int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
       double2 x = v[k];
       if (sten && j0 >= 2 && j0 < len) { x.x = fma(sc[j0], u[k].x, x.x); x.y = fma(sc[j0 + 1], u[k].y, x.y); }
       x.x *= a;
@@ -281,9 +291,11 @@ __device__ __forceinline__ void op_load(const LaneProg& P, const LaneOp& op, dou
   __syncthreads();
 }
 
-__device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, const double* __restrict__ W, int g, int gl) {
+__device__ __noinline__ void op_store(const LaneProg& P, const LaneOp& op, const double* __restrict__ W, int g, int gl) {
   const int T = blockDim.x, LP = P.LP;
-  const int npieces = P.in_tiles * 8;
+  const int LN = P.LN, psh = LN == 4 ? 3 : 2, pm = 2 * LN - 1, hl = LN >> 1;
+  const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;
+  const int npieces = P.in_tiles * 2 * LN;
   const int len = op.i0;
   const double a = op.a;
   const int flags = op.i2;
@@ -291,7 +303,8 @@ __device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, co
   if (flags & ST_TRANS) {
     double* const* peers = reinterpret_cast<double* const*>(op.p1);
     for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
-      int J = pidx >> 3, jl = (pidx & 7) >> 1, l0 = (pidx & 1) * 2, j = 4 * J + jl;
+      const int r = pidx & pm;
+      int J = pidx >> psh, jl = r / hl, l0 = (r % hl) * 2, j = 4 * J + jl;
       double2 v = make_double2(0.0, 0.0);
       if (j < len) { v.x = a * W[l0 * LP + j]; v.y = a * W[(l0 + 1) * LP + j]; }
       double2* d = dst;
@@ -303,22 +316,23 @@ __device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, co
                                        (reinterpret_cast<const char*>(op.p0) - reinterpret_cast<const char*>(peers[P.rank])));
       }
       // tiled: tile (Jl, g) holds [jl][l];  row-major ("plain", for the GEMM): row 4*Jl+jl, columns 4g+l
-      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + l0) >> 1)
-                                      : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + l0) >> 1);
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + lb + l0) >> 1)
+                                      : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + lb + l0) >> 1);
       if (flags & ST_ACC) { double2 o = d[idx]; v.x += o.x; v.y += o.y; }
       d[idx] = v;
     }
   } else {
     const size_t slab = (size_t)gl * P.in_tiles * 8;
     for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
-      int J = pidx >> 3, l = (pidx & 7) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
       double2 v = make_double2(0.0, 0.0);
       if (j0 < len) {
         double2 w = *reinterpret_cast<const double2*>(W + l * LP + j0);
         v.x = a * w.x;
         v.y = (j0 + 1 < len) ? a * w.y : 0.0;
       }
-      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * gl + l) * P.in_tiles * 4 + j0) >> 1) : (slab + pidx);
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1)
+                                      : (slab + (size_t)J * 8 + (lb + l) * 2 + (pidx & 1));
       if (flags & ST_ACC) { double2 o = dst[idx]; v.x += o.x; v.y += o.y; }
       dst[idx] = v;
     }
@@ -326,159 +340,165 @@ __device__ __forceinline__ void op_store(const LaneProg& P, const LaneOp& op, co
   __syncthreads();
 }
 
-__device__ __forceinline__ void op_band(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
-  const int TPL = P.TPL, C = P.C, LP = P.LP;
+// ---- chunked lane ops -------------------------------------------------------------------------
+// Thread q of a lane owns CP consecutive PAIRS (2p, 2p+1), p = q*CP + t.  All banded operators of the
+// path couple elements at even distance only, so every recurrence is a plain double2 recurrence over
+// pairs (no parity bookkeeping), shared-memory accesses are 16-byte with stride CP = E+1 (odd: no bank
+// conflicts) and coefficient vectors are stored "pair/scan" ordered, [t][q] as double2 (coalesced).
+__device__ __forceinline__ double2 d2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ double2 d2fma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+__device__ __forceinline__ double2 d2mul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+
+template <int CP>
+__device__ __noinline__ void op_band(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  // y_i = sum_m c_m[i] x_{i+o_m}, o_m even.  Thread q of a lane takes the pairs p = q + t*TPL (coalesced
+  // coefficient loads in natural order, conflict-free shared-memory reads); results are staged in
+  // registers because the operation is in place.
+  const int TPL = P.TPL, HP = P.LP >> 1;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
-  const int len_out = op.i0, len_in = op.i2;
-  const int o0 = (int)(signed char)(op.i1 & 0xff), o1 = (int)(signed char)((op.i1 >> 8) & 0xff), o2 = (int)(signed char)((op.i1 >> 16) & 0xff);
-  const double* c0 = (const double*)op.p0; const double* c1 = (const double*)op.p1; const double* c2 = (const double*)op.p2;
-  const double* w = W + l * LP;
-  double y[B2_CMAX];
-  const int base = q * C;
+  const int len_out = op.i0;
+  const int h0 = (int)(signed char)(op.i1 & 0xff), h1 = (int)(signed char)((op.i1 >> 8) & 0xff), h2 = (int)(signed char)((op.i1 >> 16) & 0xff);
+  const double2* __restrict__ c0 = (const double2*)op.p0;
+  const double2* __restrict__ c1 = (const double2*)op.p1;
+  const double2* __restrict__ c2 = (const double2*)op.p2;
+  const double2* w2 = reinterpret_cast<const double2*>(W + l * P.LP);
+  const double2 zero = d2(0.0, 0.0);
+  double2 y[CP];
 #pragma unroll
-  for (int ii = 0; ii < B2_CMAX; ii++) {
-    int i = base + ii;
-    double acc = 0.0;
-    if (ii < C && i < len_out) {
-      const int k = ii * TPL + q;   // coefficient vectors are stored chunk-transposed: coalesced across the lane's threads
-      if (o0 != 127) { int j = i + o0; if (j >= 0 && j < len_in) acc = (c0 ? c0[k] : 1.0) * w[j]; }
-      if (o1 != 127) { int j = i + o1; if (j >= 0 && j < len_in) acc = fma(c1 ? c1[k] : 1.0, w[j], acc); }
-      if (o2 != 127) { int j = i + o2; if (j >= 0 && j < len_in) acc = fma(c2 ? c2[k] : 1.0, w[j], acc); }
+  for (int t = 0; t < CP; t++) y[t] = zero;
+  auto term = [&](int h, const double2* __restrict__ c) {
+    const int hp = h >> 1;
+#pragma unroll
+    for (int t = 0; t < CP; t++) {
+      const int p = q + t * TPL, pp = p + hp;
+      const bool ok = pp >= 0 && pp < HP && p < HP;
+      const double2 x = w2[ok ? pp : 0];
+      const double2 cc = c ? ldg(c + (p < HP ? p : 0)) : d2(1.0, 1.0);
+      if (ok) y[t] = d2fma(cc, x, y[t]);
     }
-    y[ii] = acc;
-  }
+  };
+  if (h0 != 127) term(h0, c0);
+  if (h1 != 127) term(h1, c1);
+  if (h2 != 127) term(h2, c2);
   __syncthreads();
-  double* wo = W + l * LP;
+  double2* wo = reinterpret_cast<double2*>(W + l * P.LP);
 #pragma unroll
-  for (int ii = 0; ii < B2_CMAX; ii++) {
-    int i = base + ii;
-    if (ii < C && i < LP) wo[i] = y[ii];
+  for (int t = 0; t < CP; t++) {
+    const int p = q + t * TPL;
+    double2 v = y[t];
+    if (2 * p >= len_out) v.x = 0.0;
+    if (2 * p + 1 >= len_out) v.y = 0.0;
+    if (p < HP) wo[p] = v;
   }
   __syncthreads();
 }
 
-// Chebyshev derivative: b_k = S_{k+1},  S_m = 2 m a_m + S_{m+2};  b_0 *= 1/2;  result * scale
-__device__ __forceinline__ void op_deriv(const LaneProg& P, const LaneOp& op, double* __restrict__ W, void* scratch) {
-  const int TPL = P.TPL, C = P.C, LP = P.LP;
+// Chebyshev derivative: b_k = S_{k+1},  S_m = 2 m a_m + S_{m+2};  b_0 *= 1/2;  result * scale.
+// In pairs: S[p] = (2(2p) a_2p, 2(2p+1) a_2p+1) + S[p+1];  out[p] = (S[p].y, S[p+1].x).
+template <int CP>
+__device__ __noinline__ void op_deriv(const LaneProg& P, const LaneOp& op, double* __restrict__ W, void* scratch) {
+  const int TPL = P.TPL, HP = P.LP >> 1;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
-  const int n = op.i0;
-  double* w = W + l * LP;
-  const int base = q * C;
+  double2* w2 = reinterpret_cast<double2*>(W + l * P.LP);
   for (int rep = 0; rep < op.i1; rep++) {
-    // pass 1: chunk totals per parity
-    double tot0 = 0.0, tot1 = 0.0;
+    double2 tp[CP];
+    double2 tot = d2(0.0, 0.0);
 #pragma unroll
-    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
-      int i = base + ii;
-      if (ii < C && i < n) { double t = 2.0 * i * w[i]; if (i & 1) tot1 += t; else tot0 += t; }
+    for (int t = 0; t < CP; t++) {
+      const int p = q * CP + t;
+      double2 a = (p < HP) ? w2[p < HP ? p : 0] : d2(0.0, 0.0);
+      tp[t] = d2(2.0 * (2 * p) * a.x, 2.0 * (2 * p + 1) * a.y);
+      tot.x += tp[t].x; tot.y += tp[t].y;
     }
-    Aff1::V m; m.d[0] = 1; m.d[1] = tot0; m.d[2] = 1; m.d[3] = tot1;
+    Aff1::V m; m.d[0] = 1; m.d[1] = tot.x; m.d[2] = 1; m.d[3] = tot.y;
     Aff1::V inc = lane_scan_excl<Aff1, true>(m, TPL, (Aff1::V*)scratch);
-    double s0 = inc.d[1], s1 = inc.d[3];
-    double y[B2_CMAX];
-#pragma unroll
-    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
-      int i = base + ii;
-      double v = 0.0;
-      if (ii < C && i < LP) {
-        double t = (i < n) ? 2.0 * i * w[i] : 0.0;
-        if (i & 1) { s1 += t; v = s1; } else { s0 += t; v = s0; }
-      }
-      y[ii] = v;   // = S_i
-    }
-    __syncthreads();
+    double2 S = d2(inc.d[1], inc.d[3]);   // S of the first pair of the next chunk
     const double sc = (rep == op.i1 - 1) ? op.a : 1.0;
 #pragma unroll
-    for (int ii = 0; ii < B2_CMAX; ii++) {
-      int i = base + ii;
-      if (ii < C && i < LP && i >= 1) w[i - 1] = y[ii] * (i == 1 ? 0.5 * sc : sc);
+    for (int t = CP - 1; t >= 0; t--) {
+      const int p = q * CP + t;
+      const double nx = S.x;
+      S.x += tp[t].x; S.y += tp[t].y;
+      double2 o = d2(S.y * sc, nx * sc);
+      if (p == 0) o.x *= 0.5;
+      if (p < HP) w2[p] = o;
     }
-    if (q == TPL - 1) w[LP - 1] = 0.0;
     __syncthreads();
   }
 }
-
-// Coefficient access for the banded LU solve: shared vectors in chunk-transposed order (ii*TPL + q) or
-// per-lane arrays in "scan layout" ((g*C + ii)*4 + l)*TPL + q: coalesced across the CTA at every step.
-struct FdCoef {
-  const double* fl; const double* id; const double* u1; const double* u2;
-  size_t pbase; int stride;
-  __device__ __forceinline__ size_t ix(int, int ii) const { return pbase + (size_t)ii * stride; }
-};
 
 // In-place solve of the LU-factored 4-diagonal (-2,0,+2,+4) system (reference: src/solver/fdma.rs:101-118):
 //   forward:  x_i -= fl_i x_{i-2}                     (fl_i = swept low_{i-2})
 //   backward: x_i = (x_i - u1_i x_{i+2} - u2_i x_{i+4}) * id_i
-// Each thread owns a chunk; chunk maps are combined with an exclusive scan over the lane.
-__device__ __forceinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, void* scratch) {
-  const int TPL = P.TPL, C = P.C, LP = P.LP;
+// As pair recurrences: y_p = b_p - fl_p * y_{p-1};  x_p = (y_p - u1_p x_{p+1} - u2_p x_{p+2}) id_p.
+// Each thread reduces its CP pairs to an affine map; maps are combined by a scan across the lane's threads.
+template <int CP>
+__device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, void* scratch) {
+  const int TPL = P.TPL, HP = P.LP >> 1;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
   const int n = op.i0;
-  double* w = W + l * LP;
-  const int base = q * C;
-  FdCoef cf;
-  cf.fl = (const double*)op.p0; cf.id = (const double*)op.p1; cf.u1 = (const double*)op.p2; cf.u2 = (const double*)op.p3;
-  // shared vectors: chunk-transposed [ii][q]; per-lane arrays: [group][ii][lane][q]  -- both coalesced
-  if (op.i2 & FD_PERLANE) { cf.stride = 4 * TPL; cf.pbase = ((size_t)gl * C * 4 + l) * TPL + q; }
-  else { cf.stride = TPL; cf.pbase = q; }
+  double2* w2 = reinterpret_cast<double2*>(W + l * P.LP);
+  const double2* __restrict__ cfl = (const double2*)op.p0; const double2* __restrict__ cid = (const double2*)op.p1;
+  const double2* __restrict__ cu1 = (const double2*)op.p2; const double2* __restrict__ cu2 = (const double2*)op.p3;
+  // shared vectors: [t][q]; per-lane arrays: [group][t][lane][q]  (double2 units, coalesced at every step)
+  size_t base; int stride;
+  if (op.i2 & FD_PERLANE) { const int lb = (blockIdx.x & ((4 / P.LN) - 1)) * P.LN; stride = 4 * TPL; base = ((size_t)gl * CP * 4 + lb + l) * TPL + q; }
+  else { stride = TPL; base = q; }
   const bool nou2 = op.i2 & FD_NOU2;
-  // ---- forward elimination (first order, prefix) ----
+  const double2 zero = d2(0.0, 0.0);
+  const int p0 = q * CP;
+  auto rd = [&](int t) -> double2 {   // right-hand side / intermediate at pair p0+t, zero outside [0, n)
+    const int p = p0 + t;
+    const bool ok = p < HP;
+    double2 v = ok ? w2[ok ? p : 0] : zero;
+    if (2 * p >= n) v.x = 0.0;
+    if (2 * p + 1 >= n) v.y = 0.0;
+    return v;
+  };
+  // ---- forward elimination: y_p = b_p - fl_p y_{p-1} ----
   {
-    Aff1::V m = Aff1::identity();
-#pragma unroll
-    for (int ii = 0; ii < B2_CMAX; ii++) {
-      int i = base + ii;
-      if (ii < C && i < n) {
-        double a = -cf.fl[cf.ix(i, ii)], b = w[i];
-        int h = (i & 1) * 2;
-        m.d[h + 1] = fma(a, m.d[h + 1], b);
-        m.d[h] *= a;
-      }
+    double2 A = d2(1.0, 1.0), B = zero;
+#pragma unroll 6
+    for (int t = 0; t < CP; t++) {
+      const double2 f = ldg(cfl + base + (size_t)t * stride), b = rd(t);
+      B = d2(fma(-f.x, B.x, b.x), fma(-f.y, B.y, b.y));
+      A = d2(-f.x * A.x, -f.y * A.y);
     }
+    Aff1::V m; m.d[0] = A.x; m.d[1] = B.x; m.d[2] = A.y; m.d[3] = B.y;
     Aff1::V inc = lane_scan_excl<Aff1, false>(m, TPL, (Aff1::V*)scratch);
-    double y0 = inc.d[1], y1 = inc.d[3];  // x of the last even / odd element before this chunk (start state is 0)
-#pragma unroll
-    for (int ii = 0; ii < B2_CMAX; ii++) {
-      int i = base + ii;
-      if (ii < C && i < n) {
-        double a = -cf.fl[cf.ix(i, ii)];
-        if (i & 1) { y1 = fma(a, y1, w[i]); w[i] = y1; } else { y0 = fma(a, y0, w[i]); w[i] = y0; }
-      }
+    double2 y = d2(inc.d[1], inc.d[3]);   // y of the last pair before this chunk (the start state is 0)
+#pragma unroll 6
+    for (int t = 0; t < CP; t++) {
+      const double2 f = ldg(cfl + base + (size_t)t * stride), b = rd(t);
+      y = d2(fma(-f.x, y.x, b.x), fma(-f.y, y.y, b.y));
+      if (p0 + t < HP) w2[p0 + t] = y;
     }
   }
-  // no sync needed: every thread only touches its own chunk
-  // ---- back substitution (second order, suffix) ----
+  // every thread only touched its own chunk: no barrier needed before the back substitution
+  // ---- back substitution: x_p = (y_p - u1_p x_{p+1} - u2_p x_{p+2}) id_p ----
   {
     Aff2::V m = Aff2::identity();
-#pragma unroll
-    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
-      int i = base + ii;
-      if (ii < C && i < n) {
-        size_t k = cf.ix(i, ii);
-        double idv = cf.id[k];
-        double m0 = -cf.u1[k] * idv, m1 = nou2 ? 0.0 : -cf.u2[k] * idv, v0 = w[i] * idv;
-        double* M = m.d + 6 * (i & 1);
-        double r0 = m0 * M[0] + m1 * M[2], r1 = m0 * M[1] + m1 * M[3], rp = m0 * M[4] + m1 * M[5] + v0;
-        M[2] = M[0]; M[3] = M[1]; M[5] = M[4];
-        M[0] = r0; M[1] = r1; M[4] = rp;
-      }
+#pragma unroll 6
+    for (int t = CP - 1; t >= 0; t--) {
+      const size_t k = base + (size_t)t * stride;
+      const double2 idv = ldg(cid + k), u1 = ldg(cu1 + k), u2 = nou2 ? zero : ldg(cu2 + k), y = rd(t);
+      const double2 m0 = d2(-u1.x * idv.x, -u1.y * idv.y), m1 = d2(-u2.x * idv.x, -u2.y * idv.y), g0 = d2(y.x * idv.x, y.y * idv.y);
+      double* M = m.d;   // compose onto the chunk map; state = (x_{p+1}, x_{p+2}) per component
+      double r0 = m0.x * M[0] + m1.x * M[2], r1 = m0.x * M[1] + m1.x * M[3], rp = m0.x * M[4] + m1.x * M[5] + g0.x;
+      M[2] = M[0]; M[3] = M[1]; M[5] = M[4]; M[0] = r0; M[1] = r1; M[4] = rp;
+      M = m.d + 6;
+      r0 = m0.y * M[0] + m1.y * M[2]; r1 = m0.y * M[1] + m1.y * M[3]; rp = m0.y * M[4] + m1.y * M[5] + g0.y;
+      M[2] = M[0]; M[3] = M[1]; M[5] = M[4]; M[0] = r0; M[1] = r1; M[4] = rp;
     }
     Aff2::V inc = lane_scan_excl<Aff2, true>(m, TPL, (Aff2::V*)scratch);
-    // incoming state (x_{i+2}, x_{i+4}) per parity; the far-end state is (0,0) so only the offsets matter
-    double s[4] = {inc.d[4], inc.d[5], inc.d[10], inc.d[11]};
-#pragma unroll
-    for (int ii = B2_CMAX - 1; ii >= 0; ii--) {
-      int i = base + ii;
-      if (ii < C && i < n) {
-        size_t k = cf.ix(i, ii);
-        double idv = cf.id[k];
-        double* st = s + 2 * (i & 1);
-        double x = w[i] - cf.u1[k] * st[0];
-        if (!nou2) x -= cf.u2[k] * st[1];
-        x *= idv;
-        st[1] = st[0]; st[0] = x;
-        w[i] = x;
-      }
+    double2 s1 = d2(inc.d[4], inc.d[10]), s2 = d2(inc.d[5], inc.d[11]);   // x_{p+1}, x_{p+2} entering the chunk
+#pragma unroll 6
+    for (int t = CP - 1; t >= 0; t--) {
+      const size_t k = base + (size_t)t * stride;
+      const double2 idv = ldg(cid + k), u1 = ldg(cu1 + k), u2 = nou2 ? zero : ldg(cu2 + k), y = rd(t);
+      double2 x = d2((y.x - u1.x * s1.x - u2.x * s2.x) * idv.x, (y.y - u1.y * s1.y - u2.y * s2.y) * idv.y);
+      s2 = s1; s1 = x;
+      if (p0 + t < HP) w2[p0 + t] = x;
     }
   }
   __syncthreads();
@@ -508,7 +528,7 @@ __device__ __forceinline__ void fft_stage(double* __restrict__ wl, int Nc, int N
     if (Ns > 1) {
       int tstep = k * (Nc / (Ns * R));
 #pragma unroll
-      for (int r = 1; r < R; r++) v[b * R + r] = cmul(v[b * R + r], tw[r * tstep]);
+      for (int r = 1; r < R; r++) v[b * R + r] = cmul(v[b * R + r], ldg(tw + r * tstep));
     }
     Dft<R>::run(v + b * R);
     int j0 = (j - k) * R + k;
@@ -537,7 +557,7 @@ __device__ __forceinline__ void lane_fft(double* __restrict__ W, int LP, int Nc,
 //   mode 1 (backward): v = DCT-I(y)/2, y_k = (-1)^k c_k, y_0 and y_N doubled
 // tw: exp(-2 pi i t/(N/2)), tw2[j] = exp(-2 pi i j/N) (j <= N/2), isin[k] = 1/(4 sin(pi k/N))
 template <int E>
-__device__ __forceinline__ void op_dct(const LaneProg& P, const LaneOp& op, double* __restrict__ W, double* scratch) {
+__device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double* __restrict__ W, double* scratch) {
   const int TPL = P.TPL, LP = P.LP;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
   const int N = op.i0 - 1, M = N >> 1, mode = op.i1;
@@ -564,7 +584,7 @@ __device__ __forceinline__ void op_dct(const LaneProg& P, const LaneOp& op, doub
       double xm_p = (jm == M) ? xm_m : xin(2 * jm + 1);   // x_{2jm+1}, x_{N+1} = x_{N-1}
       cplx zj = make_double2(xin(2 * j), xo_p - xo_m);
       cplx zmc = make_double2(xin(2 * jm), -(xm_p - xm_m));  // conj(z_{M-j})
-      cplx e = cadd(zj, zmc), d = cmul(csub(zj, zmc), tw2[j]);
+      cplx e = cadd(zj, zmc), d = cmul(csub(zj, zmc), ldg(tw2 + j));
       gj[pi] = make_double2(e.x - d.y, e.y + d.x);           // e + i d
       gm[pi] = make_double2(e.x + d.y, -e.y + d.x);          // conj(e) + i conj(d)
       if (j < M / 2) r0 += xo_p + xm_m;
@@ -590,7 +610,7 @@ __device__ __forceinline__ void op_dct(const LaneProg& P, const LaneOp& op, doub
     else if (k == M) { xk = w[M]; xn = xk; }
     else {
       double zk = w[k], zn = w[N - k];
-      double A = 0.5 * (zk + zn), R = (zn - zk) * isin[k];
+      double A = 0.5 * (zk + zn), R = (zn - zk) * ldg(isin + k);
       xk = A + R; xn = A - R;
     }
     double sk = fs, sn = fs;
@@ -604,7 +624,7 @@ __device__ __forceinline__ void op_dct(const LaneProg& P, const LaneOp& op, doub
 // Real FFT of n points along the lane (Fourier axis): forward r2c is unnormalised,
 // n/2+1 interleaved complex modes; backward c2r carries 1/n and ignores Im of the k=0 and k=n/2 modes.
 template <int E>
-__device__ __forceinline__ void op_rfft(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+__device__ __noinline__ void op_rfft(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
   const int TPL = P.TPL, LP = P.LP;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
   const int n = op.i0, M = n >> 1, mode = op.i1;
@@ -619,7 +639,7 @@ __device__ __forceinline__ void op_rfft(const LaneProg& P, const LaneOp& op, dou
         *reinterpret_cast<cplx*>(w + 2 * M) = make_double2(z.x - z.y, 0.0);
       } else {
         cplx zk = *reinterpret_cast<cplx*>(w + 2 * k), zm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
-        cplx S = cadd(zk, zm), D = cmul(tw2[k], csub(zk, zm));   // w_k D
+        cplx S = cadd(zk, zm), D = cmul(ldg(tw2 + k), csub(zk, zm));   // w_k D
         // X_k = (S - i wD)/2 ; X_{M-k} = conj((S + i wD)/2)
         *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
         if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
@@ -634,7 +654,7 @@ __device__ __forceinline__ void op_rfft(const LaneProg& P, const LaneOp& op, dou
         *reinterpret_cast<cplx*>(w) = make_double2(0.5 * (x0 + xm), -0.5 * (x0 - xm));
       } else {
         cplx xk = *reinterpret_cast<cplx*>(w + 2 * k), xm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
-        cplx S = cadd(xk, xm), D = cmul(cconj(tw2[k]), csub(xk, xm));  // conj(w_k) D'
+        cplx S = cadd(xk, xm), D = cmul(cconj(ldg(tw2 + k)), csub(xk, xm));  // conj(w_k) D'
         // Zc_k = (S + i cD)/2 ; Zc_{M-k} = conj((S - i cD)/2); store conjugates
         *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
         if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
@@ -653,6 +673,7 @@ __device__ __forceinline__ void op_rfft(const LaneProg& P, const LaneOp& op, dou
 
 __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int g) {
   const int TPL = P.TPL, LP = P.LP;
+  const int lb = (blockIdx.x & ((4 / P.LN) - 1)) * P.LN;
   const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
   double* w = W + l * LP;
   switch (op.code) {
@@ -672,16 +693,16 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
     } break;
     case OP_SCALEVEC: {
       const double* v = (const double*)op.p0;
-      for (int e = q; e < op.i0; e += TPL) w[e] *= v[e >> op.i1];
+      for (int e = q; e < op.i0; e += TPL) w[e] *= ldg(v + (e >> op.i1));
     } break;
     case OP_ZEROTAIL:
       for (int e = op.i0 + q; e < LP; e += TPL) w[e] = 0.0;
       break;
     case OP_LANEMASK:
-      if (4 * g + l >= op.i0) for (int e = q; e < LP; e += TPL) w[e] = 0.0;
+      if (4 * g + lb + l >= op.i0) for (int e = q; e < LP; e += TPL) w[e] = 0.0;
       break;
     case OP_ZEROELEM:
-      if (4 * g + l == op.i0 && q == 0) w[op.i1] = 0.0;
+      if (4 * g + lb + l == op.i0 && q == 0) w[op.i1] = 0.0;
       break;
     case OP_SCALE:
       for (int e = q; e < LP; e += TPL) w[e] *= op.a;
@@ -693,21 +714,27 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
 template <int E>
 __global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg P) {
   B2_DYN_SMEM(double, smem);
-  double* W = smem;                       // [4][LP]
-  void* scratch = smem + 4 * P.LP;        // 32 * sizeof(DVec<12>) = 3 KB
-  const int gl = blockIdx.x;              // local lane group (addresses this GPU's slab)
+  double* W = smem;                       // [LN][LP]
+  void* scratch = smem + P.LN * P.LP;     // 32 * sizeof(DVec<12>) = 3 KB
+  const int gl = blockIdx.x / (4 / P.LN); // local lane group (addresses this GPU's slab)
   const int g = P.group0 + gl;            // global lane group (mode indices, transposed stores)
   for (int o = 0; o < P.nops; o++) {
     const LaneOp& op = P.ops[o];
+    long long t0 = 0;
+    if (P.prof) t0 = clock64();
     switch (op.code) {
       case OP_LOAD: op_load(P, op, W, gl); break;
       case OP_STORE: op_store(P, op, W, g, gl); break;
-      case OP_BAND: op_band(P, op, W); break;
-      case OP_DERIV: op_deriv(P, op, W, scratch); break;
-      case OP_FDMA: op_fdma(P, op, W, gl, scratch); break;
+      case OP_BAND: op_band<E + 1>(P, op, W); break;
+      case OP_DERIV: op_deriv<E + 1>(P, op, W, scratch); break;
+      case OP_FDMA: op_fdma<E + 1>(P, op, W, gl, scratch); break;
       case OP_DCT: op_dct<E>(P, op, W, (double*)scratch); break;
       case OP_RFFT: op_rfft<E>(P, op, W); break;
       default: op_pointwise(P, op, W, g); break;
+    }
+    if (P.prof && threadIdx.x == 0) {
+      atomicAdd(P.prof + op.code, (unsigned long long)(clock64() - t0));
+      atomicAdd(P.prof + 32 + op.code, 1ull);
     }
   }
 }

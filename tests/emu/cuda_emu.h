@@ -25,6 +25,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)
@@ -155,6 +156,11 @@ static inline double __shfl_xor_sync(unsigned, double v, int d, int width = 32) 
   const int src = lane ^ d;
   return emu::shfl(v, (src / width == lane / width) ? src : lane);
 }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  std::lock_guard<std::mutex> lk(emu::g_atomic_mutex);
+  unsigned long long o = *p; *p = o + v; return o;
+}
+static inline long long clock64() { return 0; }
 static inline double atomicAdd(double* p, double v) {
   std::lock_guard<std::mutex> lk(emu::g_atomic_mutex);
   double o = *p; *p = o + v; return o;
