@@ -1405,13 +1405,17 @@ static int nav_update_fused(b2_navier* nv) {
     const int P1loc = P1 / ctx->nranks;
     Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_TRANS | ST_PLAIN);
     RET(run_pass(so, 0, y));
+    RET(gemm_mark(ctx));
     CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->fwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
+    RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x; x.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x.store(nv->U1, ps->m0, ST_TRANS);
     RET(run_pass(so, 1, x));
     Prog y2; y2.load(nv->U1, byp.m); y2.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_TRANS | ST_PLAIN);
     RET(run_pass(so, 0, y2));
+    RET(gemm_mark(ctx));
     CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->bwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
+    RET(gemm_mark(ctx));
     ctx->launches++;
     Prog x2; x2.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, ps->m0, ST_TRANS);
     RET(run_pass(so, 1, x2));

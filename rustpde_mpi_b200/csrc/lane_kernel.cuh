@@ -564,59 +564,54 @@ __device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double*
   const cplx* tw = (const cplx*)op.p0; const cplx* tw2 = (const cplx*)op.p1; const double* isin = (const double*)op.p2;
   double* w = W + l * LP;
   constexpr int NP = E / 2 + 1;
-  // ---- pre: x -> g (N/2 complex), pairs (j, M-j) ----
+  const cplx* w2 = reinterpret_cast<const cplx*>(w);
+  // ---- pre: x -> g (N/2 complex), pairs (j, M-j); branch-free, 16-byte shared-memory reads ----
   cplx gj[NP], gm[NP];
   double r0 = 0.0;
-  auto xin = [&](int i) -> double {  // input sample with the backward-mode pre-scaling folded in
-    double v = w[i];
-    if (mode == 1) { if (i & 1) v = -v; if (i == 0 || i == N) v *= 2.0; }
-    return v;
-  };
+  const double sg = (mode == 1) ? -1.0 : 1.0, endf = (mode == 1) ? 2.0 : 1.0;   // backward: y_k = (-1)^k c_k, ends doubled
 #pragma unroll
   for (int pi = 0; pi < NP; pi++) {
-    int j = q + pi * TPL;
-    gj[pi] = make_double2(0, 0); gm[pi] = make_double2(0, 0);
-    if (j <= M / 2) {
-      int jm = M - j;
-      double xo_p = xin(2 * j + 1);                       // x_{2j+1}
-      double xo_m = (j == 0) ? xo_p : xin(2 * j - 1);     // x_{2j-1}, x_{-1} = x_1
-      double xm_m = xin(2 * jm - 1);                      // x_{2jm-1}
-      double xm_p = (jm == M) ? xm_m : xin(2 * jm + 1);   // x_{2jm+1}, x_{N+1} = x_{N-1}
-      cplx zj = make_double2(xin(2 * j), xo_p - xo_m);
-      cplx zmc = make_double2(xin(2 * jm), -(xm_p - xm_m));  // conj(z_{M-j})
-      cplx e = cadd(zj, zmc), d = cmul(csub(zj, zmc), ldg(tw2 + j));
-      gj[pi] = make_double2(e.x - d.y, e.y + d.x);           // e + i d
-      gm[pi] = make_double2(e.x + d.y, -e.y + d.x);          // conj(e) + i conj(d)
-      if (j < M / 2) r0 += xo_p + xm_m;
-    }
+    const int j0 = q + pi * TPL;
+    const int j = j0 <= M / 2 ? j0 : M / 2, jm = M - j;
+    const cplx pj = w2[j], pjl = w2[j > 0 ? j - 1 : 0], pm = w2[jm], pml = w2[jm - 1];
+    const double xo_p = sg * pj.y;                              // x_{2j+1}
+    const double xo_m = (j == 0) ? xo_p : sg * pjl.y;           // x_{2j-1}, x_{-1} = x_1
+    const double xm_m = sg * pml.y;                             // x_{2jm-1}
+    const double xm_p = (jm == M) ? xm_m : sg * pm.y;           // x_{2jm+1}, x_{N+1} = x_{N-1}
+    const cplx zj = make_double2(pj.x * (j == 0 ? endf : 1.0), xo_p - xo_m);
+    const cplx zmc = make_double2(pm.x * (jm == M ? endf : 1.0), -(xm_p - xm_m));   // conj(z_{M-j})
+    const cplx e = cadd(zj, zmc), d = cmul(csub(zj, zmc), ldg(tw2 + j));
+    gj[pi] = make_double2(e.x - d.y, e.y + d.x);           // e + i d
+    gm[pi] = make_double2(e.x + d.y, -e.y + d.x);          // conj(e) + i conj(d)
+    r0 += (j0 < M / 2) ? (xo_p + xm_m) : 0.0;
   }
   r0 = 2.0 * lane_sum(r0, TPL, scratch);   // R_0 = 2 * sum of odd samples
   __syncthreads();
 #pragma unroll
   for (int pi = 0; pi < NP; pi++) {
-    int j = q + pi * TPL;
-    if (j <= M / 2) {
-      *reinterpret_cast<cplx*>(w + 2 * j) = gj[pi];
-      if (j > 0 && j < M / 2) *reinterpret_cast<cplx*>(w + 2 * (M - j)) = gm[pi];
-    }
+    const int j = q + pi * TPL;
+    if (j <= M / 2) *reinterpret_cast<cplx*>(w + 2 * j) = gj[pi];
+    if (j > 0 && j < M / 2) *reinterpret_cast<cplx*>(w + 2 * (M - j)) = gm[pi];
   }
   __syncthreads();
   lane_fft<E>(W, LP, M, TPL, tw);
-  // ---- post: Z (N reals) -> X (N+1), pairs (k, N-k) ----
+  // ---- post: Z (N reals) -> X (N+1), pairs (k, N-k), 1 <= k <= M-1 in a branch-free unrolled loop ----
   const double fs = (mode == 0) ? 1.0 / N : 0.5;
-  for (int k = q; k <= M; k += TPL) {
-    double xk, xn;
-    if (k == 0) { double z0 = w[0]; xk = z0 + r0; xn = z0 - r0; if (mode == 0) { xk *= 0.5; xn *= 0.5; } }
-    else if (k == M) { xk = w[M]; xn = xk; }
-    else {
-      double zk = w[k], zn = w[N - k];
-      double A = 0.5 * (zk + zn), R = (zn - zk) * ldg(isin + k);
-      xk = A + R; xn = A - R;
-    }
-    double sk = fs, sn = fs;
-    if (mode == 0) { if (k & 1) sk = -fs; if ((N - k) & 1) sn = -fs; }
-    w[k] = xk * sk;
-    if (k != M) w[N - k] = xn * sn;
+#pragma unroll
+  for (int pi = 0; pi < E + 1; pi++) {
+    const int k0 = q + pi * TPL;
+    const bool ok = k0 >= 1 && k0 <= M - 1;
+    const int k = ok ? k0 : 1;
+    const double zk = w[k], zn = w[N - k];
+    const double A = 0.5 * (zk + zn), R = (zn - zk) * ldg(isin + k);
+    const double sk = (mode == 0 && (k & 1)) ? -fs : fs;      // N is even: k and N-k have the same parity
+    if (ok) { w[k] = (A + R) * sk; w[N - k] = (A - R) * sk; }
+  }
+  if (q == 0) {   // k = 0 (and N), k = M: untouched by the loop above
+    const double z0 = w[0], e0 = (mode == 0) ? 0.5 * fs : fs;
+    w[0] = (z0 + r0) * e0;
+    w[N] = (z0 - r0) * e0;
+    w[M] = w[M] * ((mode == 0 && (M & 1)) ? -fs : fs);
   }
   __syncthreads();
 }
