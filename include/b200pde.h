@@ -56,6 +56,8 @@ int b2_ctx_timer_stop(b2_ctx* ctx, double* ms);
 int b2_ctx_launch_count(const b2_ctx* ctx, long long* kernels_launched);
 /* profiling aid: per-op cycle counters of the lane kernel; out64[code] = cycles, out64[32+code] = calls */
 int b2_ctx_opprof(b2_ctx* ctx, int on, unsigned long long* out64);
+/* memory-pipeline probe of the lane kernel (tools/copyprobe.py); not part of the reference surface */
+int b2_debug_copy(b2_space* sp, int mode, int reps, double* ms);
 /* read (and reset) the time spent in the dense Poisson GEMMs since profiling was switched on */
 int b2_ctx_profile(b2_ctx* ctx, int on, double* gemm_ms);
 int b2_ctx_heap_handle(b2_ctx* ctx, void* handle64 /* 64 bytes out */);

@@ -27,6 +27,7 @@ SYMBOLS = {
     "b2_ctx_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "b2_ctx_profile": (_I, [_P, _I, _DP]),
     "b2_ctx_opprof": (_I, [_P, _I, C.POINTER(C.c_ulonglong)]),
+    "b2_debug_copy": (_I, [_P, _I, _I, C.POINTER(C.c_double)]),
     "b2_ctx_heap_handle": (_I, [_P, _P]),
     "b2_ctx_attach_peers": (_I, [_P, _P]),
     "b2_ctx_nranks": (_I, [_P]),

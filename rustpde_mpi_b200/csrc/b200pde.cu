@@ -264,7 +264,12 @@ int Base1::init(int C, int TPL) {
   return B2_OK;
 }
 
-struct PassCfg { int in_tiles, out_tiles, LP, TPL, C, E, groups, LN; size_t smem; };
+struct PassCfg {
+  int in_tiles, out_tiles, LP, TPL, C, E, groups, LN;
+  bool fast;   // transform-sized lane: N = 2*E*TPL and LP >= N + 4 (lane_fast.cuh)
+  int NT, CH, nch, NS, CHD, nchd, ld_bytes, st_bytes, ld_tx, w_off, ld_off, st_off;   // TMA pipeline geometry (lane_kernel.cuh)
+  size_t smem;
+};
 
 struct b2_space {
   b2_ctx* ctx = nullptr;
@@ -420,16 +425,36 @@ struct Prog {
   }
 };
 
-template <int E> static int launch_E(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
+template <int E, int LN, int TPLC> static int launch_ELT(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
   static size_t set_smem = 0;
   if (c.smem > set_smem) {
-    CK(cudaFuncSetAttribute(lane_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    CK(cudaFuncSetAttribute(lane_kernel<E, LN, TPLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     set_smem = c.smem;
   }
-  B2_LAUNCH(lane_kernel<E>, (c.groups / ctx->nranks) * (4 / c.LN), c.LN * c.TPL, c.smem, ctx->stream, p);
+  B2_LAUNCH((lane_kernel<E, LN, TPLC>), (c.groups / ctx->nranks) * (4 / c.LN), c.NT, c.smem, ctx->stream, p);
   CK(cudaGetLastError());
   return B2_OK;
 }
+// Kernel instances: transform-sized lanes (c.fast) get the compile-time-geometry instance of their (E, LN, TPL);
+// every other geometry runs the generic instance of its (E, LN).
+static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
+#define B2_INST(e, ln, tpl) if (c.fast && c.E == e && c.LN == ln && c.TPL == tpl) return launch_ELT<e, ln, tpl>(ctx, c, p);
+  B2_INST(16, 4, 128) B2_INST(16, 4, 64) B2_INST(16, 4, 32) B2_INST(16, 4, 16) B2_INST(16, 4, 8)
+  B2_INST(16, 2, 256) B2_INST(16, 2, 128)
+  B2_INST(8, 4, 8) B2_INST(4, 4, 8)
+#undef B2_INST
+  if (c.LN == 4) {
+    if (c.E == 16) return launch_ELT<16, 4, 0>(ctx, c, p);
+    if (c.E == 8) return launch_ELT<8, 4, 0>(ctx, c, p);
+    return launch_ELT<4, 4, 0>(ctx, c, p);
+  }
+  if (c.E == 16) return launch_ELT<16, 2, 0>(ctx, c, p);
+  if (c.E == 8) return launch_ELT<8, 2, 0>(ctx, c, p);
+  return launch_ELT<4, 2, 0>(ctx, c, p);
+}
+
+static bool g_use_tma = getenv("B2_NOTMA") == nullptr;     // B2_NOTMA=1: every load/store on the per-thread LDG/STG path (A/B measurements)
+static bool g_use_direct = getenv("B2_NODIRECT") == nullptr; // B2_NODIRECT=1: plain loads/stores go through the ring / staging as well
 
 // orient 0: lanes along axis 1; orient 1: lanes along axis 0
 static int run_pass(b2_space* sp, int orient, Prog& pr) {
@@ -440,18 +465,53 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
   p.group0 = ctx->rank * (c.groups / ctx->nranks); p.groups_per_rank = c.in_tiles / ctx->nranks; p.rank = ctx->rank;
   p.prof = ctx->d_prof; p.LN = c.LN;
+  p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
+  p.w_off = c.w_off; p.ld_off = c.ld_off; p.st_off = c.st_off;
+  p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
   bool exchange = false;
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
       if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
   }
-  ctx->launches++;
-  int r;
-  switch (c.E) {
-    case 4: r = launch_E<4>(ctx, c, p); break;
-    case 8: r = launch_E<8>(ctx, c, p); break;
-    default: r = launch_E<16>(ctx, c, p); break;
+  // TMA views.  Arrays are 4x4-tiled: tile (I, J) at ((I * tiles_per_row) + J) * 128 bytes, element [i][j] inside.
+  //   slab view (loads, same-orientation stores): [16 doubles of a tile][tile J of the lane group][lane group]
+  //   transposed view (transposing stores): tile (J, g) of the destination holds [jl][lane]:
+  //                   [lane 0..3][jl 0..3][g : tile column][J : tile row]
+  const int groups_local = c.groups / ctx->nranks;
+  for (int i = 0; i < p.nops && g_use_tma; i++) {
+    LaneOp& op = p.ops[i];
+    B2TMapDesc d; memset(&d, 0, sizeof(d));
+    if (op.code == OP_LOAD && !(op.i2 & LD_PLAIN)) {
+      const bool direct = g_use_direct && !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
+      d.base = const_cast<void*>(op.p0); d.rank = 3;
+      d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
+      d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
+      d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CH + 1; d.box[2] = 1;
+      op.i2 |= direct ? LD_DIRECT : LD_TMA;
+      for (int k = 0; k < i; k++)
+        if (p.ops[k].code == OP_STORE && p.ops[k].p0 == op.p0) op.i2 |= LD_AFTER_STORE;
+    } else if (op.code == OP_STORE && !(op.i2 & (ST_PLAIN | ST_PEER))) {
+      d.base = const_cast<void*>(op.p0);
+      if (op.i2 & ST_TRANS) {
+        d.rank = 4;
+        d.dim[0] = 4; d.dim[1] = 4; d.dim[2] = (uint64_t)c.out_tiles; d.dim[3] = (uint64_t)c.in_tiles;
+        d.stride[1] = 32; d.stride[2] = 128; d.stride[3] = (uint64_t)c.out_tiles * 128;
+        d.box[0] = c.LN; d.box[1] = 4; d.box[2] = 1; d.box[3] = c.CH;
+        op.i2 |= ST_TMA;
+      } else {
+        const bool direct = g_use_direct && !(op.i2 & ST_ACC) && op.a == 1.0;
+        d.rank = 3;
+        d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
+        d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
+        d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CH; d.box[2] = 1;
+        op.i2 |= direct ? ST_DIRECT : ST_TMA;
+      }
+    } else continue;
+    const int er = b2_encode_tmap(d, &p.tm[i]);
+    if (er) return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(er) + ")");
   }
+  ctx->launches++;
+  const int r = launch_pass(ctx, c, p);
   if (r != B2_OK) return r;
   return exchange ? ctx_barrier(ctx) : B2_OK;
 }
@@ -470,7 +530,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
     const int Nc = N / 2;
     for (int e = want; e >= 4; e /= 2) {
       const int tpl = Nc / e;
-      if (tpl >= 8 && tpl * LN <= 512 && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
+      if (tpl >= 8 && (tpl * LN) % 32 == 0 && tpl * LN <= 512 && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
     }
     return false;
   };
@@ -486,6 +546,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
     bool ok = false;
     if (ln_want == 4 && smem4 <= 227 * 1024) ok = pick(4, want) || pick(4, 16);
     if (!ok) ok = pick(2, want) || pick(2, 16);
+    if (!ok && smem4 <= 227 * 1024) ok = pick(4, want) || pick(4, 16);
     if (!ok) return fail(B2_ERR_UNSUPPORTED, "lane of " + std::to_string(Pl) + " points: no supported thread layout");
   } else {  // no transform along this axis: banded ops only
     c->E = 16; c->LN = 4;
@@ -495,8 +556,32 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
     if (t > 128) return fail(B2_ERR_UNSUPPORTED, "lane too long");
   }
   c->C = c->E + 1;
-  c->smem = ((size_t)c->LN * c->LP + 32 * 12) * sizeof(double);
-  if (c->smem > 227 * 1024) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
+  c->NT = c->LN * c->TPL;
+  c->fast = is_pow2(N) && N >= 64 && N == 2 * c->E * c->TPL && Pl >= N + 4 && getenv("B2_NOFAST") == nullptr;
+  if (c->NT % 32) return fail(B2_ERR_UNSUPPORTED, "compute threads must fill whole warps");
+  // shared memory: [mbarriers 256][scratch][W][NS load slots of CH+1 tiles][3 store slots of CH tiles]
+  const int tile_bytes = c->LN * 32;
+  c->nchd = (c->in_tiles + 255) / 256;                     // direct copies: boxes of <= 256 tiles straight into / out of W
+  c->CHD = roundup((c->in_tiles + c->nchd - 1) / c->nchd, 4 / c->LN);   // box bytes multiple of 128: TMA shared-memory alignment
+  const size_t budget = 227 * 1024, fixed = 256 + B2_SCRATCH;
+  const size_t wbytes = (size_t)roundup(c->nchd * c->CHD * tile_bytes, 128);   // the last direct box may overhang the lane by < nchd tiles
+  if (fixed + wbytes > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
+  c->NS = 2;
+  if (const char* e = getenv("B2_NS")) { int v = atoi(e); if (v >= 1 && v <= B2_MAXLD) c->NS = v; }
+  // short lanes: keep the CTA near 72 KB so that three fit on an SM; long lanes: one CTA owns the SM
+  size_t room = budget - fixed - wbytes;
+  if (wbytes <= 40 * 1024) room = std::min(room, std::max((size_t)8192, (size_t)72 * 1024 - std::min((size_t)72 * 1024, fixed + wbytes)));
+  int chmax = (int)(room / (size_t)(c->NS + B2_ST_SLOTS) / tile_bytes) - 2;
+  if (const char* e = getenv("B2_CH")) { int v = atoi(e); if (v >= 4) chmax = std::min(chmax, v); }
+  chmax = std::max(4, std::min(chmax, 254));
+  c->nch = (c->in_tiles + chmax - 1) / chmax;
+  c->CH = (c->in_tiles + c->nch - 1) / c->nch;
+  c->ld_tx = (c->CH + 1) * tile_bytes;
+  c->ld_bytes = roundup(c->ld_tx, 128);
+  c->st_bytes = roundup(c->CH * tile_bytes, 128);
+  c->w_off = (int)fixed; c->ld_off = c->w_off + (int)wbytes; c->st_off = c->ld_off + c->NS * c->ld_bytes;
+  c->smem = (size_t)c->st_off + (size_t)B2_ST_SLOTS * c->st_bytes;
+  if (c->smem > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
   return B2_OK;
 }
 
@@ -666,7 +751,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     for (int k = 0; k < b0.m; k++) lam[2 * k] = lam[2 * k + 1] = -(double)k * k * c0;
     if (std::fabs(lam[0]) < 1e-10) for (auto& v : lam) v -= 1e-10;
   } else { delete s; return fail(B2_ERR_UNSUPPORTED, "Poisson axis-0 base"); }
-  // per-lane LU of (lap1 + lam_i mass1), src/solver/poisson.rs:222-229, in scan layout
+  // per-lane LU of (lap1 + lam_i mass1), src/solver/poisson.rs:222-229, in scan layout [group][t][q][lane]
   Diags lap1, mass1;
   poisson_axis(b1, c1, &lap1, &mass1);
   const PassCfg& c = sp->cfg[0];
@@ -687,7 +772,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     const int g = (lane - lane0) / 4, l = lane % 4;
     for (int i = 0; i < m1; i++) {
       const int pr = i / 2, q = pr / c.C, t = pr % c.C;
-      const size_t k = ((((size_t)g * c.C + t) * 4 + l) * c.TPL + q) * 2 + (i & 1);
+      const size_t k = ((((size_t)g * c.C + t) * c.TPL + q) * 4 + l) * 2 + (i & 1);
       pfl[k] = lu.fl[i]; pid[k] = lu.id[i]; pu1[k] = lu.u1[i]; pu2[k] = lu.u2[i];
     }
   }
@@ -870,6 +955,31 @@ int b2_ctx_profile(b2_ctx* c, int on, double* gemm_ms) {
   c->gemm_events.clear();
   if (gemm_ms) *gemm_ms = tot;
   c->profile = on != 0;
+  return B2_OK;
+}
+// Memory-pipeline probe (tools/copyprobe.py): `reps` passes of { load a slab, optional DCT, store it (transposed or not) }
+// over a full array of the space, timed with CUDA events.  mode bit 0: transposing store; bit 1: add a backward DCT;
+// bit 2: scale by 2 on load (forces the ring path); bit 3: scale on store (forces the staged path).
+int b2_debug_copy(b2_space* sp, int mode, int reps, double* ms) {
+  double *a = nullptr, *b = nullptr;
+  RET(alloc_zero(sp, &a)); RET(alloc_zero(sp, &b));
+  b2_ctx* ctx = sp->ctx;
+  const Base1& by = sp->b[1];
+  auto pass = [&]() -> int {
+    Prog y; y.load(a, by.rows_ortho, (mode & 4) ? 2.0 : 1.0);
+    if (mode & 2) y.dct(by, 1);
+    y.store(b, by.rows_ortho, (mode & 1) ? ST_TRANS : 0, (mode & 8) ? 2.0 : 1.0);
+    return run_pass(sp, 0, y);
+  };
+  RET(pass());
+  if (!ctx->ev0) { CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; r++) RET(pass());
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float t = 0; CK(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+  *ms = t / reps;
+  ctx_free(ctx, a); ctx_free(ctx, b);
   return B2_OK;
 }
 int b2_ctx_nranks(const b2_ctx* c) { return c->nranks; }

@@ -1,14 +1,20 @@
 // Lane-program kernel: the one CUDA kernel family behind every per-axis operator
 // of the Navier2D spectral hot path.
 //
-// A CTA owns one "lane group" = 4 neighbouring 1-D lanes (pencils) of a 2-D array
-// and keeps them resident in shared memory while it interprets a short program of
-// 1-D operators (load / banded mat-vec / Chebyshev recurrence / banded LU solve /
-// DCT-I / real FFT / masks / store).  Arrays live in HBM in a 4x4 micro-tiled
-// layout (128-byte tiles), so a lane group is ONE contiguous slab on the way in
-// and full 128-byte lines on the way out, whether the store keeps the orientation
-// or transposes it (that is how the x<->y pencil switch happens: every pass of a
-// 2-D operator ends in a transposing store, locally or into a peer GPU's memory).
+// A CTA owns one "lane group" = 4 neighbouring 1-D lanes (pencils) of a 2-D array (or half a group for
+// very long lanes) and keeps them resident in shared memory while it interprets a short program of
+// 1-D operators (load / banded mat-vec / Chebyshev recurrence / banded LU solve / DCT-I / real FFT /
+// masks / store).  Arrays live in HBM in a 4x4 micro-tiled layout (128-byte tiles), so a lane group is ONE
+// contiguous slab, and shared memory keeps exactly that layout (tile J of the group = [lane][4 positions]):
+//   * a plain load is a zero-copy bulk tensor copy (TMA) of the slab into shared memory, a plain store the
+//     reverse; loads that combine with the resident operand (accumulate, multiply, composite->orthonormal
+//     stencil) stream through a small TMA ring that thread 0 keeps full across op boundaries;
+//   * a transposing store (the x<->y pencil switch: every pass of a 2-D operator ends in one) transposes
+//     each 4x4 tile on its way into a staging slot and leaves as ONE 4-D tensor store per chunk -- full
+//     128-byte lines into the transposed array (or, multi-GPU, per-thread stores into the peer's slab);
+//   * threads map lane-fastest (tid -> lane = tid % LN, q = tid / LN), which makes every shared-memory
+//     access of every operator bank-conflict free in this layout and lets the 4 lanes of a group share
+//     each coefficient / twiddle load (one broadcast request instead of four).
 //
 // sm_100a only.  No CPU fallback, no library calls in here.
 #pragma once
@@ -16,13 +22,17 @@
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
-#define B2_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define B2_DYN_SMEM(type, name) extern __shared__ __align__(1024) type name[]
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 #include <stdint.h>
+#include "async_ops.cuh"
 
 #define B2_MAXOPS 24
 #define B2_MAXPEERS 8
+#define B2_ST_SLOTS 3    // store-staging slots (3: one CTA barrier per chunk, see store_staged)
+#define B2_MAXLD 8       // max load-ring slots
+#define B2_SCRATCH 8192  // bytes of scan scratch (16 warps x 4 lanes x (Aff2 map + state))
 
 enum LaneOpCode {
   OP_LOAD = 1,     // W = [W +|*] a * src           i0=len  i2=flags(LD_*)       p0=src (p1 = stencil coefficients)
@@ -39,8 +49,13 @@ enum LaneOpCode {
   OP_ZEROELEM = 12,// W[lane i0][pos i1] = 0 (global lane index)
   OP_SCALE = 13,   // W *= a
 };
-enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8 };  // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
-enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16 };
+enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
+       LD_TMA = 16,          // set by the launcher: the slab streams through the TMA ring (tensor map tm[op])
+       LD_AFTER_STORE = 32,  // set by the launcher: the source was stored earlier in this program (flush stores first)
+       LD_DIRECT = 64 };     // set by the launcher: zero-copy TMA straight into W (plain load, a == 1)
+enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16,
+       ST_TMA = 32,          // set by the launcher: staged, bulk tensor store / reduction
+       ST_DIRECT = 64 };     // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
 enum { FD_PERLANE = 1, FD_NOU2 = 2 };
 
 struct LaneOp {
@@ -54,19 +69,26 @@ struct LaneOp {
 
 struct LaneProg {
   int nops;
-  int LP;         // shared-memory lane pitch in doubles (multiple of 4, >= every length used)
+  int LP;         // lane pitch in doubles = 4 * in_tiles (>= every length used)
   int in_tiles;   // 4x4 tiles per lane of arrays in the orientation being read
   int out_tiles;  // tiles per row of the transposed orientation (= number of lane groups)
-  int TPL;        // threads per lane (blockDim.x = 4*TPL)
+  int TPL;        // threads per lane
   int C;          // pairs per thread per lane (= E+1 of the kernel instance), 2*C*TPL >= LP
   int group0;     // first lane group of this launch (multi-GPU slabs)
   int groups_per_rank;  // for ST_PEER: owner(J) = J / groups_per_rank (destination orientation)
   int rank;       // this GPU's rank (peer table index)
-  int pad_;
-  unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
   int LN;         // lanes per CTA: 4 (a whole lane group) or 2 (half a group; grid = 2 x groups)
-  int pad2_;
+  int NT;         // threads per CTA = LN*TPL (multiple of 32)
+  // TMA pipeline geometry
+  int CH, nch, NS;            // ring / staging: tiles per chunk, chunks per lane, load-ring slots (one halo tile in front)
+  int CHD, nchd;              // direct copies: tiles per box (<= 256), boxes per lane
+  int ld_bytes, st_bytes;     // slot pitch of the load ring / the store staging (multiples of 128)
+  int ld_tx;                  // bytes one ring box delivers ((CH+1) tiles x LN lanes x 32)
+  int w_off, ld_off, st_off;  // byte offsets inside dynamic shared memory (128-aligned)
+  int bulk1d;                 // LN == 4: the slab is contiguous, so slab-shaped copies are plain 1-D bulk copies (no tensor map)
+  unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
   LaneOp ops[B2_MAXOPS];
+  B2TMap tm[B2_MAXOPS];       // tensor map of op i (3-D slab view, or 4-D transposed view for transposing stores)
 };
 
 #ifdef B2_EMU
@@ -80,6 +102,21 @@ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x +
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
 __device__ __forceinline__ cplx cmulmi(cplx a) { return make_double2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ cplx csq(cplx a) { return make_double2(fma(a.x, a.x, -a.y * a.y), (a.x + a.x) * a.y); }
+__device__ __forceinline__ double2 d2(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ double2 d2fma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory layout of the resident lanes = the slab layout: tile J holds [lane][4 positions].
+// ---------------------------------------------------------------------------------------------
+template <int LN> struct Lay {
+  static constexpr int LOG = (LN == 4) ? 2 : 1;   // log2 LN
+  static constexpr int LSH = LOG + 1;             // log2 (16-byte pieces per tile)
+  // pair p = elements (2p, 2p+1) of a lane, in double2 units relative to the lane's base (W2 + 2*lane)
+  static __device__ __forceinline__ int pix(int p) { return (p >> 1) * (1 << LSH) + (p & 1); }
+  // element e of a lane, in double units relative to the lane's base (W + 4*lane)
+  static __device__ __forceinline__ int eix(int e) { return (e >> 2) * (1 << (LSH + 1)) + (e & 3); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Radix-R DFT in registers (forward, e^{-2 pi i jk/R}), natural order in and out.
@@ -137,104 +174,158 @@ template <> struct Dft<16> {
   }
 };
 
+// v[r] *= w1^r for r = 1..R-1.  The powers are generated in registers from the one loaded twiddle (chain
+// depth <= 4 multiplications, error a few ulp) instead of R-1 dependent table loads per butterfly.
+template <int R> struct Twid;
+template <> struct Twid<2> { static __device__ __forceinline__ void run(cplx* v, cplx w1) { v[1] = cmul(v[1], w1); } };
+template <> struct Twid<4> {
+  static __device__ __forceinline__ void run(cplx* v, cplx w1) {
+    const cplx w2 = csq(w1);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], cmul(w2, w1));
+  }
+};
+template <> struct Twid<8> {
+  static __device__ __forceinline__ void run(cplx* v, cplx w1) {
+    const cplx w2 = csq(w1), w3 = cmul(w2, w1), w4 = csq(w2);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], csq(w3)); v[7] = cmul(v[7], cmul(w4, w3));
+  }
+};
+template <> struct Twid<16> {
+  static __device__ __forceinline__ void run(cplx* v, cplx w1) {
+    const cplx w2 = csq(w1), w3 = cmul(w2, w1), w4 = csq(w2);
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    const cplx w5 = cmul(w4, w1), w7 = cmul(w4, w3), w8 = csq(w4);
+    v[5] = cmul(v[5], w5); v[6] = cmul(v[6], csq(w3)); v[7] = cmul(v[7], w7); v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], csq(w5)); v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], csq(w7));
+    v[15] = cmul(v[15], cmul(w8, w7));
+  }
+};
+template <int V> struct Log2 { static constexpr int v = 1 + Log2<V / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
 // ---------------------------------------------------------------------------------------------
 // shuffle helpers for small structs of doubles
 // ---------------------------------------------------------------------------------------------
 template <int K> struct DVec { double d[K]; };
-template <int K> __device__ __forceinline__ DVec<K> shfl_up(const DVec<K>& m, int delta, int width) {
+template <int K> __device__ __forceinline__ DVec<K> shfl_up(const DVec<K>& m, int delta) {
   DVec<K> r;
 #pragma unroll
-  for (int i = 0; i < K; i++) r.d[i] = __shfl_up_sync(0xffffffffu, m.d[i], delta, width);
+  for (int i = 0; i < K; i++) r.d[i] = __shfl_up_sync(0xffffffffu, m.d[i], delta, 32);
   return r;
 }
-template <int K> __device__ __forceinline__ DVec<K> shfl_down(const DVec<K>& m, int delta, int width) {
+template <int K> __device__ __forceinline__ DVec<K> shfl_down(const DVec<K>& m, int delta) {
   DVec<K> r;
 #pragma unroll
-  for (int i = 0; i < K; i++) r.d[i] = __shfl_down_sync(0xffffffffu, m.d[i], delta, width);
+  for (int i = 0; i < K; i++) r.d[i] = __shfl_down_sync(0xffffffffu, m.d[i], delta, 32);
   return r;
 }
 
-// Affine maps used by the lane recurrences.  "then(f, s)" = apply f first, then s.
-// First order, two independent parities:  y -> A y + B.      d = {A0,B0,A1,B1}
+// Affine maps used by the lane recurrences.  "then(f, s)" = apply f first, then s; "apply(m, v)" = m(v).
+// First order, two independent parities:  y -> A y + B.      d = {A0,B0,A1,B1};  state = {y0, y1}
 struct Aff1 {
   typedef DVec<4> V;
+  typedef DVec<2> S;
   static __device__ __forceinline__ V identity() { V v; v.d[0] = 1; v.d[1] = 0; v.d[2] = 1; v.d[3] = 0; return v; }
+  static __device__ __forceinline__ S zero() { S s; s.d[0] = 0; s.d[1] = 0; return s; }
   static __device__ __forceinline__ V then(const V& f, const V& s) {
     V r;
     r.d[0] = s.d[0] * f.d[0]; r.d[1] = fma(s.d[0], f.d[1], s.d[1]);
     r.d[2] = s.d[2] * f.d[2]; r.d[3] = fma(s.d[2], f.d[3], s.d[3]);
     return r;
   }
+  static __device__ __forceinline__ S apply(const V& m, const S& v) {
+    S r; r.d[0] = fma(m.d[0], v.d[0], m.d[1]); r.d[1] = fma(m.d[2], v.d[1], m.d[3]); return r;
+  }
 };
-// Second order, two parities: state (u,w) -> P (u,w) + p.   d = {P00,P01,P10,P11,p0,p1} x 2
+// Second order, two parities: state (u,w) -> P (u,w) + p.   d = {P00,P01,P10,P11,p0,p1} x 2;  state = {u0,w0,u1,w1}
 struct Aff2 {
   typedef DVec<12> V;
+  typedef DVec<4> S;
   static __device__ __forceinline__ V identity() {
     V v;
 #pragma unroll
     for (int h = 0; h < 2; h++) { v.d[6*h+0] = 1; v.d[6*h+1] = 0; v.d[6*h+2] = 0; v.d[6*h+3] = 1; v.d[6*h+4] = 0; v.d[6*h+5] = 0; }
     return v;
   }
+  static __device__ __forceinline__ S zero() { S s; s.d[0] = s.d[1] = s.d[2] = s.d[3] = 0; return s; }
   static __device__ __forceinline__ V then(const V& f, const V& s) {
     V r;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const double* F = f.d + 6 * h; const double* S = s.d + 6 * h; double* R = r.d + 6 * h;
-      R[0] = S[0] * F[0] + S[1] * F[2]; R[1] = S[0] * F[1] + S[1] * F[3];
-      R[2] = S[2] * F[0] + S[3] * F[2]; R[3] = S[2] * F[1] + S[3] * F[3];
-      R[4] = S[0] * F[4] + S[1] * F[5] + S[4];
-      R[5] = S[2] * F[4] + S[3] * F[5] + S[5];
+      const double* F = f.d + 6 * h; const double* S_ = s.d + 6 * h; double* R = r.d + 6 * h;
+      R[0] = S_[0] * F[0] + S_[1] * F[2]; R[1] = S_[0] * F[1] + S_[1] * F[3];
+      R[2] = S_[2] * F[0] + S_[3] * F[2]; R[3] = S_[2] * F[1] + S_[3] * F[3];
+      R[4] = S_[0] * F[4] + S_[1] * F[5] + S_[4];
+      R[5] = S_[2] * F[4] + S_[3] * F[5] + S_[5];
+    }
+    return r;
+  }
+  static __device__ __forceinline__ S apply(const V& m, const S& v) {
+    S r;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const double* M = m.d + 6 * h;
+      r.d[2*h+0] = M[0] * v.d[2*h] + M[1] * v.d[2*h+1] + M[4];
+      r.d[2*h+1] = M[2] * v.d[2*h] + M[3] * v.d[2*h+1] + M[5];
     }
     return r;
   }
 };
 
-// Exclusive scan of per-thread maps across the TPL threads of one lane.
-// PREFIX: result = composition of the maps of threads q' < q (lowest applied first).
-// SUFFIX: result = composition of the maps of threads q' > q (highest applied first).
-// scratch: shared, >= 4 lanes * 8 warps entries of M::V.  All threads of the CTA must call.
-template <class M, bool SUFFIX>
-__device__ __forceinline__ typename M::V lane_scan_excl(typename M::V mine, int TPL, typename M::V* scratch) {
+// State entering each thread's chunk: the maps of the threads before it (PREFIX: q' < q, lowest applied first;
+// SUFFIX: q' > q, highest applied first) applied to the zero state.  Threads of a lane sit LN apart in a warp
+// (32/LN of them per warp); warp totals go through shared memory and ONE thread per lane runs the short
+// serial recurrence over the warps (vector recurrence only -- no matrix products on the critical path).
+// scratch: >= 16 warps * LN lanes * (V + S).  All threads of the CTA must call.
+template <class M, bool SUFFIX, int LN>
+__device__ __forceinline__ typename M::S lane_scan_state(typename M::V mine, int TPL, void* scratch) {
   typedef typename M::V V;
-  const int tid = threadIdx.x;
-  const int q = tid % TPL, lane = tid / TPL;
-  const int width = TPL < 32 ? TPL : 32;
-  const int qi = q % width;   // position inside the shuffle segment
+  typedef typename M::S S;
+  constexpr int QW = 32 / LN;                    // threads of one lane inside a warp
+  const int tid = threadIdx.x, l = tid & (LN - 1);
+  const int qi = (tid & 31) >> Lay<LN>::LOG;     // position inside the warp's segment of the lane
+  const int width = TPL < QW ? TPL : QW;
   V inc = mine;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < QW; d <<= 1) {
     if (d < width) {
-      V o = SUFFIX ? shfl_down(inc, d, width) : shfl_up(inc, d, width);
+      V o = SUFFIX ? shfl_down(inc, d * LN) : shfl_up(inc, d * LN);
       bool take = SUFFIX ? (qi + d < width) : (qi >= d);
       if (take) inc = M::then(o, inc);
     }
   }
-  V exc = SUFFIX ? shfl_down(inc, 1, width) : shfl_up(inc, 1, width);
+  V exc = SUFFIX ? shfl_down(inc, LN) : shfl_up(inc, LN);
   if (SUFFIX ? (qi == width - 1) : (qi == 0)) exc = M::identity();
-  if (TPL > 32) {
-    const int nw = TPL / 32, w = q / 32;
-    if (SUFFIX ? (qi == 0) : (qi == 31)) scratch[lane * 8 + w] = inc;
-    __syncthreads();
-    V carry = M::identity();
-    if (SUFFIX) { for (int k = nw - 1; k > w; k--) carry = M::then(carry, scratch[lane * 8 + k]); }
-    else        { for (int k = 0; k < w; k++) carry = M::then(carry, scratch[lane * 8 + k]); }
-    exc = M::then(carry, exc);
-    __syncthreads();
+  if (TPL <= QW) return M::apply(exc, M::zero());
+  const int nw = TPL / QW, w = tid >> 5;
+  V* tot = reinterpret_cast<V*>(scratch);                  // [warp][lane] warp totals
+  S* ent = reinterpret_cast<S*>(tot + 16 * LN);            // [warp][lane] state entering the warp
+  if (SUFFIX ? (qi == 0) : (qi == QW - 1)) tot[w * LN + l] = inc;
+  __syncthreads();
+  if (tid < LN) {
+    S s = M::zero();
+    if (SUFFIX) { for (int k = nw - 1; k >= 0; k--) { ent[k * LN + l] = s; s = M::apply(tot[k * LN + l], s); } }
+    else        { for (int k = 0; k < nw; k++) { ent[k * LN + l] = s; s = M::apply(tot[k * LN + l], s); } }
   }
-  return exc;
+  __syncthreads();
+  return M::apply(exc, ent[w * LN + l]);
 }
 
 // sum over the TPL threads of a lane (result valid in every thread of the lane)
+template <int LN>
 __device__ __forceinline__ double lane_sum(double v, int TPL, double* scratch) {
-  const int tid = threadIdx.x, q = tid % TPL, lane = tid / TPL;
-  const int width = TPL < 32 ? TPL : 32;
-  for (int d = width >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d, width);
-  if (TPL > 32) {
-    const int nw = TPL / 32, w = q / 32;
-    if ((q & 31) == 0) scratch[lane * 8 + w] = v;
+  constexpr int QW = 32 / LN;
+  const int tid = threadIdx.x, l = tid & (LN - 1);
+  const int width = TPL < QW ? TPL : QW;
+  for (int d = width >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d * LN, 32);
+  if (TPL > QW) {
+    const int nw = TPL / QW, w = tid >> 5;
+    if ((tid & 31) < LN) scratch[w * LN + l] = v;
     __syncthreads();
     double s = 0;
-    for (int k = 0; k < nw; k++) s += scratch[lane * 8 + k];
+    for (int k = 0; k < nw; k++) s += scratch[k * LN + l];
     __syncthreads();
     v = s;
   }
@@ -242,31 +333,150 @@ __device__ __forceinline__ double lane_sum(double v, int TPL, double* scratch) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// ops
+// Shared memory: [mbarriers 256 B][scan scratch][W = LN lanes, slab layout][load ring][store staging]
+//   full[s] / empty[s] : load-ring slot s filled by the copy engine / drained by all warps
+//   dfull              : a direct (zero-copy) load has landed in W
+// Thread 0 is the producer: it walks the program's ring loads with a prefetch cursor and keeps the ring
+// full -- NS chunks are requested before the first op runs, and every drained chunk immediately requests
+// the next one, across op boundaries (the first chunks of the next operand arrive while the warps are still
+// transforming the current one).  Stores leave through bulk tensor stores (async-group completion), so no
+// warp ever waits for DRAM on the way out.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void op_load(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl) {
-  const int T = blockDim.x, LP = P.LP;
-  const int LN = P.LN, psh = LN == 4 ? 3 : 2, pm = 2 * LN - 1;   // 2*LN 16-byte pieces per tile belong to this CTA
-  const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;             // first lane of the group handled by this CTA
-  const int npieces = LN * LP / 2;
-  const int len = op.i0;
+struct SmemView {
+  uint64_t* full; uint64_t* empty; uint64_t* dfull;
+  void* scratch; double* W; char* ld; char* st;
+};
+__device__ __forceinline__ SmemView smem_view(const LaneProg& P, char* base) {
+  SmemView v;
+  v.full = reinterpret_cast<uint64_t*>(base); v.empty = v.full + B2_MAXLD; v.dfull = v.full + 2 * B2_MAXLD;
+  v.scratch = base + 256; v.W = reinterpret_cast<double*>(base + P.w_off); v.ld = base + P.ld_off; v.st = base + P.st_off;
+  return v;
+}
+struct Prefetch { int it, op, c, gl, lb; unsigned dphase; };   // used by thread 0 (dphase by everyone)
+__device__ __forceinline__ int next_ring_load(const LaneProg& P, int o) {
+  while (o < P.nops && !(P.ops[o].code == OP_LOAD && (P.ops[o].i2 & LD_TMA))) o++;
+  return o;
+}
+// Request the next chunk of the program (thread 0).  A load flagged LD_AFTER_STORE re-reads an array this CTA
+// stored earlier in the program: it is only requested from inside its own op (cur_op), after the stores drained.
+__device__ __forceinline__ bool prefetch_next(const LaneProg& P, const SmemView& sv, Prefetch& pf, int cur_op) {
+  if (pf.op >= P.nops) return false;
+  if ((P.ops[pf.op].i2 & LD_AFTER_STORE) && pf.op != cur_op) return false;
+  const int slot = pf.it % P.NS; const unsigned ph = (unsigned)(pf.it / P.NS) & 1u;
+  mbar_wait(&sv.empty[slot], ph ^ 1u);
+  if (P.bulk1d) {   // contiguous slab: tiles [J0-1, J0+CH) clipped to the lane, no halo in front of the first chunk
+    const int J0 = pf.c * P.CH, t0 = J0 > 0 ? J0 - 1 : 0, t1 = min(J0 + P.CH, P.in_tiles);
+    const uint32_t bytes = (uint32_t)(t1 - t0) * 128u;
+    mbar_arrive_expect_tx(&sv.full[slot], bytes);
+    bulk_load_1d(sv.ld + (size_t)slot * P.ld_bytes + (size_t)(t0 - (J0 - 1)) * 128,
+                 static_cast<const char*>(P.ops[pf.op].p0) + ((size_t)pf.gl * P.in_tiles + t0) * 128, bytes, &sv.full[slot]);
+  } else {
+    mbar_arrive_expect_tx(&sv.full[slot], (uint32_t)P.ld_tx);
+    tma_load_3d(sv.ld + (size_t)slot * P.ld_bytes, &P.tm[pf.op], pf.lb * 4, pf.c * P.CH - 1, pf.gl, &sv.full[slot]);
+  }
+  pf.it++;
+  if (++pf.c == P.nch) { pf.c = 0; pf.op = next_ring_load(P, pf.op + 1); }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// loads
+// ---------------------------------------------------------------------------------------------
+// W = src: the slab lands in W as it is (zero-copy); elements at and beyond len are cleared afterwards.
+template <int LN>
+__device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, Prefetch& pf) {
+  if (threadIdx.x == 0) {
+    if (op.i2 & LD_AFTER_STORE) bulk_wait<0>();
+    if (P.bulk1d) {
+      const char* src = static_cast<const char*>(op.p0) + (size_t)pf.gl * P.in_tiles * 128;
+      mbar_arrive_expect_tx(sv.dfull, (uint32_t)P.in_tiles * 128u);
+      for (int c = 0; c < P.nchd; c++) {
+        const int t0 = c * P.CHD, t1 = min(t0 + P.CHD, P.in_tiles);
+        bulk_load_1d(reinterpret_cast<char*>(sv.W) + (size_t)t0 * 128, src + (size_t)t0 * 128, (uint32_t)(t1 - t0) * 128u, sv.dfull);
+      }
+    } else {
+      mbar_arrive_expect_tx(sv.dfull, (uint32_t)(P.nchd * P.CHD * LN * 32));
+      for (int c = 0; c < P.nchd; c++)
+        tma_load_3d(reinterpret_cast<char*>(sv.W) + (size_t)c * P.CHD * LN * 32, tm, pf.lb * 4, c * P.CHD, pf.gl, sv.dfull);
+    }
+  }
+  mbar_wait(sv.dfull, pf.dphase);
+  pf.dphase ^= 1u;
+  const int len = op.i0, ntail = P.LP - len;
+  for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
+    const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
+    sv.W[4 * l + Lay<LN>::eix(e)] = 0.0;
+  }
+  __syncthreads();
+}
+
+// W = [W +|*] a * src, src arriving through the ring.  Slot layout: [tile t = 0..CH][lane][4] -- the slab's own
+// layout, so the combine is elementwise; t = 0 is the halo tile in front of the chunk (the composite ->
+// orthonormal stencil needs element j-2 of the same lane).
+template <int LN>
+__device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int o, const SmemView& sv, int& ld_it, Prefetch& pf) {
+  constexpr int LSH = Lay<LN>::LSH;
+  const int NT = P.NT, len = op.i0;
   const double a = op.a;
-  const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, plain = op.i2 & LD_PLAIN;
+  const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, sten = op.i2 & LD_STENCIL;
+  const double* sc = reinterpret_cast<const double*>(op.p1);
+  double2* W2 = reinterpret_cast<double2*>(sv.W);
+  if ((op.i2 & LD_AFTER_STORE) && threadIdx.x == 0) {   // the stored data must have landed before it is read back
+    bulk_wait<0>();
+    while (pf.it - ld_it < P.NS && prefetch_next(P, sv, pf, o)) {}
+  }
+  const int npc = P.CH << LSH;
+  for (int c = 0; c < P.nch; c++, ld_it++) {
+    const int slot = ld_it % P.NS; const unsigned ph = (unsigned)(ld_it / P.NS) & 1u;
+    mbar_wait(&sv.full[slot], ph);
+    const double2* st = reinterpret_cast<const double2*>(sv.ld + (size_t)slot * P.ld_bytes) + (1 << LSH);
+    const int J0 = c * P.CH;
+#pragma unroll 2
+    for (int pc = threadIdx.x; pc < npc; pc += NT) {
+      const int J = J0 + (pc >> LSH), j0 = 4 * J + 2 * (pc & 1);
+      if (J >= P.in_tiles) continue;
+      double2 v = st[pc];
+      if (sten && j0 >= 2) {
+        const double2 u = (pc & 1) ? st[pc - 1] : st[pc - (1 << LSH) + 1];
+        const double2 cf = ldg(reinterpret_cast<const double2*>(sc + j0));
+        v.x = fma(cf.x, u.x, v.x); v.y = fma(cf.y, u.y, v.y);
+      }
+      v.x = (j0 < len) ? v.x * a : 0.0;
+      v.y = (j0 + 1 < len) ? v.y * a : 0.0;
+      double2* w = W2 + ((size_t)J0 << LSH) + pc;
+      if (acc) { const double2 ov = *w; v.x += ov.x; v.y += ov.y; }
+      else if (mul) { const double2 ov = *w; v.x *= ov.x; v.y *= ov.y; }
+      *w = v;
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&sv.empty[slot]);
+    if (threadIdx.x == 0) prefetch_next(P, sv, pf, o);   // waits until every warp has released a slot, then refills it
+  }
+  __syncthreads();
+}
+
+// Per-thread path (row-major "plain" sources written by the GEMM; everything when TMA is switched off).
+template <int LN, int U>   // U = 16-byte global loads in flight per thread
+__device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, const SmemView& sv, int gl, int lb) {
+  constexpr int LSH = Lay<LN>::LSH;
+  const int T = P.NT, len = op.i0;
+  const int npieces = P.in_tiles << LSH;
+  const double a = op.a;
+  const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, plain = op.i2 & LD_PLAIN, sten = op.i2 & LD_STENCIL;
   const double2* src = reinterpret_cast<const double2*>(op.p0);
   const size_t slab = (size_t)gl * P.in_tiles * 8;  // in double2 units
   const double* sc = reinterpret_cast<const double*>(op.p1);
-  const bool sten = op.i2 & LD_STENCIL;
-  constexpr int U = 8;   // loads in flight per thread: all U global loads are issued before the first use
+  double2* W2 = reinterpret_cast<double2*>(sv.W);
   for (int p0 = threadIdx.x; p0 < npieces; p0 += U * T) {
     double2 v[U], u[U];
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      const int pidx = p0 + k * T;
-      const int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      const int pc = p0 + k * T;
+      const int J = pc >> LSH, l = (pc >> 1) & (LN - 1), j0 = 4 * J + (pc & 1) * 2;
       v[k] = make_double2(0.0, 0.0); u[k] = make_double2(0.0, 0.0);
-      if (pidx < npieces && J < P.in_tiles && j0 < len) {
+      if (pc < npieces && j0 < len) {
         v[k] = plain ? src[((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1]
-                     : src[slab + (size_t)J * 8 + (lb + l) * 2 + (pidx & 1)];
+                     : src[slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1)];
         if (sten && j0 >= 2) {   // composite -> orthonormal on the fly: + p1[j] * src[j-2]  (tiled sources only)
           const int jm = j0 - 2;
           u[k] = src[slab + ((size_t)(jm >> 2) * 16 + (lb + l) * 4 + (jm & 3)) / 2];
@@ -275,38 +485,134 @@ __device__ __noinline__ void op_load(const LaneProg& P, const LaneOp& op, double
     }
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      const int pidx = p0 + k * T;
-      if (pidx >= npieces) break;
-      const int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+      const int pc = p0 + k * T;
+      if (pc >= npieces) break;
+      const int j0 = 4 * (pc >> LSH) + (pc & 1) * 2;
       double2 x = v[k];
       if (sten && j0 >= 2 && j0 < len) { x.x = fma(sc[j0], u[k].x, x.x); x.y = fma(sc[j0 + 1], u[k].y, x.y); }
       x.x *= a;
       x.y = (j0 + 1 < len) ? x.y * a : 0.0;
-      double2* w = reinterpret_cast<double2*>(W + l * LP + j0);
-      if (acc) { double2 o = *w; x.x += o.x; x.y += o.y; }
-      else if (mul) { double2 o = *w; x.x *= o.x; x.y *= o.y; }
+      double2* w = W2 + pc;
+      if (acc) { double2 ov = *w; x.x += ov.x; x.y += ov.y; }
+      else if (mul) { double2 ov = *w; x.x *= ov.x; x.y *= ov.y; }
       *w = x;
     }
   }
   __syncthreads();
 }
 
-__device__ __noinline__ void op_store(const LaneProg& P, const LaneOp& op, const double* __restrict__ W, int g, int gl) {
-  const int T = blockDim.x, LP = P.LP;
-  const int LN = P.LN, psh = LN == 4 ? 3 : 2, pm = 2 * LN - 1, hl = LN >> 1;
-  const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;
-  const int npieces = P.in_tiles * 2 * LN;
-  const int len = op.i0;
+// ---------------------------------------------------------------------------------------------
+// stores
+// ---------------------------------------------------------------------------------------------
+// dst = W, same orientation: W leaves as it is (zero-copy) once its tail (>= len) is cleared.
+template <int LN>
+__device__ __noinline__ void store_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, int gl, int lb) {
+  const int len = op.i0, ntail = P.LP - len;
+  for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
+    const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
+    sv.W[4 * l + Lay<LN>::eix(e)] = 0.0;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (P.bulk1d) {
+      char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + (size_t)gl * P.in_tiles * 128;
+      for (int c = 0; c < P.nchd; c++) {
+        const int t0 = c * P.CHD, t1 = min(t0 + P.CHD, P.in_tiles);
+        bulk_store_1d(dst + (size_t)t0 * 128, reinterpret_cast<const char*>(sv.W) + (size_t)t0 * 128, (uint32_t)(t1 - t0) * 128u);
+      }
+    } else {
+      for (int c = 0; c < P.nchd; c++)
+        tma_store_3d(tm, lb * 4, c * P.CHD, gl, reinterpret_cast<const char*>(sv.W) + (size_t)c * P.CHD * LN * 32);
+    }
+    bulk_commit();
+    bulk_wait_read<0>();   // W is rewritten by whatever comes next
+  }
+  __syncthreads();
+}
+
+// dst = [dst +] a * W through the staging slots and bulk tensor stores / reductions.  Slot k % 3 is rewritten
+// while the stores of chunks k-1 and k-2 may still be reading theirs: thread 0 waits (before the barrier of
+// chunk k) until at most one group is unread, i.e. chunk k-2 and older are done, which frees slot (k+1) % 3 for
+// everyone who passes that barrier -- one CTA barrier per chunk.
+template <int LN>
+__device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv,
+                                          int g, int gl, int lb, int& st_it) {
+  constexpr int LSH = Lay<LN>::LSH, HL = LN / 2;
+  const int NT = P.NT, len = op.i0, flags = op.i2;
   const double a = op.a;
-  const int flags = op.i2;
+  const double* W = sv.W;
+  const double2* W2 = reinterpret_cast<const double2*>(sv.W);
+  const int npc = P.CH << LSH;
+  for (int c = 0; c < P.nch; c++, st_it++) {
+    double2* st = reinterpret_cast<double2*>(sv.st + (size_t)(st_it % B2_ST_SLOTS) * P.st_bytes);
+    const int J0 = c * P.CH;
+    if (threadIdx.x == 0) bulk_wait_read<B2_ST_SLOTS - 2>();
+    if (flags & ST_TRANS) {
+      // slot layout [tile][jl][lane]: each 4x4 tile transposed.  Piece (tile, jl, lane pair lp) = elements
+      // (2lp, jl), (2lp+1, jl); odd tiles read the two in the opposite order so that the 16 threads of a
+      // half-warp touch 16 different 8-byte banks.
+#pragma unroll 2
+      for (int pc = threadIdx.x; pc < npc; pc += NT) {
+        const int lp = pc & (HL - 1), jl = (pc / HL) & 3, tt = pc >> LSH;
+        const int j = 4 * (J0 + tt) + jl, sw = tt & 1;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < len) {
+          const double* wt = W + ((size_t)(J0 + tt) << (LSH + 1)) + jl;
+          const double e0 = wt[4 * (2 * lp + sw)], e1 = wt[4 * (2 * lp + 1 - sw)];
+          v.x = a * (sw ? e1 : e0); v.y = a * (sw ? e0 : e1);
+        }
+        st[pc] = v;
+      }
+    } else {                  // slot layout [tile][lane][4]: the slab itself
+#pragma unroll 2
+      for (int pc = threadIdx.x; pc < npc; pc += NT) {
+        const int j0 = 4 * (J0 + (pc >> LSH)) + 2 * (pc & 1);
+        double2 v = make_double2(0.0, 0.0);
+        if (j0 < len) {
+          const double2 w = W2[((size_t)J0 << LSH) + pc];
+          v.x = a * w.x; v.y = (j0 + 1 < len) ? a * w.y : 0.0;
+        }
+        st[pc] = v;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (flags & ST_TRANS) {
+        if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);
+      } else if (P.bulk1d) {
+        char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + ((size_t)gl * P.in_tiles + J0) * 128;
+        const uint32_t bytes = (uint32_t)(min(J0 + P.CH, P.in_tiles) - J0) * 128u;
+        if (flags & ST_ACC) bulk_reduce_add_1d(dst, st, bytes); else bulk_store_1d(dst, st, bytes);
+      } else {
+        if (flags & ST_ACC) tma_reduce_add_3d(tm, lb * 4, J0, gl, st); else tma_store_3d(tm, lb * 4, J0, gl, st);
+      }
+      bulk_commit();
+    }
+  }
+}
+
+// Per-thread path: row-major "plain" destinations (GEMM operands), peer GPUs' slabs, TMA switched off.
+template <int LN>
+__device__ __noinline__ void store_threads(const LaneProg& P, const LaneOp& op, const SmemView& sv, int g, int gl, int lb) {
+  constexpr int LSH = Lay<LN>::LSH, HL = LN / 2;
+  const int T = P.NT, len = op.i0, flags = op.i2;
+  const int npieces = P.in_tiles << LSH;
+  const double a = op.a;
+  const double* W = sv.W;
+  const double2* W2 = reinterpret_cast<const double2*>(sv.W);
   double2* dst = reinterpret_cast<double2*>(const_cast<void*>(op.p0));
   if (flags & ST_TRANS) {
     double* const* peers = reinterpret_cast<double* const*>(op.p1);
-    for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
-      const int r = pidx & pm;
-      int J = pidx >> psh, jl = r / hl, l0 = (r % hl) * 2, j = 4 * J + jl;
+    for (int pc = threadIdx.x; pc < npieces; pc += T) {
+      const int lp = pc & (HL - 1), jl = (pc / HL) & 3, J = pc >> LSH, j = 4 * J + jl, sw = J & 1;
       double2 v = make_double2(0.0, 0.0);
-      if (j < len) { v.x = a * W[l0 * LP + j]; v.y = a * W[(l0 + 1) * LP + j]; }
+      if (j < len) {
+        const double* wt = W + ((size_t)J << (LSH + 1)) + jl;
+        const double e0 = wt[4 * (2 * lp + sw)], e1 = wt[4 * (2 * lp + 1 - sw)];
+        v.x = a * (sw ? e1 : e0); v.y = a * (sw ? e0 : e1);
+      }
       double2* d = dst;
       int Jl = J;
       if (flags & ST_PEER) {  // row block J of the transposed array lives on rank J / groups_per_rank
@@ -316,24 +622,24 @@ __device__ __noinline__ void op_store(const LaneProg& P, const LaneOp& op, const
                                        (reinterpret_cast<const char*>(op.p0) - reinterpret_cast<const char*>(peers[P.rank])));
       }
       // tiled: tile (Jl, g) holds [jl][l];  row-major ("plain", for the GEMM): row 4*Jl+jl, columns 4g+l
-      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + lb + l0) >> 1)
-                                      : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + lb + l0) >> 1);
-      if (flags & ST_ACC) { double2 o = d[idx]; v.x += o.x; v.y += o.y; }
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + lb + 2 * lp) >> 1)
+                                      : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + lb + 2 * lp) >> 1);
+      if (flags & ST_ACC) { double2 ov = d[idx]; v.x += ov.x; v.y += ov.y; }
       d[idx] = v;
     }
   } else {
     const size_t slab = (size_t)gl * P.in_tiles * 8;
-    for (int pidx = threadIdx.x; pidx < npieces; pidx += T) {
-      int J = pidx >> psh, l = (pidx & pm) >> 1, j0 = 4 * J + (pidx & 1) * 2;
+    for (int pc = threadIdx.x; pc < npieces; pc += T) {
+      const int J = pc >> LSH, l = (pc >> 1) & (LN - 1), j0 = 4 * J + (pc & 1) * 2;
       double2 v = make_double2(0.0, 0.0);
       if (j0 < len) {
-        double2 w = *reinterpret_cast<const double2*>(W + l * LP + j0);
+        const double2 w = W2[pc];
         v.x = a * w.x;
         v.y = (j0 + 1 < len) ? a * w.y : 0.0;
       }
       size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1)
-                                      : (slab + (size_t)J * 8 + (lb + l) * 2 + (pidx & 1));
-      if (flags & ST_ACC) { double2 o = dst[idx]; v.x += o.x; v.y += o.y; }
+                                      : (slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1));
+      if (flags & ST_ACC) { double2 ov = dst[idx]; v.x += ov.x; v.y += ov.y; }
       dst[idx] = v;
     }
   }
@@ -343,25 +649,21 @@ __device__ __noinline__ void op_store(const LaneProg& P, const LaneOp& op, const
 // ---- chunked lane ops -------------------------------------------------------------------------
 // Thread q of a lane owns CP consecutive PAIRS (2p, 2p+1), p = q*CP + t.  All banded operators of the
 // path couple elements at even distance only, so every recurrence is a plain double2 recurrence over
-// pairs (no parity bookkeeping), shared-memory accesses are 16-byte with stride CP = E+1 (odd: no bank
-// conflicts) and coefficient vectors are stored "pair/scan" ordered, [t][q] as double2 (coalesced).
-__device__ __forceinline__ double2 d2(double x, double y) { return make_double2(x, y); }
-__device__ __forceinline__ double2 d2fma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
-__device__ __forceinline__ double2 d2mul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
-
-template <int CP>
+// pairs (no parity bookkeeping).  CP = E+1 is odd and the threads of a warp are lane-fastest, so
+// the 8 threads of a quarter-warp hit 8 different 16-byte banks; coefficient vectors are stored
+// "pair/scan" ordered, [t][q] as double2 -- one broadcast request serves the LN lanes of a q.
+template <int CP, int LN>
 __device__ __noinline__ void op_band(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
   // y_i = sum_m c_m[i] x_{i+o_m}, o_m even.  Thread q of a lane takes the pairs p = q + t*TPL (coalesced
-  // coefficient loads in natural order, conflict-free shared-memory reads); results are staged in
-  // registers because the operation is in place.
+  // coefficient loads in natural order); results are staged in registers because the operation is in place.
   const int TPL = P.TPL, HP = P.LP >> 1;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
   const int len_out = op.i0;
   const int h0 = (int)(signed char)(op.i1 & 0xff), h1 = (int)(signed char)((op.i1 >> 8) & 0xff), h2 = (int)(signed char)((op.i1 >> 16) & 0xff);
   const double2* __restrict__ c0 = (const double2*)op.p0;
   const double2* __restrict__ c1 = (const double2*)op.p1;
   const double2* __restrict__ c2 = (const double2*)op.p2;
-  const double2* w2 = reinterpret_cast<const double2*>(W + l * P.LP);
+  double2* w2 = reinterpret_cast<double2*>(W) + 2 * l;
   const double2 zero = d2(0.0, 0.0);
   double2 y[CP];
 #pragma unroll
@@ -372,7 +674,7 @@ __device__ __noinline__ void op_band(const LaneProg& P, const LaneOp& op, double
     for (int t = 0; t < CP; t++) {
       const int p = q + t * TPL, pp = p + hp;
       const bool ok = pp >= 0 && pp < HP && p < HP;
-      const double2 x = w2[ok ? pp : 0];
+      const double2 x = w2[Lay<LN>::pix(ok ? pp : 0)];
       const double2 cc = c ? ldg(c + (p < HP ? p : 0)) : d2(1.0, 1.0);
       if (ok) y[t] = d2fma(cc, x, y[t]);
     }
@@ -381,38 +683,37 @@ __device__ __noinline__ void op_band(const LaneProg& P, const LaneOp& op, double
   if (h1 != 127) term(h1, c1);
   if (h2 != 127) term(h2, c2);
   __syncthreads();
-  double2* wo = reinterpret_cast<double2*>(W + l * P.LP);
 #pragma unroll
   for (int t = 0; t < CP; t++) {
     const int p = q + t * TPL;
     double2 v = y[t];
     if (2 * p >= len_out) v.x = 0.0;
     if (2 * p + 1 >= len_out) v.y = 0.0;
-    if (p < HP) wo[p] = v;
+    if (p < HP) w2[Lay<LN>::pix(p)] = v;
   }
   __syncthreads();
 }
 
 // Chebyshev derivative: b_k = S_{k+1},  S_m = 2 m a_m + S_{m+2};  b_0 *= 1/2;  result * scale.
 // In pairs: S[p] = (2(2p) a_2p, 2(2p+1) a_2p+1) + S[p+1];  out[p] = (S[p].y, S[p+1].x).
-template <int CP>
+template <int CP, int LN>
 __device__ __noinline__ void op_deriv(const LaneProg& P, const LaneOp& op, double* __restrict__ W, void* scratch) {
   const int TPL = P.TPL, HP = P.LP >> 1;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
-  double2* w2 = reinterpret_cast<double2*>(W + l * P.LP);
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  double2* w2 = reinterpret_cast<double2*>(W) + 2 * l;
   for (int rep = 0; rep < op.i1; rep++) {
     double2 tp[CP];
     double2 tot = d2(0.0, 0.0);
 #pragma unroll
     for (int t = 0; t < CP; t++) {
       const int p = q * CP + t;
-      double2 a = (p < HP) ? w2[p < HP ? p : 0] : d2(0.0, 0.0);
+      double2 a = (p < HP) ? w2[Lay<LN>::pix(p < HP ? p : 0)] : d2(0.0, 0.0);
       tp[t] = d2(2.0 * (2 * p) * a.x, 2.0 * (2 * p + 1) * a.y);
       tot.x += tp[t].x; tot.y += tp[t].y;
     }
     Aff1::V m; m.d[0] = 1; m.d[1] = tot.x; m.d[2] = 1; m.d[3] = tot.y;
-    Aff1::V inc = lane_scan_excl<Aff1, true>(m, TPL, (Aff1::V*)scratch);
-    double2 S = d2(inc.d[1], inc.d[3]);   // S of the first pair of the next chunk
+    Aff1::S in = lane_scan_state<Aff1, true, LN>(m, TPL, scratch);
+    double2 S = d2(in.d[0], in.d[1]);   // S of the first pair of the next chunk
     const double sc = (rep == op.i1 - 1) ? op.a : 1.0;
 #pragma unroll
     for (int t = CP - 1; t >= 0; t--) {
@@ -421,7 +722,7 @@ __device__ __noinline__ void op_deriv(const LaneProg& P, const LaneOp& op, doubl
       S.x += tp[t].x; S.y += tp[t].y;
       double2 o = d2(S.y * sc, nx * sc);
       if (p == 0) o.x *= 0.5;
-      if (p < HP) w2[p] = o;
+      if (p < HP) w2[Lay<LN>::pix(p)] = o;
     }
     __syncthreads();
   }
@@ -432,17 +733,17 @@ __device__ __noinline__ void op_deriv(const LaneProg& P, const LaneOp& op, doubl
 //   backward: x_i = (x_i - u1_i x_{i+2} - u2_i x_{i+4}) * id_i
 // As pair recurrences: y_p = b_p - fl_p * y_{p-1};  x_p = (y_p - u1_p x_{p+1} - u2_p x_{p+2}) id_p.
 // Each thread reduces its CP pairs to an affine map; maps are combined by a scan across the lane's threads.
-template <int CP>
-__device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, void* scratch) {
+template <int CP, int LN>
+__device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, int lb, void* scratch) {
   const int TPL = P.TPL, HP = P.LP >> 1;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
   const int n = op.i0;
-  double2* w2 = reinterpret_cast<double2*>(W + l * P.LP);
+  double2* w2 = reinterpret_cast<double2*>(W) + 2 * l;
   const double2* __restrict__ cfl = (const double2*)op.p0; const double2* __restrict__ cid = (const double2*)op.p1;
   const double2* __restrict__ cu1 = (const double2*)op.p2; const double2* __restrict__ cu2 = (const double2*)op.p3;
-  // shared vectors: [t][q]; per-lane arrays: [group][t][lane][q]  (double2 units, coalesced at every step)
+  // shared vectors: [t][q]; per-lane arrays: [group][t][q][lane of 4]  (double2 units, coalesced at every step)
   size_t base; int stride;
-  if (op.i2 & FD_PERLANE) { const int lb = (blockIdx.x & ((4 / P.LN) - 1)) * P.LN; stride = 4 * TPL; base = ((size_t)gl * CP * 4 + lb + l) * TPL + q; }
+  if (op.i2 & FD_PERLANE) { stride = 4 * TPL; base = ((size_t)gl * CP * TPL + q) * 4 + lb + l; }
   else { stride = TPL; base = q; }
   const bool nou2 = op.i2 & FD_NOU2;
   const double2 zero = d2(0.0, 0.0);
@@ -450,7 +751,7 @@ __device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double
   auto rd = [&](int t) -> double2 {   // right-hand side / intermediate at pair p0+t, zero outside [0, n)
     const int p = p0 + t;
     const bool ok = p < HP;
-    double2 v = ok ? w2[ok ? p : 0] : zero;
+    double2 v = ok ? w2[Lay<LN>::pix(ok ? p : 0)] : zero;
     if (2 * p >= n) v.x = 0.0;
     if (2 * p + 1 >= n) v.y = 0.0;
     return v;
@@ -465,13 +766,13 @@ __device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double
       A = d2(-f.x * A.x, -f.y * A.y);
     }
     Aff1::V m; m.d[0] = A.x; m.d[1] = B.x; m.d[2] = A.y; m.d[3] = B.y;
-    Aff1::V inc = lane_scan_excl<Aff1, false>(m, TPL, (Aff1::V*)scratch);
-    double2 y = d2(inc.d[1], inc.d[3]);   // y of the last pair before this chunk (the start state is 0)
+    Aff1::S in = lane_scan_state<Aff1, false, LN>(m, TPL, scratch);
+    double2 y = d2(in.d[0], in.d[1]);   // y of the last pair before this chunk (the start state is 0)
 #pragma unroll 6
     for (int t = 0; t < CP; t++) {
       const double2 f = ldg(cfl + base + (size_t)t * stride), b = rd(t);
       y = d2(fma(-f.x, y.x, b.x), fma(-f.y, y.y, b.y));
-      if (p0 + t < HP) w2[p0 + t] = y;
+      if (p0 + t < HP) w2[Lay<LN>::pix(p0 + t)] = y;
     }
   }
   // every thread only touched its own chunk: no barrier needed before the back substitution
@@ -490,15 +791,15 @@ __device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double
       r0 = m0.y * M[0] + m1.y * M[2]; r1 = m0.y * M[1] + m1.y * M[3]; rp = m0.y * M[4] + m1.y * M[5] + g0.y;
       M[2] = M[0]; M[3] = M[1]; M[5] = M[4]; M[0] = r0; M[1] = r1; M[4] = rp;
     }
-    Aff2::V inc = lane_scan_excl<Aff2, true>(m, TPL, (Aff2::V*)scratch);
-    double2 s1 = d2(inc.d[4], inc.d[10]), s2 = d2(inc.d[5], inc.d[11]);   // x_{p+1}, x_{p+2} entering the chunk
+    Aff2::S in = lane_scan_state<Aff2, true, LN>(m, TPL, scratch);
+    double2 s1 = d2(in.d[0], in.d[2]), s2 = d2(in.d[1], in.d[3]);   // x_{p+1}, x_{p+2} entering the chunk
 #pragma unroll 6
     for (int t = CP - 1; t >= 0; t--) {
       const size_t k = base + (size_t)t * stride;
       const double2 idv = ldg(cid + k), u1 = ldg(cu1 + k), u2 = nou2 ? zero : ldg(cu2 + k), y = rd(t);
       double2 x = d2((y.x - u1.x * s1.x - u2.x * s2.x) * idv.x, (y.y - u1.y * s1.y - u2.y * s2.y) * idv.y);
       s2 = s1; s1 = x;
-      if (p0 + t < HP) w2[p0 + t] = x;
+      if (p0 + t < HP) w2[Lay<LN>::pix(p0 + t)] = x;
     }
   }
   __syncthreads();
@@ -506,49 +807,62 @@ __device__ __noinline__ void op_fdma(const LaneProg& P, const LaneOp& op, double
 
 // ---------------------------------------------------------------------------------------------
 // complex FFT of Nc points per lane, in place in shared memory (Stockham autosort, register-staged:
-// every thread reads its E points, the CTA syncs, then everything is written back).
-// tw[t] = exp(-2 pi i t / Nc)
+// every thread reads its E points, the CTA syncs, then everything is written back).  Complex point i of a
+// lane is pair i of that lane.  tw[t] = exp(-2 pi i t / Nc)
 // ---------------------------------------------------------------------------------------------
-template <int E, int R>
-__device__ __forceinline__ void fft_stage(double* __restrict__ wl, int Nc, int Ns, int q, int TPL, const cplx* __restrict__ tw) {
-  constexpr int NB = E / R;
+// One Stockham pass.  FIRST: Ns == 1 (no twiddles).  The Ns == 1 pass scatters each thread's R results to R
+// consecutive points (neighbouring q's write points of equal parity = the same bank pair): it writes point i at
+// i ^ ((i >> log2 E) & swz) and the following pass reads through the same map (swz = 1), which restores the
+// alternation; both sides are then conflict-free.
+template <int E, int R, bool FIRST, int LN>
+__device__ __forceinline__ void fft_stage(double2* __restrict__ wl, int Nc, int Ns, int q, int TPL, const cplx* __restrict__ tw,
+                                          int swz_in, int swz_out) {
+  constexpr int NB = E / R, LE = Log2<E>::v;
   cplx v[E];
+  cplx w1[NB];
   const int stride = Nc / R;
 #pragma unroll
   for (int b = 0; b < NB; b++) {
-    int j = q + b * TPL;
+    const int j = q + b * TPL;
+    if (!FIRST) w1[b] = ldg(tw + (j & (Ns - 1)) * (stride / Ns));   // issued ahead of the barrier
 #pragma unroll
-    for (int r = 0; r < R; r++) v[b * R + r] = *reinterpret_cast<const cplx*>(wl + 2 * (j + r * stride));
+    for (int r = 0; r < R; r++) {
+      int i = j + r * stride;
+      i ^= (i >> LE) & swz_in;
+      v[b * R + r] = wl[Lay<LN>::pix(i)];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int b = 0; b < NB; b++) {
-    int j = q + b * TPL;
-    int k = j % Ns;
-    if (Ns > 1) {
-      int tstep = k * (Nc / (Ns * R));
-#pragma unroll
-      for (int r = 1; r < R; r++) v[b * R + r] = cmul(v[b * R + r], ldg(tw + r * tstep));
-    }
+    const int j = q + b * TPL;
+    const int k = j & (Ns - 1);
+    if (!FIRST) Twid<R>::run(v + b * R, w1[b]);
     Dft<R>::run(v + b * R);
-    int j0 = (j - k) * R + k;
+    const int j0 = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; r++) *reinterpret_cast<cplx*>(wl + 2 * (j0 + r * Ns)) = v[b * R + r];
+    for (int r = 0; r < R; r++) {
+      int i = j0 + r * Ns;
+      i ^= (i >> LE) & swz_out;
+      wl[Lay<LN>::pix(i)] = v[b * R + r];
+    }
   }
   __syncthreads();
 }
 
-template <int E>
-__device__ __forceinline__ void lane_fft(double* __restrict__ W, int LP, int Nc, int TPL, const cplx* __restrict__ tw) {
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
-  double* wl = W + l * LP;
-  int Ns = 1;
+template <int E, int LN>
+__device__ __forceinline__ void lane_fft(double* __restrict__ W, int Nc, int TPL, const cplx* __restrict__ tw) {
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  double2* wl = reinterpret_cast<double2*>(W) + 2 * l;
   // radix plan: as many radix-E passes as fit, then one pass with the remainder (1, 2, 4 or 8)
-  while (Nc / Ns >= E) { fft_stage<E, E>(wl, Nc, Ns, q, TPL, tw); Ns *= E; }
+  int swz = (Nc > E) ? 1 : 0;
+  fft_stage<E, E, true, LN>(wl, Nc, 1, q, TPL, tw, 0, swz);
+  int Ns = E;
+  while (Nc / Ns >= E) { fft_stage<E, E, false, LN>(wl, Nc, Ns, q, TPL, tw, swz, 0); swz = 0; Ns *= E; }
   const int rem = Nc / Ns;
-  if constexpr (E >= 16) { if (rem == 8) fft_stage<E, 8>(wl, Nc, Ns, q, TPL, tw); }
-  if constexpr (E >= 8) { if (rem == 4) fft_stage<E, 4>(wl, Nc, Ns, q, TPL, tw); }
-  if (rem == 2) fft_stage<E, 2>(wl, Nc, Ns, q, TPL, tw);
+  if constexpr (E >= 16) { if (rem == 8) fft_stage<E, 8, false, LN>(wl, Nc, Ns, q, TPL, tw, swz, 0); }
+  if constexpr (E >= 8) { if (rem == 4) fft_stage<E, 4, false, LN>(wl, Nc, Ns, q, TPL, tw, swz, 0); }
+  if (rem == 2) fft_stage<E, 2, false, LN>(wl, Nc, Ns, q, TPL, tw, swz, 0);
 }
 
 // Chebyshev transform (DCT-I of n = N+1 points on Gauss-Lobatto nodes x_j = -cos(pi j/N)) through ONE
@@ -556,15 +870,15 @@ __device__ __forceinline__ void lane_fft(double* __restrict__ W, int LP, int Nc,
 //   mode 0 (forward):  c_k = (-1)^k X_k / N, c_0 and c_N halved,  X = DCT-I(v)
 //   mode 1 (backward): v = DCT-I(y)/2, y_k = (-1)^k c_k, y_0 and y_N doubled
 // tw: exp(-2 pi i t/(N/2)), tw2[j] = exp(-2 pi i j/N) (j <= N/2), isin[k] = 1/(4 sin(pi k/N))
-template <int E>
+template <int E, int LN>
 __device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double* __restrict__ W, double* scratch) {
-  const int TPL = P.TPL, LP = P.LP;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int TPL = P.TPL;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
   const int N = op.i0 - 1, M = N >> 1, mode = op.i1;
   const cplx* tw = (const cplx*)op.p0; const cplx* tw2 = (const cplx*)op.p1; const double* isin = (const double*)op.p2;
-  double* w = W + l * LP;
+  double* w = W + 4 * l;
+  cplx* w2 = reinterpret_cast<cplx*>(W) + 2 * l;
   constexpr int NP = E / 2 + 1;
-  const cplx* w2 = reinterpret_cast<const cplx*>(w);
   // ---- pre: x -> g (N/2 complex), pairs (j, M-j); branch-free, 16-byte shared-memory reads ----
   cplx gj[NP], gm[NP];
   double r0 = 0.0;
@@ -573,7 +887,7 @@ __device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double*
   for (int pi = 0; pi < NP; pi++) {
     const int j0 = q + pi * TPL;
     const int j = j0 <= M / 2 ? j0 : M / 2, jm = M - j;
-    const cplx pj = w2[j], pjl = w2[j > 0 ? j - 1 : 0], pm = w2[jm], pml = w2[jm - 1];
+    const cplx pj = w2[Lay<LN>::pix(j)], pjl = w2[Lay<LN>::pix(j > 0 ? j - 1 : 0)], pm = w2[Lay<LN>::pix(jm)], pml = w2[Lay<LN>::pix(jm - 1)];
     const double xo_p = sg * pj.y;                              // x_{2j+1}
     const double xo_m = (j == 0) ? xo_p : sg * pjl.y;           // x_{2j-1}, x_{-1} = x_1
     const double xm_m = sg * pml.y;                             // x_{2jm-1}
@@ -585,16 +899,16 @@ __device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double*
     gm[pi] = make_double2(e.x + d.y, -e.y + d.x);          // conj(e) + i conj(d)
     r0 += (j0 < M / 2) ? (xo_p + xm_m) : 0.0;
   }
-  r0 = 2.0 * lane_sum(r0, TPL, scratch);   // R_0 = 2 * sum of odd samples
+  r0 = 2.0 * lane_sum<LN>(r0, TPL, scratch);   // R_0 = 2 * sum of odd samples
   __syncthreads();
 #pragma unroll
   for (int pi = 0; pi < NP; pi++) {
     const int j = q + pi * TPL;
-    if (j <= M / 2) *reinterpret_cast<cplx*>(w + 2 * j) = gj[pi];
-    if (j > 0 && j < M / 2) *reinterpret_cast<cplx*>(w + 2 * (M - j)) = gm[pi];
+    if (j <= M / 2) w2[Lay<LN>::pix(j)] = gj[pi];
+    if (j > 0 && j < M / 2) w2[Lay<LN>::pix(M - j)] = gm[pi];
   }
   __syncthreads();
-  lane_fft<E>(W, LP, M, TPL, tw);
+  lane_fft<E, LN>(W, M, TPL, tw);
   // ---- post: Z (N reals) -> X (N+1), pairs (k, N-k), 1 <= k <= M-1 in a branch-free unrolled loop ----
   const double fs = (mode == 0) ? 1.0 / N : 0.5;
 #pragma unroll
@@ -602,80 +916,82 @@ __device__ __noinline__ void op_dct(const LaneProg& P, const LaneOp& op, double*
     const int k0 = q + pi * TPL;
     const bool ok = k0 >= 1 && k0 <= M - 1;
     const int k = ok ? k0 : 1;
-    const double zk = w[k], zn = w[N - k];
+    const double zk = w[Lay<LN>::eix(k)], zn = w[Lay<LN>::eix(N - k)];
     const double A = 0.5 * (zk + zn), R = (zn - zk) * ldg(isin + k);
     const double sk = (mode == 0 && (k & 1)) ? -fs : fs;      // N is even: k and N-k have the same parity
-    if (ok) { w[k] = (A + R) * sk; w[N - k] = (A - R) * sk; }
+    if (ok) { w[Lay<LN>::eix(k)] = (A + R) * sk; w[Lay<LN>::eix(N - k)] = (A - R) * sk; }
   }
   if (q == 0) {   // k = 0 (and N), k = M: untouched by the loop above
     const double z0 = w[0], e0 = (mode == 0) ? 0.5 * fs : fs;
     w[0] = (z0 + r0) * e0;
-    w[N] = (z0 - r0) * e0;
-    w[M] = w[M] * ((mode == 0 && (M & 1)) ? -fs : fs);
+    w[Lay<LN>::eix(N)] = (z0 - r0) * e0;
+    w[Lay<LN>::eix(M)] = w[Lay<LN>::eix(M)] * ((mode == 0 && (M & 1)) ? -fs : fs);
   }
   __syncthreads();
 }
 
 // Real FFT of n points along the lane (Fourier axis): forward r2c is unnormalised,
 // n/2+1 interleaved complex modes; backward c2r carries 1/n and ignores Im of the k=0 and k=n/2 modes.
-template <int E>
+template <int E, int LN>
 __device__ __noinline__ void op_rfft(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
   const int TPL = P.TPL, LP = P.LP;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
   const int n = op.i0, M = n >> 1, mode = op.i1;
   const cplx* tw = (const cplx*)op.p0; const cplx* tw2 = (const cplx*)op.p1;
-  double* w = W + l * LP;
+  double* w = W + 4 * l;
+  cplx* w2 = reinterpret_cast<cplx*>(W) + 2 * l;
   if (mode == 0) {
-    lane_fft<E>(W, LP, M, TPL, tw);
+    lane_fft<E, LN>(W, M, TPL, tw);
     for (int k = q; k <= M / 2; k += TPL) {
       if (k == 0) {
-        cplx z = *reinterpret_cast<cplx*>(w);
-        *reinterpret_cast<cplx*>(w) = make_double2(z.x + z.y, 0.0);
-        *reinterpret_cast<cplx*>(w + 2 * M) = make_double2(z.x - z.y, 0.0);
+        cplx z = w2[0];
+        w2[0] = make_double2(z.x + z.y, 0.0);
+        w2[Lay<LN>::pix(M)] = make_double2(z.x - z.y, 0.0);
       } else {
-        cplx zk = *reinterpret_cast<cplx*>(w + 2 * k), zm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
+        cplx zk = w2[Lay<LN>::pix(k)], zm = cconj(w2[Lay<LN>::pix(M - k)]);
         cplx S = cadd(zk, zm), D = cmul(ldg(tw2 + k), csub(zk, zm));   // w_k D
         // X_k = (S - i wD)/2 ; X_{M-k} = conj((S + i wD)/2)
-        *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
-        if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
+        w2[Lay<LN>::pix(k)] = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
+        if (k != M - k) w2[Lay<LN>::pix(M - k)] = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
       }
     }
     __syncthreads();
   } else {
     for (int k = q; k <= M / 2; k += TPL) {
       if (k == 0) {
-        double x0 = w[0], xm = w[2 * M];
+        double x0 = w[0], xm = w[Lay<LN>::eix(2 * M)];
         // Zc_0 = ((x0+xm) + i(x0-xm))/2 ; FFT input is conj(Zc)
-        *reinterpret_cast<cplx*>(w) = make_double2(0.5 * (x0 + xm), -0.5 * (x0 - xm));
+        w2[0] = make_double2(0.5 * (x0 + xm), -0.5 * (x0 - xm));
       } else {
-        cplx xk = *reinterpret_cast<cplx*>(w + 2 * k), xm = cconj(*reinterpret_cast<cplx*>(w + 2 * (M - k)));
+        cplx xk = w2[Lay<LN>::pix(k)], xm = cconj(w2[Lay<LN>::pix(M - k)]);
         cplx S = cadd(xk, xm), D = cmul(cconj(ldg(tw2 + k)), csub(xk, xm));  // conj(w_k) D'
         // Zc_k = (S + i cD)/2 ; Zc_{M-k} = conj((S - i cD)/2); store conjugates
-        *reinterpret_cast<cplx*>(w + 2 * k) = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
-        if (k != M - k) *reinterpret_cast<cplx*>(w + 2 * (M - k)) = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
+        w2[Lay<LN>::pix(k)] = make_double2(0.5 * (S.x - D.y), -0.5 * (S.y + D.x));
+        if (k != M - k) w2[Lay<LN>::pix(M - k)] = make_double2(0.5 * (S.x + D.y), 0.5 * (S.y - D.x));
       }
     }
     __syncthreads();
-    lane_fft<E>(W, LP, M, TPL, tw);
+    lane_fft<E, LN>(W, M, TPL, tw);
     const double s = 1.0 / M;
     for (int e = q; e < LP; e += TPL) {
-      double v = w[e];
-      w[e] = (e < n) ? ((e & 1) ? -v * s : v * s) : 0.0;
+      double v = w[Lay<LN>::eix(e)];
+      w[Lay<LN>::eix(e)] = (e < n) ? ((e & 1) ? -v * s : v * s) : 0.0;
     }
     __syncthreads();
   }
 }
 
-__device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int g) {
+template <int LN>
+__device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int g, int lb) {
   const int TPL = P.TPL, LP = P.LP;
-  const int lb = (blockIdx.x & ((4 / P.LN) - 1)) * P.LN;
-  const int q = threadIdx.x % TPL, l = threadIdx.x / TPL;
-  double* w = W + l * LP;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  double* w = W + 4 * l;
+  cplx* w2 = reinterpret_cast<cplx*>(W) + 2 * l;
   switch (op.code) {
     case OP_FDIFF: {   // interleaved complex: (re, im) *= (i k)^d * a
       const int m = op.i0, d = op.i1 & 3;
       for (int k = q; k < m; k += TPL) {
-        cplx c = *reinterpret_cast<cplx*>(w + 2 * k);
+        cplx c = w2[Lay<LN>::pix(k)];
         double f = op.a;
         for (int t = 0; t < op.i1; t++) f *= (double)k;
         cplx r;
@@ -683,53 +999,92 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
         else if (d == 1) r = make_double2(-c.y * f, c.x * f);
         else if (d == 2) r = make_double2(-c.x * f, -c.y * f);
         else r = make_double2(c.y * f, -c.x * f);
-        *reinterpret_cast<cplx*>(w + 2 * k) = r;
+        w2[Lay<LN>::pix(k)] = r;
       }
     } break;
     case OP_SCALEVEC: {
       const double* v = (const double*)op.p0;
-      for (int e = q; e < op.i0; e += TPL) w[e] *= ldg(v + (e >> op.i1));
+      for (int e = q; e < op.i0; e += TPL) w[Lay<LN>::eix(e)] *= ldg(v + (e >> op.i1));
     } break;
     case OP_ZEROTAIL:
-      for (int e = op.i0 + q; e < LP; e += TPL) w[e] = 0.0;
+      for (int e = op.i0 + q; e < LP; e += TPL) w[Lay<LN>::eix(e)] = 0.0;
       break;
     case OP_LANEMASK:
-      if (4 * g + lb + l >= op.i0) for (int e = q; e < LP; e += TPL) w[e] = 0.0;
+      if (4 * g + lb + l >= op.i0) for (int e = q; e < LP; e += TPL) w[Lay<LN>::eix(e)] = 0.0;
       break;
     case OP_ZEROELEM:
-      if (4 * g + lb + l == op.i0 && q == 0) w[op.i1] = 0.0;
+      if (4 * g + lb + l == op.i0 && q == 0) w[Lay<LN>::eix(op.i1)] = 0.0;
       break;
     case OP_SCALE:
-      for (int e = q; e < LP; e += TPL) w[e] *= op.a;
+      for (int e = q; e < LP; e += TPL) w[Lay<LN>::eix(e)] *= op.a;
       break;
   }
   __syncthreads();
 }
 
-template <int E>
+#include "lane_fast.cuh"
+
+// E = FFT points per thread (16: radix-16 passes, 128 registers; 8 and 4 for short lanes); LN = lanes per CTA;
+// TPLC = threads per lane as a compile-time constant for transform-sized lanes (N = 2*E*TPLC: the hot operators
+// then run their compile-time-geometry versions of lane_fast.cuh), 0 = generic geometry read from the program.
+template <int E, int LN, int TPLC>
 __global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg P) {
-  B2_DYN_SMEM(double, smem);
-  double* W = smem;                       // [LN][LP]
-  void* scratch = smem + P.LN * P.LP;     // 32 * sizeof(DVec<12>) = 3 KB
-  const int gl = blockIdx.x / (4 / P.LN); // local lane group (addresses this GPU's slab)
+  B2_DYN_SMEM(char, smem_raw);
+  const SmemView sv = smem_view(P, smem_raw);
+  double* W = sv.W;
+  void* scratch = sv.scratch;
+  const int gl = blockIdx.x / (4 / LN);   // local lane group (addresses this GPU's slab)
   const int g = P.group0 + gl;            // global lane group (mode indices, transposed stores)
+  const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;
+  Prefetch pf; pf.it = 0; pf.c = 0; pf.gl = gl; pf.lb = lb; pf.op = P.nops; pf.dphase = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.NS; i++) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], P.NT / 32); }
+    mbar_init(sv.dfull, 1);
+    mbar_fence_init();
+    for (int o = 0; o < P.nops; o++)
+      if ((P.ops[o].code == OP_LOAD && (P.ops[o].i2 & (LD_TMA | LD_DIRECT))) || (P.ops[o].code == OP_STORE && (P.ops[o].i2 & (ST_TMA | ST_DIRECT))))
+        tmap_prefetch(&P.tm[o]);
+    pf.op = next_ring_load(P, 0);
+    for (int i = 0; i < P.NS; i++) prefetch_next(P, sv, pf, -1);
+  }
+  __syncthreads();
+  int ld_it = 0, st_it = 0;
   for (int o = 0; o < P.nops; o++) {
     const LaneOp& op = P.ops[o];
     long long t0 = 0;
     if (P.prof) t0 = clock64();
     switch (op.code) {
-      case OP_LOAD: op_load(P, op, W, gl); break;
-      case OP_STORE: op_store(P, op, W, g, gl); break;
-      case OP_BAND: op_band<E + 1>(P, op, W); break;
-      case OP_DERIV: op_deriv<E + 1>(P, op, W, scratch); break;
-      case OP_FDMA: op_fdma<E + 1>(P, op, W, gl, scratch); break;
-      case OP_DCT: op_dct<E>(P, op, W, (double*)scratch); break;
-      case OP_RFFT: op_rfft<E>(P, op, W); break;
-      default: op_pointwise(P, op, W, g); break;
+      case OP_LOAD:
+        if (op.i2 & LD_DIRECT) load_direct<LN>(P, op, &P.tm[o], sv, pf);
+        else if (op.i2 & LD_TMA) load_ring<LN>(P, op, o, sv, ld_it, pf);
+        else load_threads<LN, (E == 16 ? 8 : 4)>(P, op, sv, gl, lb);
+        break;
+      case OP_STORE:
+        if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &P.tm[o], sv, gl, lb);
+        else if (op.i2 & ST_TMA) store_staged<LN>(P, op, &P.tm[o], sv, g, gl, lb, st_it);
+        else store_threads<LN>(P, op, sv, g, gl, lb);
+        break;
+      case OP_BAND:
+        if constexpr (TPLC > 0) band_fast<E, LN, TPLC>(P, op, W); else op_band<E + 1, LN>(P, op, W);
+        break;
+      case OP_DERIV:
+        if constexpr (TPLC > 0) deriv_fast<E, LN, TPLC>(P, op, W, scratch); else op_deriv<E + 1, LN>(P, op, W, scratch);
+        break;
+      case OP_FDMA:
+        if constexpr (TPLC > 0) fdma_fast<E, LN, TPLC>(P, op, W, gl, lb, scratch); else op_fdma<E + 1, LN>(P, op, W, gl, lb, scratch);
+        break;
+      case OP_DCT:
+        if constexpr (TPLC > 0) dct_fast<E, LN, TPLC>(op, W, (double*)scratch); else op_dct<E, LN>(P, op, W, (double*)scratch);
+        break;
+      case OP_RFFT:
+        if constexpr (TPLC > 0) rfft_fast<E, LN, TPLC>(P, op, W); else op_rfft<E, LN>(P, op, W);
+        break;
+      default: op_pointwise<LN>(P, op, W, g, lb); break;
     }
     if (P.prof && threadIdx.x == 0) {
       atomicAdd(P.prof + op.code, (unsigned long long)(clock64() - t0));
       atomicAdd(P.prof + 32 + op.code, 1ull);
     }
   }
+  if (threadIdx.x == 0) bulk_wait<0>();   // shared memory must outlive the bulk stores that read it
 }

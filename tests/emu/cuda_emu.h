@@ -35,6 +35,8 @@
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 using std::fma;
+using std::min;
+using std::max;
 
 namespace emu {
 struct Dim3 { int x = 1, y = 1, z = 1; };
@@ -116,7 +118,7 @@ class Pool {
 template <class F> inline void launch(int grid, int blockdim, size_t smem, F&& body) {
   Block& b = block();
   g_blockDim.x = blockdim; g_gridDim.x = grid;
-  b.dyn.assign(smem + 64, 0);
+  b.dyn.assign(smem + 256, 0);
   b.bar.reset(blockdim);
   const int nw = (blockdim + 31) / 32;
   for (int w = 0; w < nw; w++) b.warps[w].bar.reset(std::min(32, blockdim - 32 * w));
@@ -143,6 +145,7 @@ inline double shfl(double v, int src_lane) {
 #define gridDim emu::g_gridDim
 
 static inline void __syncthreads() { emu::block().bar.wait(); }
+static inline void __syncwarp() { emu::block().warps[threadIdx.x / 32].bar.wait(); }
 static inline double __shfl_up_sync(unsigned, double v, int d, int width = 32) {
   const int lane = threadIdx.x % 32;
   return emu::shfl(v, (lane % width) >= d ? lane - d : lane);
@@ -256,5 +259,5 @@ static inline cublasStatus_t cublasDgemm(cublasHandle_t, cublasOperation_t ta, c
   return 0;
 }
 
-#define B2_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::block().dyn.data()) + 15) & ~uintptr_t(15))
+#define B2_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::block().dyn.data()) + 127) & ~uintptr_t(127))
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })

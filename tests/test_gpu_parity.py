@@ -9,7 +9,7 @@ from tests import gpu_checks as g
 pytestmark = pytest.mark.gpu
 
 SPACES = [(1, 65, 1, 65), (2, 129, 1, 65), (0, 65, 0, 129), (2, 129, 2, 129), (4, 64, 1, 65), (4, 128, 0, 129),
-          (4, 256, 2, 65), (1, 257, 1, 513), (1, 1025, 2, 129), (4, 2048, 1, 129)]
+          (4, 256, 2, 65), (1, 257, 1, 513), (1, 1025, 2, 129), (4, 2048, 1, 129), (2, 2049, 1, 65), (1, 65, 2, 4097)]
 IDS = ["-".join(f"{g.KIND_NAME[s[i]]}{s[i+1]}" for i in (0, 2)) for s in SPACES]
 
 
