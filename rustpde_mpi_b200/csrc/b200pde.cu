@@ -48,7 +48,11 @@ static inline int roundup(int a, int b) { return (a + b - 1) / b * b; }
 // ------------------------------------------------------------------------------------------------
 struct b2_ctx {
   int device = 0, rank = 0, nranks = 1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // origin stream: everything is ordered on it
+  cudaStream_t side[2] = {nullptr, nullptr};   // side streams: independent passes of a step run as parallel graph branches
+  cudaStream_t cur = nullptr;         // stream the next pass is launched on (origin or a side stream)
+  cudaEvent_t evp[16] = {nullptr};    // fork / join events
+  int evn = 0;
   cublasHandle_t blas = nullptr;
   long long launches = 0;  // lane-kernel + helper launches (counted, for bench.py's gpu_launches)
   double* stage = nullptr; size_t stage_bytes = 0;   // host<->device staging (plain layout)
@@ -431,7 +435,7 @@ template <int E, int LN, int TPLC> static int launch_ELT(b2_ctx* ctx, const Pass
     CK(cudaFuncSetAttribute(lane_kernel<E, LN, TPLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     set_smem = c.smem;
   }
-  B2_LAUNCH((lane_kernel<E, LN, TPLC>), (c.groups / ctx->nranks) * (4 / c.LN), c.NT, c.smem, ctx->stream, p);
+  B2_LAUNCH((lane_kernel<E, LN, TPLC>), (c.groups / ctx->nranks) * (4 / c.LN), c.NT, c.smem, ctx->cur, p);
   CK(cudaGetLastError());
   return B2_OK;
 }
@@ -441,7 +445,7 @@ static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 #define B2_INST(e, ln, tpl) if (c.fast && c.E == e && c.LN == ln && c.TPL == tpl) return launch_ELT<e, ln, tpl>(ctx, c, p);
   B2_INST(16, 4, 128) B2_INST(16, 4, 64) B2_INST(16, 4, 32) B2_INST(16, 4, 16) B2_INST(16, 4, 8)
   B2_INST(16, 2, 256) B2_INST(16, 2, 128)
-  B2_INST(8, 4, 8) B2_INST(4, 4, 8)
+  B2_INST(8, 4, 64) B2_INST(8, 4, 32) B2_INST(8, 4, 16) B2_INST(8, 4, 8) B2_INST(4, 4, 8)
 #undef B2_INST
   if (c.LN == 4) {
     if (c.E == 16) return launch_ELT<16, 4, 0>(ctx, c, p);
@@ -468,6 +472,12 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
   p.w_off = c.w_off; p.ld_off = c.ld_off; p.st_off = c.st_off;
   p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
+  {   // share of a direct load that the copy engine takes (percent, B2_SPLIT; the threads fetch the rest)
+    int pct = 100;
+    if (const char* e = getenv("B2_SPLIT")) pct = std::max(0, std::min(100, atoi(e)));
+    p.dsplit = std::min(c.in_tiles, ((c.in_tiles * pct / 100 + c.CHD - 1) / c.CHD) * c.CHD);
+    if (pct == 0) p.dsplit = 0;
+  }
   bool exchange = false;
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
@@ -536,7 +546,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   };
   if (is_pow2(N) && N >= 64) {
     const int Nc = N / 2;
-    int want = Nc >= 128 ? 16 : (Nc >= 64 ? 8 : 4);
+    int want = Nc >= 1024 ? 16 : (Nc >= 64 ? 8 : 4);   // short lanes: fewer points per thread = more threads per lane
     if (const char* e = getenv("B2_E")) {   // tuning knob
       int ev = atoi(e);
       if (ev == 4 || ev == 8 || ev == 16) want = ev;
@@ -860,10 +870,11 @@ struct b2_navier {
   double* d_scalar = nullptr;
   // fused schedule: intermediates (suffix T = stored in the transposed orientation)
   double *Pf[3] = {nullptr}, *Qf[3] = {nullptr}, *V1[3] = {nullptr}, *Cx[3] = {nullptr}, *Zf[3] = {nullptr};
-  double *VTv = nullptr, *uxT = nullptr, *uyT = nullptr, *cv = nullptr, *PH = nullptr, *PHy = nullptr, *F1 = nullptr, *F2 = nullptr, *R0 = nullptr;
+  double *VTv = nullptr, *uxT = nullptr, *uyT = nullptr, *cv[3] = {nullptr}, *PH = nullptr, *PHy = nullptr, *F1 = nullptr, *F2 = nullptr, *R0 = nullptr;
   double *G0 = nullptr, *G1 = nullptr, *U1 = nullptr, *U2 = nullptr, *U3 = nullptr;
   double *GxT = nullptr, *GyT = nullptr, *KbT = nullptr, *KTT = nullptr;   // constants of the step
   int fused = 1;
+  int branches = 1;   // run independent passes of the fused step as parallel graph branches
   long long launches_per_step = 0;
 #ifndef B2_EMU
   cudaGraphExec_t graph = nullptr;
@@ -892,6 +903,9 @@ int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** 
   b2_ctx* c = new b2_ctx();
   c->device = device; c->rank = rank; c->nranks = nranks;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->cur = c->stream;
+  for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&c->evp[i], cudaEventDisableTiming));
   CKB(cublasCreate(&c->blas));
   CKB(cublasSetStream(c->blas, c->stream));
 #ifndef B2_EMU
@@ -1274,7 +1288,7 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
   }
   // ---- fused schedule: work arrays and the constants that never change during a run ----
   {
-    double** fw[] = {&nv->VTv, &nv->uxT, &nv->uyT, &nv->cv, &nv->PH, &nv->PHy, &nv->F1, &nv->F2, &nv->R0, &nv->G0, &nv->G1,
+    double** fw[] = {&nv->VTv, &nv->uxT, &nv->uyT, &nv->cv[0], &nv->cv[1], &nv->cv[2], &nv->PH, &nv->PHy, &nv->F1, &nv->F2, &nv->R0, &nv->G0, &nv->G1,
                      &nv->U1, &nv->U2, &nv->U3, &nv->GxT, &nv->GyT, &nv->KbT, &nv->KTT};
     for (auto w : fw) RET(nav_alloc(so, w));
     for (int i = 0; i < 3; i++) { RET(nav_alloc(so, &nv->Pf[i])); RET(nav_alloc(so, &nv->Qf[i])); RET(nav_alloc(so, &nv->V1[i])); RET(nav_alloc(so, &nv->Cx[i])); RET(nav_alloc(so, &nv->Zf[i])); }
@@ -1303,7 +1317,7 @@ int b2_navier_destroy(b2_navier* nv) {
   double* work[] = {nv->that, nv->tbc_ortho, nv->tbc_diff, nv->rhs, nv->g1, nv->g2, nv->conv, nv->div, nv->ux, nv->uy};
   for (auto w : work) ctx_free(nv->ctx, w);
   if (nv->d_scalar) cudaFree(nv->d_scalar);
-  double* fw[] = {nv->VTv, nv->uxT, nv->uyT, nv->cv, nv->PH, nv->PHy, nv->F1, nv->F2, nv->R0, nv->G0, nv->G1, nv->U1, nv->U2, nv->U3,
+  double* fw[] = {nv->VTv, nv->uxT, nv->uyT, nv->cv[0], nv->cv[1], nv->cv[2], nv->PH, nv->PHy, nv->F1, nv->F2, nv->R0, nv->G0, nv->G1, nv->U1, nv->U2, nv->U3,
                   nv->GxT, nv->GyT, nv->KbT, nv->KTT};
   for (auto w : fw) ctx_free(nv->ctx, w);
   for (int i = 0; i < 3; i++) { ctx_free(nv->ctx, nv->Pf[i]); ctx_free(nv->ctx, nv->Qf[i]); ctx_free(nv->ctx, nv->V1[i]); ctx_free(nv->ctx, nv->Cx[i]); ctx_free(nv->ctx, nv->Zf[i]); }
@@ -1399,6 +1413,17 @@ static int nav_update_unfused(b2_navier* nv) {
   return B2_OK;
 }
 
+// Parallel branches: stream k (0 = origin, 1/2 = side streams).  "after(k, j)": whatever is launched on stream k
+// next also waits for everything launched on stream j so far.  Under stream capture these become graph edges.
+static cudaStream_t nav_stream(b2_ctx* c, int k) { return k == 0 ? c->stream : c->side[k - 1]; }
+static int nav_after(b2_ctx* c, int k, int j) {
+  if (k == j) return B2_OK;
+  cudaEvent_t e = c->evp[c->evn++ & 15];
+  CK(cudaEventRecord(e, nav_stream(c, j)));
+  CK(cudaStreamWaitEvent(nav_stream(c, k), e, 0));
+  return B2_OK;
+}
+
 // Fused schedule: the same algebra as navier.rs:438-466 (all operators are tensor products, so the
 // per-axis factors can be regrouped freely), organised as 23 lane passes + 2 GEMMs per step with
 // ~91 array touches (SURVEY 8d work model) instead of one pass pair per reference call.
@@ -1414,8 +1439,23 @@ static int nav_update_fused(b2_navier* nv) {
   const int cut0 = (shape0 * 2 / 3) * (bxo.cheb ? 1 : 2), cut1 = shape1 * 2 / 3;
   const int P0 = so->P[0], P1 = so->P[1];
 
+  // Independent passes run as parallel branches (three streams = three branches of the captured graph): a pass
+  // has ~P/4 CTAs, which fills the GPU only for the largest grids.  Single-GPU only: the multi-GPU flag
+  // barrier that follows every exchanging pass is one shared epoch counter.
+  const bool par = (ctx->nranks == 1) && nv->branches;
+  auto on = [&](int k) { ctx->cur = par ? nav_stream(ctx, k) : ctx->stream; };
+  auto after = [&](int k, int j) -> int { return par ? nav_after(ctx, k, j) : B2_OK; };
+  RET(after(1, 0)); RET(after(2, 0));   // fork
+  {  // branch 2 first: pressure gradient terms, Helmholtz-y of pres and of d/dy pres
+    on(2);
+    Prog y;
+    y.load(nv->pres->vhat->d, byo.rows_ortho); emit_hh_axis(y, nv->hh[0], 1); y.store(nv->PH, nv->sp_vel->b[1].m, ST_TRANS);
+    y.load(nv->pres->vhat->d, byo.rows_ortho); y.deriv_axis(byo, 1, sy); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->PHy, nv->sp_vel->b[1].m, ST_TRANS);
+    RET(run_pass(so, 0, y));
+  }
   // ---- A: along y on the three advected fields: values, d/dy values, Helmholtz-y of the old field ----
   for (int i = 0; i < 3; i++) {
+    on(i);
     const b2_field* f = fld[i];
     const Base1& by = f->sp->b[1];
     const double* src = f->vhat->d;
@@ -1428,41 +1468,41 @@ static int nav_update_fused(b2_navier* nv) {
   }
   // ---- A-x: convection velocities ux, uy (physical, x-lane orientation) ----
   for (int i = 0; i < 2; i++) {
+    on(i);
     const Base1& bx = fld[i]->sp->b[0];
     Prog x; x.load(nv->Pf[i], bx.rows_spec); x.to_ortho(bx); int l = x.backward_ortho(bx); x.store(i == 0 ? nv->uxT : nv->uyT, l, 0);
     RET(run_pass(so, 1, x));
   }
+  RET(after(1, 0)); RET(after(0, 1)); RET(after(2, 0)); RET(after(2, 1));   // every branch needs ux and uy
   // ---- B: u . grad f in physical space, forward transform along x, dealias rows ----
   for (int i = 0; i < 3; i++) {
+    on(i);
     const Base1& bx = fld[i]->sp->b[0];
     Prog x;
     x.load(nv->Pf[i], bx.rows_spec); x.to_ortho(bx); x.deriv_axis(bx, 1, sx); int l = x.backward_ortho(bx);
     if (i == 2) x.load(nv->GxT, l, 1.0, LD_ACC);
     x.load(nv->uxT, l, 1.0, LD_MUL);
-    x.store(nv->cv, l, 0);
+    x.store(nv->cv[i], l, 0);
     x.load(nv->Qf[i], bx.rows_spec); x.to_ortho(bx); l = x.backward_ortho(bx);
     if (i == 2) x.load(nv->GyT, l, 1.0, LD_ACC);
     x.load(nv->uyT, l, 1.0, LD_MUL);
-    x.load(nv->cv, l, 1.0, LD_ACC);
+    x.load(nv->cv[i], l, 1.0, LD_ACC);
     l = x.forward_ortho(bxo); x.zerotail(cut0);
     x.store(nv->Cx[i], l, ST_TRANS);
     RET(run_pass(so, 1, x));
   }
   // ---- C-y: forward along y, dealias columns, -dt, Helmholtz-y ----
   for (int i = 0; i < 3; i++) {
+    on(i);
     Prog y; y.load(nv->Cx[i], byo.rows_phys, -dt); y.forward_ortho(byo); y.zerotail(cut1);
     emit_hh_axis(y, nv->hh[i], 1); y.store(nv->Zf[i], fld[i]->sp->b[1].m, ST_TRANS);
     RET(run_pass(so, 0, y));
   }
-  {  // pressure gradient terms: Helmholtz-y of pres and of d/dy pres
-    Prog y;
-    y.load(nv->pres->vhat->d, byo.rows_ortho); emit_hh_axis(y, nv->hh[0], 1); y.store(nv->PH, nv->sp_vel->b[1].m, ST_TRANS);
-    y.load(nv->pres->vhat->d, byo.rows_ortho); y.deriv_axis(byo, 1, sy); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->PHy, nv->sp_vel->b[1].m, ST_TRANS);
-    RET(run_pass(so, 0, y));
-  }
   // ---- C-x: assemble rhs along x and finish the three Helmholtz solves ----
+  RET(after(0, 2)); RET(after(1, 2));   // PH, PHy, VTv come from branch 2
   {
     const Base1& bxv = nv->sp_vel->b[0]; const Base1& bxT = nv->sp_temp->b[0];
+    on(0);
     Prog x;  // velx
     x.load(nv->PH, bxo.rows_ortho, -dt); x.deriv_axis(bxo, 1, sx);
     x.load(nv->Zf[0], bxo.rows_ortho, 1.0, LD_ACC);
@@ -1470,6 +1510,7 @@ static int nav_update_fused(b2_navier* nv) {
     emit_hh_axis(x, nv->hh[0], 0);
     x.store(nv->velx->vhat->d, bxv.rows_spec, ST_TRANS);
     RET(run_pass(so, 1, x));
+    on(1);
     Prog v;  // vely (+ buoyancy dt * (to_ortho(temp) + to_ortho(tempbc)))
     v.load(nv->PHy, bxo.rows_ortho, -dt);
     v.load(nv->Zf[1], bxo.rows_ortho, 1.0, LD_ACC);
@@ -1480,6 +1521,20 @@ static int nav_update_fused(b2_navier* nv) {
     v.store(nv->vely->vhat->d, bxv.rows_spec, ST_TRANS);
     RET(run_pass(so, 1, v));
   }
+  // temperature Helmholtz (branch 2: it only needs the old fields and its own convection term)
+  {
+    on(2);
+    const Base1& bxT = nv->sp_temp->b[0];
+    Prog t;
+    t.load(nv->Zf[2], bxo.rows_ortho);
+    t.load_stencil(nv->V1[2], bxT, 1.0, true);
+    emit_hh_axis(t, nv->hh[2], 0);
+    t.load(nv->KTT, bxT.rows_spec, 1.0, LD_ACC);
+    t.store(nv->temp->vhat->d, bxT.rows_spec, ST_TRANS);
+    RET(run_pass(so, 1, t));
+  }
+  RET(after(0, 1));
+  on(0);
   // ---- D: divergence of the intermediate velocity, pressure update part 1, Poisson rhs ----
   {
     const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
@@ -1494,17 +1549,6 @@ static int nav_update_fused(b2_navier* nv) {
     x.matvec(bxp);
     x.store(nv->R0, bxp.rows_spec, ST_TRANS);
     RET(run_pass(so, 1, x));
-  }
-  // temperature Helmholtz can go any time after B (it only needs the old fields)
-  {
-    const Base1& bxT = nv->sp_temp->b[0];
-    Prog t;
-    t.load(nv->Zf[2], bxo.rows_ortho);
-    t.load_stencil(nv->V1[2], bxT, 1.0, true);
-    emit_hh_axis(t, nv->hh[2], 0);
-    t.load(nv->KTT, bxT.rows_spec, 1.0, LD_ACC);
-    t.store(nv->temp->vhat->d, bxT.rows_spec, ST_TRANS);
-    RET(run_pass(so, 1, t));
   }
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
@@ -1568,16 +1612,22 @@ static int nav_update_fused(b2_navier* nv) {
       y.store(k == 0 ? nv->U1 : (k == 1 ? nv->U2 : nv->U3), l, ST_TRANS);
     }
     RET(run_pass(so, 0, y));
+    RET(after(1, 0)); RET(after(2, 0));
+    on(0);
     Prog x1; x1.load(nv->U1, bxp.rows_spec); x1.to_ortho(bxp); x1.deriv_axis(bxo, 1, sx); int l = x1.from_ortho(bxv);
     x1.store(nv->velx->vhat->d, l, ST_TRANS | ST_ACC, -1.0);
     RET(run_pass(so, 1, x1));
+    on(1);
     Prog x2; x2.load(nv->U2, bxp.rows_spec); x2.to_ortho(bxp); l = x2.from_ortho(bxv);
     x2.store(nv->vely->vhat->d, l, ST_TRANS | ST_ACC, -1.0);
     RET(run_pass(so, 1, x2));
+    on(2);
     Prog x3; x3.load(nv->U3, bxp.rows_spec); l = x3.to_ortho(bxp);
     x3.store(nv->pres->vhat->d, l, ST_TRANS | ST_ACC, 1.0 / dt);
     RET(run_pass(so, 1, x3));
   }
+  RET(after(0, 1)); RET(after(0, 2));   // join
+  on(0);
   nv->time += dt;
   return B2_OK;
 }
@@ -1624,8 +1674,8 @@ int b2_navier_div_norm(b2_navier* nv, double* out) {
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
 int b2_navier_set_mode(b2_navier* nv, int mode) {
-  // bit 0: fused schedule; bit 1: disable CUDA-graph replay
-  nv->fused = mode & 1; nv->use_graph = !(mode & 2); nv->warm_steps = 0;
+  // bit 0: fused schedule; bit 1: disable CUDA-graph replay; bit 2: disable parallel branches
+  nv->fused = mode & 1; nv->use_graph = !(mode & 2); nv->branches = !(mode & 4); nv->warm_steps = 0;
 #ifndef B2_EMU
   if (nv->graph) { cudaGraphExecDestroy(nv->graph); nv->graph = nullptr; }
 #endif

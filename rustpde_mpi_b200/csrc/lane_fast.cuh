@@ -237,23 +237,20 @@ __device__ __noinline__ void band_fast(const LaneProg& P, const LaneOp& op, doub
     const int hp = h >> 1;                 // -1 .. 2
     const int bx = Lay<LN>::pix(q + hp);   // (q + hp = -1 gives a base that is only valid from t = 1 on)
     const bool neg = (q + hp) < 0;
-    {
-      const double2 x = w2[neg ? 0 : bx];
-      const double2 cc = c ? ldg(c + q) : one;
-      if (!neg) y[0] = d2fma(cc, x, y[0]);
-    }
+    const int pl = q + M;
+    const bool okl = pl < HP && pl + hp < HP;
+    const double2 x0 = w2[neg ? 0 : bx], xl = w2[okl ? bx + E * PS : 0];
+    if (c) {
+      const double2 c0v = ldg(c + q), clv = ldg(c + (okl ? pl : 0));
+      if (!neg) y[0] = d2fma(c0v, x0, y[0]);
 #pragma unroll
-    for (int t = 1; t < E; t++) {          // p + hp <= M + 1 < HP: always in range
-      const double2 x = w2[bx + t * PS];
-      const double2 cc = c ? ldg(c + q + t * TPL) : one;
-      y[t] = d2fma(cc, x, y[t]);
-    }
-    {
-      const int p = q + M, pp = p + hp;
-      const bool ok = p < HP && pp < HP;
-      const double2 x = w2[ok ? bx + E * PS : 0];
-      const double2 cc = c ? ldg(c + (ok ? p : 0)) : one;
-      if (ok) y[E] = d2fma(cc, x, y[E]);
+      for (int t = 1; t < E; t++) y[t] = d2fma(ldg(c + q + t * TPL), w2[bx + t * PS], y[t]);   // p + hp <= M + 1 < HP: in range
+      if (okl) y[E] = d2fma(clv, xl, y[E]);
+    } else {
+      if (!neg) { y[0].x += x0.x; y[0].y += x0.y; }
+#pragma unroll
+      for (int t = 1; t < E; t++) { const double2 x = w2[bx + t * PS]; y[t].x += x.x; y[t].y += x.y; }
+      if (okl) { y[E].x += xl.x; y[E].y += xl.y; }
     }
   };
   if (h0 != 127) term(h0, c0);

@@ -85,6 +85,7 @@ struct LaneProg {
   int ld_bytes, st_bytes;     // slot pitch of the load ring / the store staging (multiples of 128)
   int ld_tx;                  // bytes one ring box delivers ((CH+1) tiles x LN lanes x 32)
   int w_off, ld_off, st_off;  // byte offsets inside dynamic shared memory (128-aligned)
+  int dsplit;                 // direct loads: tiles [0, dsplit) come by TMA, tiles [dsplit, in_tiles) by per-thread LDG at the same time
   int bulk1d;                 // LN == 4: the slab is contiguous, so slab-shaped copies are plain 1-D bulk copies (no tensor map)
   unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
   LaneOp ops[B2_MAXOPS];
@@ -383,15 +384,19 @@ __device__ __forceinline__ bool prefetch_next(const LaneProg& P, const SmemView&
 // loads
 // ---------------------------------------------------------------------------------------------
 // W = src: the slab lands in W as it is (zero-copy); elements at and beyond len are cleared afterwards.
+// The copy engine alone keeps only a few tens of KB in flight per SM, so the tail of the slab (tiles >= dsplit)
+// is fetched by the threads at the same time (16-byte LDGs, 8 in flight each): both streams overlap.
 template <int LN>
 __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, Prefetch& pf) {
+  constexpr int LSH = Lay<LN>::LSH;
+  const int T1 = P.dsplit;   // multiple of CHD or == in_tiles
   if (threadIdx.x == 0) {
     if (op.i2 & LD_AFTER_STORE) bulk_wait<0>();
     if (P.bulk1d) {
       const char* src = static_cast<const char*>(op.p0) + (size_t)pf.gl * P.in_tiles * 128;
-      mbar_arrive_expect_tx(sv.dfull, (uint32_t)P.in_tiles * 128u);
-      for (int c = 0; c < P.nchd; c++) {
-        const int t0 = c * P.CHD, t1 = min(t0 + P.CHD, P.in_tiles);
+      mbar_arrive_expect_tx(sv.dfull, (uint32_t)T1 * 128u);
+      for (int t0 = 0; t0 < T1; t0 += P.CHD) {
+        const int t1 = min(t0 + P.CHD, T1);
         bulk_load_1d(reinterpret_cast<char*>(sv.W) + (size_t)t0 * 128, src + (size_t)t0 * 128, (uint32_t)(t1 - t0) * 128u, sv.dfull);
       }
     } else {
@@ -400,9 +405,24 @@ __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, co
         tma_load_3d(reinterpret_cast<char*>(sv.W) + (size_t)c * P.CHD * LN * 32, tm, pf.lb * 4, c * P.CHD, pf.gl, sv.dfull);
     }
   }
-  mbar_wait(sv.dfull, pf.dphase);
-  pf.dphase ^= 1u;
+  if (P.bulk1d && T1 < P.in_tiles) {
+    if ((op.i2 & LD_AFTER_STORE) && T1 == 0) { if (threadIdx.x == 0) bulk_wait<0>(); __syncthreads(); }
+    const double2* src = reinterpret_cast<const double2*>(op.p0) + (size_t)pf.gl * P.in_tiles * 8;
+    double2* W2 = reinterpret_cast<double2*>(sv.W);
+    const int npc = P.in_tiles << LSH;
+    constexpr int U = 8;
+    for (int p0 = (T1 << LSH) + threadIdx.x; p0 < npc; p0 += U * P.NT) {
+      double2 v[U];
+#pragma unroll
+      for (int k = 0; k < U; k++) { const int pc = p0 + k * P.NT; v[k] = (pc < npc) ? src[pc] : make_double2(0.0, 0.0); }
+#pragma unroll
+      for (int k = 0; k < U; k++) { const int pc = p0 + k * P.NT; if (pc < npc) W2[pc] = v[k]; }
+    }
+  }
+  if (!P.bulk1d || T1 > 0) mbar_wait(sv.dfull, pf.dphase);
+  if (!P.bulk1d || T1 > 0) pf.dphase ^= 1u;
   const int len = op.i0, ntail = P.LP - len;
+  __syncthreads();
   for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
     const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
     sv.W[4 * l + Lay<LN>::eix(e)] = 0.0;

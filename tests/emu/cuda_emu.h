@@ -230,6 +230,9 @@ typedef void* cudaEvent_t;
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(8); return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = malloc(8); return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
