@@ -347,7 +347,7 @@ def poisson_eig(kind0, n0, c0, parity_split=None):
     cm = np.zeros((m, m))
     check(lib().b2_host_poisson_matrices(kind0, n0, float(c0), _dp(a0), _dp(cm)))
     if parity_split is None:
-        parity_split = m > 600
+        parity_split = m >= 16
     if not parity_split:
         cinv = np.linalg.inv(cm)
         lam, q = _eig_sorted(cinv @ a0)

@@ -271,7 +271,7 @@ int Base1::init(int C, int TPL) {
 struct PassCfg {
   int in_tiles, out_tiles, LP, TPL, C, E, groups, LN;
   bool fast;   // transform-sized lane: N = 2*E*TPL and LP >= N + 4 (lane_fast.cuh)
-  int NT, CH, nch, NS, CHD, nchd, ld_bytes, st_bytes, ld_tx, w_off, ld_off, st_off;   // TMA pipeline geometry (lane_kernel.cuh)
+  int NT, CH, nch, NS, NP, CHD, nchd, ld_bytes, st_bytes, ld_tx, w_off, ld_off, st_off;   // TMA pipeline geometry (lane_kernel.cuh)
   size_t smem;
 };
 
@@ -308,6 +308,12 @@ struct b2_solver {
   int m0 = 0;
   DVecD fwd, bwd;           // dense (m0 x m0) row-major
   DVecD pfl, pid, pu1, pu2; // per-lane LU in scan layout
+  // parity blocks (single-GPU fused step): the eigenvectors couple indices of equal parity only, so with the modes
+  // grouped by parity class both GEMMs split into two half-size GEMMs (half the flops)
+  bool blocks = false;
+  int ce = 0, co = 0;       // even / odd indices (= modes of the even / odd class)
+  DVecD fe, fo, be, bo;     // fwd_e (ce x ce), fwd_o (co x co), bwd_e, bwd_o, row-major
+  DVecD qfl, qid, qu1, qu2; // per-lane LU for the parity-grouped mode order
   double* plain[2] = {nullptr, nullptr};
 };
 
@@ -372,8 +378,8 @@ struct Prog {
     o->code = code; o->a = 1.0;
     return o;
   }
-  void load(const double* src, int len, double a = 1.0, int flags = 0) { LaneOp* o = add(OP_LOAD); o->p0 = src; o->i0 = len; o->a = a; o->i2 = flags; }
-  void store(double* dst, int len, int flags, double a = 1.0) { LaneOp* o = add(OP_STORE); o->p0 = dst; o->i0 = len; o->a = a; o->i2 = flags; }
+  void load(const double* src, int len, double a = 1.0, int flags = 0, int i1 = 0) { LaneOp* o = add(OP_LOAD); o->p0 = src; o->i0 = len; o->a = a; o->i2 = flags; o->i1 = i1; }
+  void store(double* dst, int len, int flags, double a = 1.0, int i1 = 0) { LaneOp* o = add(OP_STORE); o->p0 = dst; o->i0 = len; o->a = a; o->i2 = flags; o->i1 = i1; }
   void band(int len_out, int len_in, int o0, const double* c0, int o1, const double* c1, int o2 = 127, const double* c2 = nullptr) {
     LaneOp* o = add(OP_BAND); o->i0 = len_out; o->i2 = len_in; o->i1 = pack_offs(o0, o1, o2); o->p0 = c0; o->p1 = c1; o->p2 = c2;
   }
@@ -469,7 +475,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
   p.group0 = ctx->rank * (c.groups / ctx->nranks); p.groups_per_rank = c.in_tiles / ctx->nranks; p.rank = ctx->rank;
   p.prof = ctx->d_prof; p.LN = c.LN;
-  p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
+  p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.NP = c.NP; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
   p.w_off = c.w_off; p.ld_off = c.ld_off; p.st_off = c.st_off;
   p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
   {   // share of a direct load that the copy engine takes (percent, B2_SPLIT; the threads fetch the rest)
@@ -573,11 +579,11 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   const int tile_bytes = c->LN * 32;
   c->nchd = (c->in_tiles + 255) / 256;                     // direct copies: boxes of <= 256 tiles straight into / out of W
   c->CHD = roundup((c->in_tiles + c->nchd - 1) / c->nchd, 4 / c->LN);   // box bytes multiple of 128: TMA shared-memory alignment
-  const size_t budget = 227 * 1024, fixed = 256 + B2_SCRATCH;
+  const size_t budget = 227 * 1024, fixed = 256 + B2_PROGCOPY + B2_SCRATCH;
   const size_t wbytes = (size_t)roundup(c->nchd * c->CHD * tile_bytes, 128);   // the last direct box may overhang the lane by < nchd tiles
   if (fixed + wbytes > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
-  c->NS = 2;
-  if (const char* e = getenv("B2_NS")) { int v = atoi(e); if (v >= 1 && v <= B2_MAXLD) c->NS = v; }
+  c->NS = 1;   // look-ahead slots (measured on C4: 1 beats 2 and 3 -- larger chunks, fewer per-chunk hand-offs)
+  if (const char* e = getenv("B2_NS")) { int v = atoi(e); if (v >= 1 && v <= B2_MAXLD - B2_ST_SLOTS) c->NS = v; }
   // short lanes: keep the CTA near 72 KB so that three fit on an SM; long lanes: one CTA owns the SM
   size_t room = budget - fixed - wbytes;
   if (wbytes <= 40 * 1024) room = std::min(room, std::max((size_t)8192, (size_t)72 * 1024 - std::min((size_t)72 * 1024, fixed + wbytes)));
@@ -588,9 +594,10 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   c->CH = (c->in_tiles + c->nch - 1) / c->nch;
   c->ld_tx = (c->CH + 1) * tile_bytes;
   c->ld_bytes = roundup(c->ld_tx, 128);
-  c->st_bytes = roundup(c->CH * tile_bytes, 128);
-  c->w_off = (int)fixed; c->ld_off = c->w_off + (int)wbytes; c->st_off = c->ld_off + c->NS * c->ld_bytes;
-  c->smem = (size_t)c->st_off + (size_t)B2_ST_SLOTS * c->st_bytes;
+  c->st_bytes = c->ld_bytes;   // one pool of NP = 3 + NS slots: 0..2 stage stores, 3.. take look-ahead loads
+  c->NP = B2_ST_SLOTS + c->NS;
+  c->w_off = (int)fixed; c->ld_off = c->w_off + (int)wbytes; c->st_off = c->ld_off;
+  c->smem = (size_t)c->ld_off + (size_t)c->NP * c->ld_bytes;
   if (c->smem > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
   return B2_OK;
 }
@@ -767,26 +774,56 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
   const PassCfg& c = sp->cfg[0];
   const int nr = sp->ctx->nranks, lane0 = sp->ctx->rank * (c.groups / nr) * 4, lane1 = lane0 + (c.groups / nr) * 4;
   const size_t total = (size_t)(c.groups / nr) * c.C * 4 * c.TPL * 2;
-  std::vector<double> pfl(total, 0.0), pid(total, 0.0), pu1(total, 0.0), pu2(total, 0.0);
   const int m1 = b1.m;
-  Diags mat(m1);
-  for (int lane = lane0; lane < std::min(lanes, lane1); lane++) {
-    const double lm = lam[lane];
-    for (int i = 0; i < m1; i++) {
-      mat.low[i] = lap1.low[i] + mass1.low[i] * lm;
-      mat.dia[i] = lap1.dia[i] + mass1.dia[i] * lm;
-      mat.up1[i] = lap1.up1[i] + mass1.up1[i] * lm;
-      mat.up2[i] = lap1.up2[i] + mass1.up2[i] * lm;
+  auto build_lanes = [&](const std::vector<double>& lamv, DVecD* dfl, DVecD* did, DVecD* du1, DVecD* du2) -> int {
+    std::vector<double> pfl(total, 0.0), pid(total, 0.0), pu1(total, 0.0), pu2(total, 0.0);
+    Diags mat(m1);
+    for (int lane = lane0; lane < std::min(lanes, lane1); lane++) {
+      const double lm = lamv[lane];
+      for (int i = 0; i < m1; i++) {
+        mat.low[i] = lap1.low[i] + mass1.low[i] * lm;
+        mat.dia[i] = lap1.dia[i] + mass1.dia[i] * lm;
+        mat.up1[i] = lap1.up1[i] + mass1.up1[i] * lm;
+        mat.up2[i] = lap1.up2[i] + mass1.up2[i] * lm;
+      }
+      LuVecs lu = sweep(mat);
+      const int g = (lane - lane0) / 4, l = lane % 4;
+      for (int i = 0; i < m1; i++) {
+        const int pr = i / 2, q = pr / c.C, t = pr % c.C;
+        const size_t k = ((((size_t)g * c.C + t) * c.TPL + q) * 4 + l) * 2 + (i & 1);
+        pfl[k] = lu.fl[i]; pid[k] = lu.id[i]; pu1[k] = lu.u1[i]; pu2[k] = lu.u2[i];
+      }
     }
-    LuVecs lu = sweep(mat);
-    const int g = (lane - lane0) / 4, l = lane % 4;
-    for (int i = 0; i < m1; i++) {
-      const int pr = i / 2, q = pr / c.C, t = pr % c.C;
-      const size_t k = ((((size_t)g * c.C + t) * c.TPL + q) * 4 + l) * 2 + (i & 1);
-      pfl[k] = lu.fl[i]; pid[k] = lu.id[i]; pu1[k] = lu.u1[i]; pu2[k] = lu.u2[i];
+    RET(dfl->upload(pfl)); RET(did->upload(pid)); RET(du1->upload(pu1)); RET(du2->upload(pu2));
+    return B2_OK;
+  };
+  RET(build_lanes(lam, &s->pfl, &s->pid, &s->pu1, &s->pu2));
+  if (s->dense && nr == 1 && getenv("B2_NOBLOCKS") == nullptr) {
+    // parity classes of the modes: row r of fwd (= mode r) touches even columns only, or odd columns only
+    const int m0 = s->m0, ce = (m0 + 1) / 2, co = m0 / 2;
+    std::vector<int> cls(m0, 0), perm;
+    bool ok = true;
+    for (int r = 0; r < m0 && ok; r++) {
+      bool ev = false, od = false;
+      for (int i = 0; i < m0; i++) {
+        if (fwd[(size_t)r * m0 + i] != 0.0) ((i & 1) ? od : ev) = true;
+        if (bwd[(size_t)i * m0 + r] != 0.0) ((i & 1) ? od : ev) = true;
+      }
+      if (ev && od) ok = false;
+      cls[r] = od ? 1 : 0;
+    }
+    for (int k = 0; k < 2 && ok; k++) for (int r = 0; r < m0; r++) if (cls[r] == k) perm.push_back(r);
+    int ne = 0; for (int r = 0; r < m0; r++) ne += (cls[r] == 0);
+    if (ok && ne == ce) {
+      std::vector<double> fe((size_t)ce * ce), fo((size_t)co * co), be((size_t)ce * ce), bo((size_t)co * co), lam2(lam.size());
+      for (int r = 0; r < ce; r++) for (int k = 0; k < ce; k++) { fe[(size_t)r * ce + k] = fwd[(size_t)perm[r] * m0 + 2 * k]; be[(size_t)k * ce + r] = bwd[(size_t)(2 * k) * m0 + perm[r]]; }
+      for (int r = 0; r < co; r++) for (int k = 0; k < co; k++) { fo[(size_t)r * co + k] = fwd[(size_t)perm[ce + r] * m0 + 2 * k + 1]; bo[(size_t)k * co + r] = bwd[(size_t)(2 * k + 1) * m0 + perm[ce + r]]; }
+      for (int r = 0; r < m0; r++) lam2[r] = lam[perm[r]];
+      RET(s->fe.upload(fe)); RET(s->fo.upload(fo)); RET(s->be.upload(be)); RET(s->bo.upload(bo));
+      RET(build_lanes(lam2, &s->qfl, &s->qid, &s->qu1, &s->qu2));
+      s->blocks = true; s->ce = ce; s->co = co;
     }
   }
-  RET(s->pfl.upload(pfl)); RET(s->pid.upload(pid)); RET(s->pu1.upload(pu1)); RET(s->pu2.upload(pu2));
   *out = s;
   return B2_OK;
 }
@@ -1200,6 +1237,7 @@ int b2_solver_destroy(b2_solver* s) {
   if (!s) return B2_OK;
   for (int ax = 0; ax < 2; ax++) { s->fl[ax].release(); s->id[ax].release(); s->u1[ax].release(); s->u2[ax].release(); s->sd[ax].release(); }
   s->fwd.release(); s->bwd.release(); s->pfl.release(); s->pid.release(); s->pu1.release(); s->pu2.release();
+  s->fe.release(); s->fo.release(); s->be.release(); s->bo.release(); s->qfl.release(); s->qid.release(); s->qu1.release(); s->qu2.release();
   for (auto& p : s->plain) ctx_free(s->sp->ctx, p);
   delete s;
   return B2_OK;
@@ -1552,7 +1590,7 @@ static int nav_update_fused(b2_navier* nv) {
   }
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
-  const double* pseu_src; int pseu_flags;
+  const double* pseu_src; int pseu_flags, pseu_i1 = 0;
   if (ps->dense && ctx->nranks > 1) {
     // slabs: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y, row-major)
     const double one = 1.0, zero = 0.0;
@@ -1574,6 +1612,24 @@ static int nav_update_fused(b2_navier* nv) {
     Prog x2; x2.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, ps->m0, ST_TRANS);
     RET(run_pass(so, 1, x2));
     pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
+  } else if (ps->dense && ps->blocks) {
+    // parity-grouped: rows of the GEMM operands are stored even indices first, then odd (ST_PSPLIT / LD_PSPLIT);
+    // G1_e = fwd_e G0_e, G1_o = fwd_o G0_o  (row-major views; half the flops of the full product)
+    const double one = 1.0, zero = 0.0;
+    const int m0 = ps->m0, ce = ps->ce, co = ps->co;
+    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN | ST_PSPLIT, 1.0, m0);
+    RET(run_pass(so, 0, y));
+    RET(gemm_mark(ctx));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ce, ce, &one, nv->G0, P1, ps->fe.d, ce, &zero, nv->G1, P1));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, co, co, &one, nv->G0 + (size_t)ce * P1, P1, ps->fo.d, co, &zero, nv->G1 + (size_t)ce * P1, P1));
+    RET(gemm_mark(ctx)); ctx->launches += 2;
+    Prog y2; y2.load(nv->G1, byp.m, 1.0, LD_PLAIN); y2.fdma(byp.m, ps->qfl.d, ps->qid.d, ps->qu1.d, ps->qu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_PLAIN);
+    RET(run_pass(so, 0, y2));
+    RET(gemm_mark(ctx));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ce, ce, &one, nv->G0, P1, ps->be.d, ce, &zero, nv->G1, P1));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, co, co, &one, nv->G0 + (size_t)ce * P1, P1, ps->bo.d, co, &zero, nv->G1 + (size_t)ce * P1, P1));
+    RET(gemm_mark(ctx)); ctx->launches += 2;
+    pseu_src = nv->G1; pseu_flags = LD_PLAIN | LD_PSPLIT; pseu_i1 = m0;
   } else if (ps->dense) {
     const double one = 1.0, zero = 0.0;
     Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN);
@@ -1600,7 +1656,7 @@ static int nav_update_fused(b2_navier* nv) {
     const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
     Prog y;
     for (int k = 0; k < 3; k++) {
-      y.load(pseu_src, byp.m, 1.0, pseu_flags);
+      y.load(pseu_src, byp.m, 1.0, pseu_flags, pseu_i1);
       if (pseu_flags & LD_PLAIN) {   // single-GPU dense path: pseu still sits in the GEMM's row-major buffer
         y.zeroelem(0, 0);
         if (k == 0) y.store(nv->pseu->vhat->d, byp.m, 0);

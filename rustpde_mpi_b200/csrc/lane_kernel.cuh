@@ -26,6 +26,7 @@
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 #include <stdint.h>
+#include <stddef.h>
 #include "async_ops.cuh"
 
 #define B2_MAXOPS 24
@@ -33,6 +34,7 @@
 #define B2_ST_SLOTS 3    // store-staging slots (3: one CTA barrier per chunk, see store_staged)
 #define B2_MAXLD 8       // max load-ring slots
 #define B2_SCRATCH 8192  // bytes of scan scratch (16 warps x 4 lanes x (Aff2 map + state))
+#define B2_PROGCOPY 2048 // shared-memory copy of the program header + ops (everything of LaneProg in front of tm[])
 
 enum LaneOpCode {
   OP_LOAD = 1,     // W = [W +|*] a * src           i0=len  i2=flags(LD_*)       p0=src (p1 = stencil coefficients)
@@ -52,10 +54,12 @@ enum LaneOpCode {
 enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
        LD_TMA = 16,          // set by the launcher: the slab streams through the TMA ring (tensor map tm[op])
        LD_AFTER_STORE = 32,  // set by the launcher: the source was stored earlier in this program (flush stores first)
-       LD_DIRECT = 64 };     // set by the launcher: zero-copy TMA straight into W (plain load, a == 1)
+       LD_DIRECT = 64,       // set by the launcher: zero-copy TMA straight into W (plain load, a == 1)
+       LD_PSPLIT = 128 };    // plain sources: rows are stored parity-split (row r < i1 lives at r/2, odd rows after the even ones)
 enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16,
        ST_TMA = 32,          // set by the launcher: staged, bulk tensor store / reduction
-       ST_DIRECT = 64 };     // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
+       ST_DIRECT = 64,       // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
+       ST_PSPLIT = 128 };    // plain destinations, same orientation: store row r < i1 at r/2 (even) or ceil(i1/2) + r/2 (odd)
 enum { FD_PERLANE = 1, FD_NOU2 = 2 };
 
 struct LaneOp {
@@ -80,7 +84,8 @@ struct LaneProg {
   int LN;         // lanes per CTA: 4 (a whole lane group) or 2 (half a group; grid = 2 x groups)
   int NT;         // threads per CTA = LN*TPL (multiple of 32)
   // TMA pipeline geometry
-  int CH, nch, NS;            // ring / staging: tiles per chunk, chunks per lane, load-ring slots (one halo tile in front)
+  int CH, nch, NS, NP;        // chunk pool: tiles per chunk, chunks per lane; NP = 3 + NS slots of CH+1 tiles (one halo tile in front):
+                              // slots 0..2 stage stores, slots 3.. take look-ahead loads, a load op in progress uses all NP
   int CHD, nchd;              // direct copies: tiles per box (<= 256), boxes per lane
   int ld_bytes, st_bytes;     // slot pitch of the load ring / the store staging (multiples of 128)
   int ld_tx;                  // bytes one ring box delivers ((CH+1) tiles x LN lanes x 32)
@@ -350,33 +355,46 @@ struct SmemView {
 __device__ __forceinline__ SmemView smem_view(const LaneProg& P, char* base) {
   SmemView v;
   v.full = reinterpret_cast<uint64_t*>(base); v.empty = v.full + B2_MAXLD; v.dfull = v.full + 2 * B2_MAXLD;
-  v.scratch = base + 256; v.W = reinterpret_cast<double*>(base + P.w_off); v.ld = base + P.ld_off; v.st = base + P.st_off;
+  v.scratch = base + 256 + B2_PROGCOPY; v.W = reinterpret_cast<double*>(base + P.w_off); v.ld = base + P.ld_off; v.st = base + P.st_off;
   return v;
 }
-struct Prefetch { int it, op, c, gl, lb; unsigned dphase; };   // used by thread 0 (dphase by everyone)
+struct Prefetch {             // producer state (thread 0) + the phase of the direct-load barrier (everyone)
+  int op, c, slot, gl, lb;    // cursor: next chunk (op, c) to request and its slot; this CTA's lane group / first lane
+  const B2TMap* tms;          // the tensor maps stay in parameter space (the program itself is read from its shared-memory copy)
+  unsigned pph, out;          // per-slot parity of the next request; slots whose chunk thread 0 has not consumed yet
+  unsigned dphase;
+};
 __device__ __forceinline__ int next_ring_load(const LaneProg& P, int o) {
   while (o < P.nops && !(P.ops[o].code == OP_LOAD && (P.ops[o].i2 & LD_TMA))) o++;
   return o;
 }
-// Request the next chunk of the program (thread 0).  A load flagged LD_AFTER_STORE re-reads an array this CTA
-// stored earlier in the program: it is only requested from inside its own op (cur_op), after the stores drained.
+__device__ __forceinline__ int slot_next(int slot, int NP) { return slot + 1 == NP ? 0 : slot + 1; }   // chunk c lives in slot (3 + c) mod NP
+// Request the next chunk of the program if its slot is free (thread 0).  Chunk c of a load goes to slot
+// (3 + c) mod NP.  Ahead of its own op (cur_op) a load may only use the look-ahead slots 3.. (its first NS
+// chunks), because slots 0..2 stage the stores of the ops in between; inside its op it uses the whole pool.
+// A load flagged LD_AFTER_STORE re-reads an array this CTA stored earlier in the program and is never
+// requested ahead of its op.
 __device__ __forceinline__ bool prefetch_next(const LaneProg& P, const SmemView& sv, Prefetch& pf, int cur_op) {
   if (pf.op >= P.nops) return false;
-  if ((P.ops[pf.op].i2 & LD_AFTER_STORE) && pf.op != cur_op) return false;
-  const int slot = pf.it % P.NS; const unsigned ph = (unsigned)(pf.it / P.NS) & 1u;
-  mbar_wait(&sv.empty[slot], ph ^ 1u);
+  if (pf.op != cur_op && ((P.ops[pf.op].i2 & LD_AFTER_STORE) || pf.c >= P.NS)) return false;
+  const int slot = pf.slot;
+  if (pf.out & (1u << slot)) return false;          // its previous chunk is still waiting for this very thread
+  if (slot < 3) bulk_wait_read<0>();                // a store may still be reading this staging slot
+  mbar_wait(&sv.empty[slot], ((pf.pph >> slot) & 1u) ^ 1u);   // every warp has released the previous chunk
+  char* dst = sv.ld + (size_t)slot * P.ld_bytes;
   if (P.bulk1d) {   // contiguous slab: tiles [J0-1, J0+CH) clipped to the lane, no halo in front of the first chunk
     const int J0 = pf.c * P.CH, t0 = J0 > 0 ? J0 - 1 : 0, t1 = min(J0 + P.CH, P.in_tiles);
     const uint32_t bytes = (uint32_t)(t1 - t0) * 128u;
     mbar_arrive_expect_tx(&sv.full[slot], bytes);
-    bulk_load_1d(sv.ld + (size_t)slot * P.ld_bytes + (size_t)(t0 - (J0 - 1)) * 128,
+    bulk_load_1d(dst + (size_t)(t0 - (J0 - 1)) * 128,
                  static_cast<const char*>(P.ops[pf.op].p0) + ((size_t)pf.gl * P.in_tiles + t0) * 128, bytes, &sv.full[slot]);
   } else {
     mbar_arrive_expect_tx(&sv.full[slot], (uint32_t)P.ld_tx);
-    tma_load_3d(sv.ld + (size_t)slot * P.ld_bytes, &P.tm[pf.op], pf.lb * 4, pf.c * P.CH - 1, pf.gl, &sv.full[slot]);
+    tma_load_3d(dst, pf.tms + pf.op, pf.lb * 4, pf.c * P.CH - 1, pf.gl, &sv.full[slot]);
   }
-  pf.it++;
-  if (++pf.c == P.nch) { pf.c = 0; pf.op = next_ring_load(P, pf.op + 1); }
+  pf.pph ^= 1u << slot; pf.out |= 1u << slot;
+  pf.slot = slot_next(slot, P.NP);
+  if (++pf.c == P.nch) { pf.c = 0; pf.slot = 3; pf.op = next_ring_load(P, pf.op + 1); }
   return true;
 }
 
@@ -422,7 +440,7 @@ __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, co
   if (!P.bulk1d || T1 > 0) mbar_wait(sv.dfull, pf.dphase);
   if (!P.bulk1d || T1 > 0) pf.dphase ^= 1u;
   const int len = op.i0, ntail = P.LP - len;
-  __syncthreads();
+  if (P.bulk1d && T1 < P.in_tiles) __syncthreads();   // the threads' share has to be complete before the tail is cleared
   for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
     const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
     sv.W[4 * l + Lay<LN>::eix(e)] = 0.0;
@@ -434,27 +452,29 @@ __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, co
 // layout, so the combine is elementwise; t = 0 is the halo tile in front of the chunk (the composite ->
 // orthonormal stencil needs element j-2 of the same lane).
 template <int LN>
-__device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int o, const SmemView& sv, int& ld_it, Prefetch& pf) {
+__device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int o, const SmemView& sv, unsigned& cph, Prefetch& pf) {
   constexpr int LSH = Lay<LN>::LSH;
   const int NT = P.NT, len = op.i0;
   const double a = op.a;
   const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, sten = op.i2 & LD_STENCIL;
   const double* sc = reinterpret_cast<const double*>(op.p1);
   double2* W2 = reinterpret_cast<double2*>(sv.W);
-  if ((op.i2 & LD_AFTER_STORE) && threadIdx.x == 0) {   // the stored data must have landed before it is read back
-    bulk_wait<0>();
-    while (pf.it - ld_it < P.NS && prefetch_next(P, sv, pf, o)) {}
+  if (threadIdx.x == 0) {
+    if (op.i2 & LD_AFTER_STORE) bulk_wait<0>();   // the stored data must have landed before it is read back
+    while (prefetch_next(P, sv, pf, o)) {}         // inside its own op a load may fill the whole pool
   }
-  const int npc = P.CH << LSH;
-  for (int c = 0; c < P.nch; c++, ld_it++) {
-    const int slot = ld_it % P.NS; const unsigned ph = (unsigned)(ld_it / P.NS) & 1u;
-    mbar_wait(&sv.full[slot], ph);
-    const double2* st = reinterpret_cast<const double2*>(sv.ld + (size_t)slot * P.ld_bytes) + (1 << LSH);
-    const int J0 = c * P.CH;
+  const int CH = P.CH, nch = P.nch, NP = P.NP, ld_bytes = P.ld_bytes, in_tiles = P.in_tiles;
+  const int npc = CH << LSH;
+  int slot = 3;
+  for (int c = 0; c < nch; c++, slot = slot_next(slot, NP)) {
+    mbar_wait(&sv.full[slot], (cph >> slot) & 1u);
+    cph ^= 1u << slot;
+    const double2* st = reinterpret_cast<const double2*>(sv.ld + (size_t)slot * ld_bytes) + (1 << LSH);
+    const int J0 = c * CH;
 #pragma unroll 2
     for (int pc = threadIdx.x; pc < npc; pc += NT) {
       const int J = J0 + (pc >> LSH), j0 = 4 * J + 2 * (pc & 1);
-      if (J >= P.in_tiles) continue;
+      if (J >= in_tiles) continue;
       double2 v = st[pc];
       if (sten && j0 >= 2) {
         const double2 u = (pc & 1) ? st[pc - 1] : st[pc - (1 << LSH) + 1];
@@ -470,7 +490,7 @@ __device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int 
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&sv.empty[slot]);
-    if (threadIdx.x == 0) prefetch_next(P, sv, pf, o);   // waits until every warp has released a slot, then refills it
+    if (threadIdx.x == 0) { pf.out &= ~(1u << slot); while (prefetch_next(P, sv, pf, o)) {} }
   }
   __syncthreads();
 }
@@ -487,6 +507,7 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
   const size_t slab = (size_t)gl * P.in_tiles * 8;  // in double2 units
   const double* sc = reinterpret_cast<const double*>(op.p1);
   double2* W2 = reinterpret_cast<double2*>(sv.W);
+  const int psplit = (op.i2 & LD_PSPLIT) ? op.i1 : 0;   // rows < psplit of a plain source are stored parity-split
   for (int p0 = threadIdx.x; p0 < npieces; p0 += U * T) {
     double2 v[U], u[U];
 #pragma unroll
@@ -495,7 +516,9 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
       const int J = pc >> LSH, l = (pc >> 1) & (LN - 1), j0 = 4 * J + (pc & 1) * 2;
       v[k] = make_double2(0.0, 0.0); u[k] = make_double2(0.0, 0.0);
       if (pc < npieces && j0 < len) {
-        v[k] = plain ? src[((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1]
+        int row = 4 * gl + lb + l;
+        if (row < psplit) row = (row & 1) ? ((psplit + 1) >> 1) + (row >> 1) : (row >> 1);
+        v[k] = plain ? src[((size_t)row * P.in_tiles * 4 + j0) >> 1]
                      : src[slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1)];
         if (sten && j0 >= 2) {   // composite -> orthonormal on the fly: + p1[j] * src[j-2]  (tiled sources only)
           const int jm = j0 - 2;
@@ -563,10 +586,12 @@ __device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, c
   const double a = op.a;
   const double* W = sv.W;
   const double2* W2 = reinterpret_cast<const double2*>(sv.W);
-  const int npc = P.CH << LSH;
-  for (int c = 0; c < P.nch; c++, st_it++) {
-    double2* st = reinterpret_cast<double2*>(sv.st + (size_t)(st_it % B2_ST_SLOTS) * P.st_bytes);
-    const int J0 = c * P.CH;
+  const int CH = P.CH, nch = P.nch, st_bytes = P.st_bytes, in_tiles = P.in_tiles;
+  const bool bulk1d = P.bulk1d;
+  const int npc = CH << LSH;
+  for (int c = 0; c < nch; c++, st_it = (st_it + 1 == B2_ST_SLOTS ? 0 : st_it + 1)) {
+    double2* st = reinterpret_cast<double2*>(sv.st + (size_t)st_it * st_bytes);
+    const int J0 = c * CH;
     if (threadIdx.x == 0) bulk_wait_read<B2_ST_SLOTS - 2>();
     if (flags & ST_TRANS) {
       // slot layout [tile][jl][lane]: each 4x4 tile transposed.  Piece (tile, jl, lane pair lp) = elements
@@ -601,9 +626,9 @@ __device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, c
     if (threadIdx.x == 0) {
       if (flags & ST_TRANS) {
         if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);
-      } else if (P.bulk1d) {
-        char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + ((size_t)gl * P.in_tiles + J0) * 128;
-        const uint32_t bytes = (uint32_t)(min(J0 + P.CH, P.in_tiles) - J0) * 128u;
+      } else if (bulk1d) {
+        char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + ((size_t)gl * in_tiles + J0) * 128;
+        const uint32_t bytes = (uint32_t)(min(J0 + CH, in_tiles) - J0) * 128u;
         if (flags & ST_ACC) bulk_reduce_add_1d(dst, st, bytes); else bulk_store_1d(dst, st, bytes);
       } else {
         if (flags & ST_ACC) tma_reduce_add_3d(tm, lb * 4, J0, gl, st); else tma_store_3d(tm, lb * 4, J0, gl, st);
@@ -657,7 +682,9 @@ __device__ __noinline__ void store_threads(const LaneProg& P, const LaneOp& op, 
         v.x = a * w.x;
         v.y = (j0 + 1 < len) ? a * w.y : 0.0;
       }
-      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * gl + lb + l) * P.in_tiles * 4 + j0) >> 1)
+      int row = 4 * gl + lb + l;
+      if ((flags & ST_PSPLIT) && row < op.i1) row = (row & 1) ? ((op.i1 + 1) >> 1) + (row >> 1) : (row >> 1);
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)row * P.in_tiles * 4 + j0) >> 1)
                                       : (slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1));
       if (flags & ST_ACC) { double2 ov = dst[idx]; v.x += ov.x; v.y += ov.y; }
       dst[idx] = v;
@@ -1048,40 +1075,52 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
 // TPLC = threads per lane as a compile-time constant for transform-sized lanes (N = 2*E*TPLC: the hot operators
 // then run their compile-time-geometry versions of lane_fast.cuh), 0 = generic geometry read from the program.
 template <int E, int LN, int TPLC>
-__global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg P) {
+__global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg Pp) {
   B2_DYN_SMEM(char, smem_raw);
+  // The ops run as separate (non-inlined) functions that get the program by reference; a reference into
+  // parameter space degrades to generic loads with global-memory latency, so the header and the op list are
+  // copied into shared memory once and everything but the tensor maps is read from there.
+  static_assert(offsetof(LaneProg, tm) <= B2_PROGCOPY, "program copy area too small");
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Pp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + 256);
+    for (int i = threadIdx.x; i < (int)(offsetof(LaneProg, tm) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const LaneProg& P = *reinterpret_cast<const LaneProg*>(smem_raw + 256);
   const SmemView sv = smem_view(P, smem_raw);
   double* W = sv.W;
   void* scratch = sv.scratch;
   const int gl = blockIdx.x / (4 / LN);   // local lane group (addresses this GPU's slab)
   const int g = P.group0 + gl;            // global lane group (mode indices, transposed stores)
   const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;
-  Prefetch pf; pf.it = 0; pf.c = 0; pf.gl = gl; pf.lb = lb; pf.op = P.nops; pf.dphase = 0;
+  Prefetch pf; pf.c = 0; pf.slot = 3; pf.gl = gl; pf.lb = lb; pf.op = P.nops; pf.pph = 0; pf.out = 0; pf.dphase = 0; pf.tms = Pp.tm;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.NS; i++) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], P.NT / 32); }
+    for (int i = 0; i < P.NP; i++) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], P.NT / 32); }
     mbar_init(sv.dfull, 1);
     mbar_fence_init();
     for (int o = 0; o < P.nops; o++)
       if ((P.ops[o].code == OP_LOAD && (P.ops[o].i2 & (LD_TMA | LD_DIRECT))) || (P.ops[o].code == OP_STORE && (P.ops[o].i2 & (ST_TMA | ST_DIRECT))))
-        tmap_prefetch(&P.tm[o]);
+        tmap_prefetch(&Pp.tm[o]);
     pf.op = next_ring_load(P, 0);
-    for (int i = 0; i < P.NS; i++) prefetch_next(P, sv, pf, -1);
+    while (prefetch_next(P, sv, pf, -1)) {}
   }
   __syncthreads();
-  int ld_it = 0, st_it = 0;
+  unsigned cph = 0;   // per-slot parity of the next chunk to consume
+  int st_it = 0;
   for (int o = 0; o < P.nops; o++) {
     const LaneOp& op = P.ops[o];
     long long t0 = 0;
     if (P.prof) t0 = clock64();
     switch (op.code) {
       case OP_LOAD:
-        if (op.i2 & LD_DIRECT) load_direct<LN>(P, op, &P.tm[o], sv, pf);
-        else if (op.i2 & LD_TMA) load_ring<LN>(P, op, o, sv, ld_it, pf);
+        if (op.i2 & LD_DIRECT) load_direct<LN>(P, op, &Pp.tm[o], sv, pf);
+        else if (op.i2 & LD_TMA) load_ring<LN>(P, op, o, sv, cph, pf);
         else load_threads<LN, (E == 16 ? 8 : 4)>(P, op, sv, gl, lb);
         break;
       case OP_STORE:
-        if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &P.tm[o], sv, gl, lb);
-        else if (op.i2 & ST_TMA) store_staged<LN>(P, op, &P.tm[o], sv, g, gl, lb, st_it);
+        if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &Pp.tm[o], sv, gl, lb);
+        else if (op.i2 & ST_TMA) store_staged<LN>(P, op, &Pp.tm[o], sv, g, gl, lb, st_it);
         else store_threads<LN>(P, op, sv, g, gl, lb);
         break;
       case OP_BAND:
