@@ -130,6 +130,8 @@ int b2_navier_update(b2_navier* nav, int nsteps);            /* Integrate::updat
 int b2_navier_div_norm(b2_navier* nav, double* out);         /* navier_eq.rs:32-49 (exit() NaN guard) */
 int b2_navier_get_time(const b2_navier* nav, double* t);
 int b2_navier_set_mode(b2_navier* nav, int mode);            /* bit0: fused schedule (default on); bit1: no CUDA-graph replay */
+/* schedule facts for bench.py: out[8] = {parity-block GEMMs, P0, P1, m0, ce, co, parallel branches, launches per step} */
+int b2_navier_info(const b2_navier* nv, long long* out8);
 int b2_navier_launch_count(const b2_navier* nav, long long* kernels_per_step);
 int b2_navier_poisson_matrices(b2_navier* nav, double* a0, double* cmat0, int* m0);
 

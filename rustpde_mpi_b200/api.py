@@ -496,6 +496,13 @@ class Navier2D:
         check(lib().b2_navier_launch_count(self._h, C.byref(k)))
         return k.value
 
+    def info(self):
+        """Schedule facts: parity-block GEMMs on/off, padded sizes, Poisson block sizes, parallel branches."""
+        v = (C.c_longlong * 8)()
+        check(lib().b2_navier_info(self._h, v))
+        keys = ("parity_blocks", "P0", "P1", "m0", "ce", "co", "branches", "launches_per_step")
+        return dict(zip(keys, (int(x) for x in v)))
+
     def state(self):
         """This rank's slabs of the four spectral state arrays."""
         return {k: getattr(self, k).vhat for k in ("temp", "velx", "vely", "pres")}

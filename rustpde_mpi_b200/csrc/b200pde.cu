@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -149,6 +150,9 @@ static LuVecs sweep(const Diags& a) {
   return r;
 }
 
+// natural-order band coefficient vector -> its scan-layout copy (same chunking as the LU coefficients of that axis)
+static std::map<const void*, const void*>& scan_of() { static std::map<const void*, const void*> m; return m; }
+
 struct Base1 {
   int kind = 0, n = 0, m = 0;
   bool cheb = false, composite = false;
@@ -156,6 +160,7 @@ struct Base1 {
   int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
   DVecD d_sten2, d_sten2s, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
+  DVecD d_s2_sc, d_bd_sc, d_bu1_sc, d_bu2_sc;   // scan-layout copies for band ops folded into an LU solve (see run_pass)
 
   // B2 = laplace_inv; pv(i, off) = (laplace_inv_eye . laplace_inv)[i, i+off]
   double pv(int i, int off) const {
@@ -199,7 +204,9 @@ struct Base1 {
     return o;
   }
   void release() {
-    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin};
+    const void* keys[] = {d_bd.d, d_bu1.d, d_bu2.d, d_s2.d};
+    for (auto k : keys) if (k) scan_of().erase(k);
+    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc};
     for (auto* v : all) v->release();
   }
 };
@@ -254,6 +261,8 @@ int Base1::init(int C, int TPL) {
       if (i < m - 4) bu2[i] = pv(i, 4);
     }
     RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
+    RET(d_bd_sc.upload(scan_layout(bd))); RET(d_bu1_sc.upload(scan_layout(bu1))); RET(d_bu2_sc.upload(scan_layout(bu2))); RET(d_s2_sc.upload(scan_layout(s2v)));
+    scan_of()[d_bd.d] = d_bd_sc.d; scan_of()[d_bu1.d] = d_bu1_sc.d; scan_of()[d_bu2.d] = d_bu2_sc.d; scan_of()[d_s2.d] = d_s2_sc.d;
   }
   // transform tables (only when the size is one the FFT core handles)
   if (is_pow2(N) && N >= 64) {
@@ -465,6 +474,8 @@ static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 
 static bool g_use_tma = getenv("B2_NOTMA") == nullptr;     // B2_NOTMA=1: every load/store on the per-thread LDG/STG path (A/B measurements)
 static bool g_use_direct = getenv("B2_NODIRECT") == nullptr; // B2_NODIRECT=1: plain loads/stores go through the ring / staging as well
+static bool g_use_ring = getenv("B2_RING") != nullptr;       // B2_RING=1: combining loads (accumulate / multiply / stencil) stream through the TMA ring;
+                                                             // default: per-thread LDGs (measured faster on C4: 64 KB in flight per SM vs the ring's chunk hand-offs)
 
 // orient 0: lanes along axis 1; orient 1: lanes along axis 0
 static int run_pass(b2_space* sp, int orient, Prog& pr) {
@@ -489,6 +500,27 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
     for (int i = 0; i < p.nops; i++)
       if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
   }
+  // Fold a banded mat-vec into the LU solve that consumes it (forward offsets only, same output length; shared
+  // coefficient vectors): the solve forms its right-hand side on the fly (lane_fast.cuh, fdma_fast_body<PREBAND>).
+  // Measured: +1.5 % on C2 (E = 8), -2 % on C4 (E = 16, where the extra coefficient streams cost more than the saved
+  // pass), so it is applied to the short-lane instances only (B2_FUSE=1 forces it on, B2_NOFUSE=1 off).
+  if (c.fast && getenv("B2_NOFUSE") == nullptr && (c.E <= 8 || getenv("B2_FUSE") != nullptr)) {
+    for (int i = 0; i + 1 < p.nops; i++) {
+      LaneOp& bo = p.ops[i]; LaneOp& fo = p.ops[i + 1];
+      if (bo.code != OP_BAND || fo.code != OP_FDMA || (fo.i2 & FD_PERLANE) || bo.i0 != fo.i0) continue;
+      bool ok = true;
+      const void* sc[3] = {nullptr, nullptr, nullptr};
+      const void* nat[3] = {bo.p0, bo.p1, bo.p2};
+      for (int m = 0; m < 3; m++) {
+        const int h = (int)(signed char)((bo.i1 >> (8 * m)) & 0xff);
+        if (h == 127) continue;
+        if (h != 0 && h != 2 && h != 4) ok = false;
+        if (nat[m]) { auto it = scan_of().find(nat[m]); if (it == scan_of().end()) ok = false; else sc[m] = it->second; }
+      }
+      if (!ok) continue;
+      bo.code = OP_PREBAND; bo.p0 = sc[0]; bo.p1 = sc[1]; bo.p2 = sc[2]; fo.i2 |= FD_PREBAND;
+    }
+  }
   // TMA views.  Arrays are 4x4-tiled: tile (I, J) at ((I * tiles_per_row) + J) * 128 bytes, element [i][j] inside.
   //   slab view (loads, same-orientation stores): [16 doubles of a tile][tile J of the lane group][lane group]
   //   transposed view (transposing stores): tile (J, g) of the destination holds [jl][lane]:
@@ -499,6 +531,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
     B2TMapDesc d; memset(&d, 0, sizeof(d));
     if (op.code == OP_LOAD && !(op.i2 & LD_PLAIN)) {
       const bool direct = g_use_direct && !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
+      if (!direct && !g_use_ring) continue;   // per-thread path
       d.base = const_cast<void*>(op.p0); d.rank = 3;
       d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
       d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
@@ -1735,6 +1768,14 @@ int b2_navier_set_mode(b2_navier* nv, int mode) {
 #ifndef B2_EMU
   if (nv->graph) { cudaGraphExecDestroy(nv->graph); nv->graph = nullptr; }
 #endif
+  return B2_OK;
+}
+// out[0..7] = {parity-block GEMMs active, P0, P1, m0, ce, co, parallel branches active, lane passes per step}
+int b2_navier_info(const b2_navier* nv, long long* out) {
+  const b2_solver* ps = nv->pois;
+  out[0] = ps && ps->blocks && nv->ctx->nranks == 1; out[1] = nv->sp_ortho->P[0]; out[2] = nv->sp_ortho->P[1];
+  out[3] = ps ? ps->m0 : 0; out[4] = ps ? ps->ce : 0; out[5] = ps ? ps->co : 0;
+  out[6] = nv->branches && nv->ctx->nranks == 1; out[7] = nv->launches_per_step;
   return B2_OK;
 }
 int b2_navier_launch_count(const b2_navier* nv, long long* k) { *k = nv->launches_per_step; return B2_OK; }

@@ -332,7 +332,7 @@ __device__ __noinline__ void deriv_fast(const LaneProg& P, const LaneOp& op, dou
 }
 
 // LU solve (see op_fdma).  PERLANE: coefficient arrays [group][t][q][lane of 4] instead of shared [t][q].
-template <int E, int LN, int TPL, bool PERLANE>
+template <int E, int LN, int TPL, bool PERLANE, bool PREBAND>
 __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, int lb, void* scratch) {
   constexpr int CP = E + 1, CS = PERLANE ? 4 * TPL : TPL;
   const int HP = P.LP >> 1;
@@ -359,7 +359,44 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
   // ---- forward elimination: y_p = b_p - fl_p y_{p-1} ----
   {
     double2 A = d2(1.0, 1.0), B = zero;
-    if (interior) {
+    if constexpr (PREBAND) {
+      // The right-hand side is a banded mat-vec of what is in W: b_p = c0_p x_p + c1_p x_{p+1} + c2_p x_{p+2}
+      // (pair offsets 0, +1, +2; a null coefficient vector = 1; scan-layout vectors [t][q]).  It is formed here, on the
+      // fly, and written back in place; the two pairs after the chunk are read before anybody writes.
+      const LaneOp& bop = *(&op - 1);
+      // every term loads unconditionally (absent / unit coefficients read the LU vector instead and are blended
+      // to 0 / 1 afterwards), so that the 3 x CP coefficient loads can all be in flight at once
+      const double2* cf[3] = {cfl, cfl, cfl};
+      double wl[3] = {0.0, 0.0, 0.0}, ad[3] = {0.0, 0.0, 0.0};   // coefficient = loaded * wl + ad
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const int h = (int)(signed char)((bop.i1 >> (8 * m)) & 0xff);
+        const double2* cp = (const double2*)(m == 0 ? bop.p0 : (m == 1 ? bop.p1 : bop.p2));
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if (h == 2 * k) { if (cp) { cf[k] = cp + q; wl[k] = 1.0; } else ad[k] = 1.0; }
+      }
+      const double2 hA = (CP < tmax) ? w2[ca.at(CP)] : zero, hB = (CP + 1 < tmax) ? w2[ca.at(CP + 1)] : zero;
+      __syncthreads();
+      double2 x0 = (0 < tmax) ? w2[ca.at(0)] : zero, x1 = (1 < tmax) ? w2[ca.at(1)] : zero;
+#pragma unroll
+      for (int t = 0; t < CP; t++) {
+        const double2 x2 = (t + 2 < CP) ? ((t + 2 < tmax) ? w2[ca.at(t + 2 < CP ? t + 2 : 0)] : zero) : (t + 2 == CP ? hA : hB);
+        double2 b = zero;
+        const double2 l0 = ldg(cf[0] + t * TPL), l1 = ldg(cf[1] + t * TPL), l2 = ldg(cf[2] + t * TPL);
+        const double2 k0 = d2(fma(l0.x, wl[0], ad[0]), fma(l0.y, wl[0], ad[0]));
+        const double2 k1 = d2(fma(l1.x, wl[1], ad[1]), fma(l1.y, wl[1], ad[1]));
+        const double2 k2 = d2(fma(l2.x, wl[2], ad[2]), fma(l2.y, wl[2], ad[2]));
+        b = d2fma(k0, x0, d2fma(k1, x1, d2(k2.x * x2.x, k2.y * x2.y)));
+        if (t >= tx) b.x = 0.0;
+        if (t >= ty) b.y = 0.0;
+        if (t < tmax) w2[ca.at(t)] = b;
+        const double2 f = ldg(cfl + t * CS);
+        B = d2(fma(-f.x, B.x, b.x), fma(-f.y, B.y, b.y));
+        A = d2(-f.x * A.x, -f.y * A.y);
+        x0 = x1; x1 = x2;
+      }
+    } else if (interior) {
 #pragma unroll
       for (int t = 0; t < CP; t++) {
         const double2 f = ldg(cfl + t * CS), b = w2[ca.at(t)];
@@ -434,6 +471,7 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
 }
 template <int E, int LN, int TPL>
 __device__ __noinline__ void fdma_fast(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, int lb, void* scratch) {
-  if (op.i2 & FD_PERLANE) fdma_fast_body<E, LN, TPL, true>(P, op, W, gl, lb, scratch);
-  else fdma_fast_body<E, LN, TPL, false>(P, op, W, gl, lb, scratch);
+  if (op.i2 & FD_PERLANE) fdma_fast_body<E, LN, TPL, true, false>(P, op, W, gl, lb, scratch);
+  else if (op.i2 & FD_PREBAND) fdma_fast_body<E, LN, TPL, false, true>(P, op, W, gl, lb, scratch);
+  else fdma_fast_body<E, LN, TPL, false, false>(P, op, W, gl, lb, scratch);
 }

@@ -50,6 +50,7 @@ enum LaneOpCode {
   OP_LANEMASK = 11,// lanes >= i0 zeroed
   OP_ZEROELEM = 12,// W[lane i0][pos i1] = 0 (global lane index)
   OP_SCALE = 13,   // W *= a
+  OP_PREBAND = 14, // an OP_BAND folded into the OP_FDMA that follows it (set by the launcher, fast geometry only): no-op here
 };
 enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
        LD_TMA = 16,          // set by the launcher: the slab streams through the TMA ring (tensor map tm[op])
@@ -60,7 +61,8 @@ enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16,
        ST_TMA = 32,          // set by the launcher: staged, bulk tensor store / reduction
        ST_DIRECT = 64,       // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
        ST_PSPLIT = 128 };    // plain destinations, same orientation: store row r < i1 at r/2 (even) or ceil(i1/2) + r/2 (odd)
-enum { FD_PERLANE = 1, FD_NOU2 = 2 };
+enum { FD_PERLANE = 1, FD_NOU2 = 2,
+       FD_PREBAND = 4 };   // the right-hand side is the banded mat-vec described by the preceding OP_PREBAND op
 
 struct LaneOp {
   int code, i0, i1, i2;
@@ -1138,6 +1140,7 @@ __global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneP
       case OP_RFFT:
         if constexpr (TPLC > 0) rfft_fast<E, LN, TPLC>(P, op, W); else op_rfft<E, LN>(P, op, W);
         break;
+      case OP_PREBAND: break;
       default: op_pointwise<LN>(P, op, W, g, lb); break;
     }
     if (P.prof && threadIdx.x == 0) {
