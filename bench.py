@@ -258,7 +258,7 @@ def main():
             nav.update(1)
             for k in names:
                 t, dt_, sh = host[k]
-                t.numpy().view(dt_).reshape(sh)[...] = getattr(nav, k).vhat
+                getattr(nav, k).vhat_into(t.numpy().view(dt_).reshape(sh))   # straight into the pinned buffer
 
         e2e_step()
         fence()

@@ -273,6 +273,17 @@ class Field2:
             check(lib().b2_field_get_vhat_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def vhat_into(self, out):
+        """Download ``vhat`` into a caller-owned C-contiguous array (e.g. a view of pinned host memory) without
+        allocating: the device-to-host copy then runs at PCIe speed instead of through a pageable bounce."""
+        shape, cx = self.space.shape(SPECTRAL)
+        want = (self.local_rows(SPECTRAL)[1], shape[1])
+        if out.shape != want or out.dtype != (np.complex128 if cx else np.float64) or not out.flags.c_contiguous:
+            raise B2Error(f"vhat_into: need a C-contiguous {want} array of {'complex128' if cx else 'float64'}")
+        if out.size:
+            check(lib().b2_field_get_vhat_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
     @vhat.setter
     def vhat(self, a):
         shape, cx = self.space.shape(SPECTRAL)
