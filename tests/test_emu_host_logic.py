@@ -52,8 +52,17 @@ elif case == "golden":
         raise SystemExit("expected a shape error")
     except b2.B2Error:
         pass
+elif case == "variants":
+    # the same step through the alternative data-movement paths selected by the environment of this process
+    errs = g.check_navier(65, 65, 1)
+    assert max(errs.values()) < g.TOL, errs
+    f = b2.Field2(b2.Space2(b2.cheb_dirichlet(17), b2.fourier_r2c(16) if False else b2.cheb_dirichlet(17)))
+    a = np.random.default_rng(0).standard_normal((15, 15))
+    f.vhat = a
+    out = np.empty((15, 15)); f.vhat_into(out)
+    assert np.array_equal(out, a)
 elif case == "navier":
-    errs = g.check_navier(65, 65, 2)
+    errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
     errs = g.check_navier(64, 65, 2, True)
     assert max(errs.values()) < g.TOL, errs
@@ -64,4 +73,15 @@ print("ok")
 @pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("env", [{"B2_RING": "1", "B2_CH": "5"},          # combining loads through the TMA ring, 4 chunks per lane
+                                 {"B2_NOTMA": "1", "B2_NOBLOCKS": "1"},   # per-thread loads/stores only, dense Poisson GEMMs
+                                 {"B2_NOFAST": "1", "B2_NODIRECT": "1"}], # generic-geometry operators, staged (not zero-copy) plain copies
+                         ids=["ring", "threads-dense", "generic-staged"])
+def test_emulated_path_variants(env):
+    """The tuning switches select alternative implementations of the same operators; each must give the same step."""
+    r = subprocess.run([sys.executable, "-c", SCRIPT, "variants"], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                       env=dict(os.environ, **env))
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
