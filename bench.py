@@ -226,7 +226,7 @@ def main():
     if per:
         gemm_flop = 0.0
     elif info["parity_blocks"]:   # two GEMM pairs on the parity blocks (half the flops of the dense products)
-        gemm_flop = 2.0 * 2.0 * info["P1"] * (info["ce"] ** 2 + info["co"] ** 2)
+        gemm_flop = 2.0 * 2.0 * info["P1"] * (info["ce"] ** 2 + info["co"] ** 2) / world
     else:
         gemm_flop = 4.0 * info["m0"] ** 2 * info["P1"] / world
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -831,7 +831,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     return B2_OK;
   };
   RET(build_lanes(lam, &s->pfl, &s->pid, &s->pu1, &s->pu2));
-  if (s->dense && nr == 1 && getenv("B2_NOBLOCKS") == nullptr) {
+  if (s->dense && getenv("B2_NOBLOCKS") == nullptr) {
     // parity classes of the modes: row r of fwd (= mode r) touches even columns only, or odd columns only
     const int m0 = s->m0, ce = (m0 + 1) / 2, co = m0 / 2;
     std::vector<int> cls(m0, 0), perm;
@@ -847,7 +847,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     }
     for (int k = 0; k < 2 && ok; k++) for (int r = 0; r < m0; r++) if (cls[r] == k) perm.push_back(r);
     int ne = 0; for (int r = 0; r < m0; r++) ne += (cls[r] == 0);
-    if (ok && ne == ce) {
+    if (ok && ne == ce && (nr == 1 || ce % 2 == 0)) {   // multi-GPU: the odd block starts at column ce of the x-pencil operands (16-byte stores)
       std::vector<double> fe((size_t)ce * ce), fo((size_t)co * co), be((size_t)ce * ce), bo((size_t)co * co), lam2(lam.size());
       for (int r = 0; r < ce; r++) for (int k = 0; k < ce; k++) { fe[(size_t)r * ce + k] = fwd[(size_t)perm[r] * m0 + 2 * k]; be[(size_t)k * ce + r] = bwd[(size_t)(2 * k) * m0 + perm[r]]; }
       for (int r = 0; r < co; r++) for (int k = 0; k < co; k++) { fo[(size_t)r * co + k] = fwd[(size_t)perm[ce + r] * m0 + 2 * k + 1]; bo[(size_t)k * co + r] = bwd[(size_t)(2 * k + 1) * m0 + perm[ce + r]]; }
@@ -1624,7 +1624,31 @@ static int nav_update_fused(b2_navier* nv) {
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
   const double* pseu_src; int pseu_flags, pseu_i1 = 0;
-  if (ps->dense && ctx->nranks > 1) {
+  if (ps->dense && ctx->nranks > 1 && ps->blocks) {
+    // slabs + parity blocks: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y,
+    // row-major, x contiguous); the x index is stored parity-split (ST_PSPLITC / LD_PSPLITC), the modes parity-grouped
+    const double one = 1.0, zero = 0.0;
+    const int P1loc = P1 / ctx->nranks, m0 = ps->m0, ce = ps->ce, co = ps->co;
+    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_TRANS | ST_PLAIN | ST_PSPLITC, 1.0, m0);
+    RET(run_pass(so, 0, y));
+    RET(gemm_mark(ctx));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ce, P1loc, ce, &one, ps->fe.d, ce, nv->G0, P0, &zero, nv->G1, P0));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, co, P1loc, co, &one, ps->fo.d, co, nv->G0 + ce, P0, &zero, nv->G1 + ce, P0));
+    RET(gemm_mark(ctx));
+    ctx->launches += 2;
+    Prog x; x.load(nv->G1, m0, 1.0, LD_PLAIN); x.store(nv->U1, m0, ST_TRANS);
+    RET(run_pass(so, 1, x));
+    Prog y2; y2.load(nv->U1, byp.m); y2.fdma(byp.m, ps->qfl.d, ps->qid.d, ps->qu1.d, ps->qu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_TRANS | ST_PLAIN);
+    RET(run_pass(so, 0, y2));
+    RET(gemm_mark(ctx));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ce, P1loc, ce, &one, ps->be.d, ce, nv->G0, P0, &zero, nv->G1, P0));
+    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, co, P1loc, co, &one, ps->bo.d, co, nv->G0 + ce, P0, &zero, nv->G1 + ce, P0));
+    RET(gemm_mark(ctx));
+    ctx->launches += 2;
+    Prog x2; x2.load(nv->G1, m0, 1.0, LD_PLAIN | LD_PSPLITC, m0); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, m0, ST_TRANS);
+    RET(run_pass(so, 1, x2));
+    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
+  } else if (ps->dense && ctx->nranks > 1) {
     // slabs: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y, row-major)
     const double one = 1.0, zero = 0.0;
     const int P1loc = P1 / ctx->nranks;
@@ -1645,7 +1669,7 @@ static int nav_update_fused(b2_navier* nv) {
     Prog x2; x2.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, ps->m0, ST_TRANS);
     RET(run_pass(so, 1, x2));
     pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
-  } else if (ps->dense && ps->blocks) {
+  } else if (ps->dense && ps->blocks && ctx->nranks == 1) {
     // parity-grouped: rows of the GEMM operands are stored even indices first, then odd (ST_PSPLIT / LD_PSPLIT);
     // G1_e = fwd_e G0_e, G1_o = fwd_o G0_o  (row-major views; half the flops of the full product)
     const double one = 1.0, zero = 0.0;
@@ -1773,7 +1797,7 @@ int b2_navier_set_mode(b2_navier* nv, int mode) {
 // out[0..7] = {parity-block GEMMs active, P0, P1, m0, ce, co, parallel branches active, lane passes per step}
 int b2_navier_info(const b2_navier* nv, long long* out) {
   const b2_solver* ps = nv->pois;
-  out[0] = ps && ps->blocks && nv->ctx->nranks == 1; out[1] = nv->sp_ortho->P[0]; out[2] = nv->sp_ortho->P[1];
+  out[0] = ps && ps->blocks; out[1] = nv->sp_ortho->P[0]; out[2] = nv->sp_ortho->P[1];
   out[3] = ps ? ps->m0 : 0; out[4] = ps ? ps->ce : 0; out[5] = ps ? ps->co : 0;
   out[6] = nv->branches && nv->ctx->nranks == 1; out[7] = nv->launches_per_step;
   return B2_OK;

@@ -56,11 +56,13 @@ enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: va
        LD_TMA = 16,          // set by the launcher: the slab streams through the TMA ring (tensor map tm[op])
        LD_AFTER_STORE = 32,  // set by the launcher: the source was stored earlier in this program (flush stores first)
        LD_DIRECT = 64,       // set by the launcher: zero-copy TMA straight into W (plain load, a == 1)
-       LD_PSPLIT = 128 };    // plain sources: rows are stored parity-split (row r < i1 lives at r/2, odd rows after the even ones)
+       LD_PSPLIT = 128,      // plain sources: rows are stored parity-split (row r < i1 lives at r/2, odd rows after the even ones)
+       LD_PSPLITC = 256 };   // plain sources: the positions along the lane (columns) are stored parity-split, i1 = m0
 enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16,
        ST_TMA = 32,          // set by the launcher: staged, bulk tensor store / reduction
        ST_DIRECT = 64,       // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
-       ST_PSPLIT = 128 };    // plain destinations, same orientation: store row r < i1 at r/2 (even) or ceil(i1/2) + r/2 (odd)
+       ST_PSPLIT = 128,      // plain destinations, same orientation: store row r < i1 at r/2 (even) or ceil(i1/2) + r/2 (odd)
+       ST_PSPLITC = 256 };   // plain transposing stores: lane index (= column) c <= i1 goes to c/2 (even) or ceil(i1/2) + c/2 (odd)
 enum { FD_PERLANE = 1, FD_NOU2 = 2,
        FD_PREBAND = 4 };   // the right-hand side is the banded mat-vec described by the preceding OP_PREBAND op
 
@@ -520,6 +522,10 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
       if (pc < npieces && j0 < len) {
         int row = 4 * gl + lb + l;
         if (row < psplit) row = (row & 1) ? ((psplit + 1) >> 1) + (row >> 1) : (row >> 1);
+        if (plain && (op.i2 & LD_PSPLITC) && j0 <= op.i1) {   // elements j0 (even) and j0+1 (odd) live in the two parity halves
+          const double* sd = reinterpret_cast<const double*>(op.p0) + (size_t)row * P.in_tiles * 4;
+          v[k] = make_double2(sd[j0 >> 1], sd[((op.i1 + 1) >> 1) + (j0 >> 1)]);
+        } else
         v[k] = plain ? src[((size_t)row * P.in_tiles * 4 + j0) >> 1]
                      : src[slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1)];
         if (sten && j0 >= 2) {   // composite -> orthonormal on the fly: + p1[j] * src[j-2]  (tiled sources only)
@@ -652,13 +658,19 @@ __device__ __noinline__ void store_threads(const LaneProg& P, const LaneOp& op, 
   double2* dst = reinterpret_cast<double2*>(const_cast<void*>(op.p0));
   if (flags & ST_TRANS) {
     double* const* peers = reinterpret_cast<double* const*>(op.p1);
+    // ST_PSPLITC (GEMM operands of the parity-block Poisson products): the lane index is the column of the plain
+    // matrix; lanes (0, 2) of the group are neighbouring even columns, lanes (1, 3) neighbouring odd columns
+    const bool csplit = (flags & ST_PSPLITC) && LN == 4 && 4 * g + 3 <= op.i1;
     for (int pc = threadIdx.x; pc < npieces; pc += T) {
       const int lp = pc & (HL - 1), jl = (pc / HL) & 3, J = pc >> LSH, j = 4 * J + jl, sw = J & 1;
       double2 v = make_double2(0.0, 0.0);
       if (j < len) {
         const double* wt = W + ((size_t)J << (LSH + 1)) + jl;
-        const double e0 = wt[4 * (2 * lp + sw)], e1 = wt[4 * (2 * lp + 1 - sw)];
-        v.x = a * (sw ? e1 : e0); v.y = a * (sw ? e0 : e1);
+        if (csplit) { v.x = a * wt[4 * lp]; v.y = a * wt[4 * (lp + 2)]; }
+        else {
+          const double e0 = wt[4 * (2 * lp + sw)], e1 = wt[4 * (2 * lp + 1 - sw)];
+          v.x = a * (sw ? e1 : e0); v.y = a * (sw ? e0 : e1);
+        }
       }
       double2* d = dst;
       int Jl = J;
@@ -669,7 +681,8 @@ __device__ __noinline__ void store_threads(const LaneProg& P, const LaneOp& op, 
                                        (reinterpret_cast<const char*>(op.p0) - reinterpret_cast<const char*>(peers[P.rank])));
       }
       // tiled: tile (Jl, g) holds [jl][l];  row-major ("plain", for the GEMM): row 4*Jl+jl, columns 4g+l
-      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + 4 * g + lb + 2 * lp) >> 1)
+      const int col = csplit ? (lp ? ((op.i1 + 1) >> 1) : 0) + 2 * g : 4 * g + lb + 2 * lp;
+      size_t idx = (flags & ST_PLAIN) ? (((size_t)(4 * Jl + jl) * P.out_tiles * 4 + col) >> 1)
                                       : ((((size_t)Jl * P.out_tiles + g) * 16 + jl * 4 + lb + 2 * lp) >> 1);
       if (flags & ST_ACC) { double2 ov = d[idx]; v.x += ov.x; v.y += ov.y; }
       d[idx] = v;
