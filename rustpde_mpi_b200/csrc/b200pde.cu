@@ -531,14 +531,14 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
     B2TMapDesc d; memset(&d, 0, sizeof(d));
     if (op.code == OP_LOAD && !(op.i2 & LD_PLAIN)) {
       const bool direct = g_use_direct && !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
+      for (int k = 0; k < i; k++)   // re-reading an array this program stored: the bulk stores have to be complete first
+        if (p.ops[k].code == OP_STORE && p.ops[k].p0 == op.p0) op.i2 |= LD_AFTER_STORE;
       if (!direct && !g_use_ring) continue;   // per-thread path
       d.base = const_cast<void*>(op.p0); d.rank = 3;
       d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
       d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
       d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CH + 1; d.box[2] = 1;
       op.i2 |= direct ? LD_DIRECT : LD_TMA;
-      for (int k = 0; k < i; k++)
-        if (p.ops[k].code == OP_STORE && p.ops[k].p0 == op.p0) op.i2 |= LD_AFTER_STORE;
     } else if (op.code == OP_STORE && !(op.i2 & (ST_PLAIN | ST_PEER))) {
       d.base = const_cast<void*>(op.p0);
       if (op.i2 & ST_TRANS) {

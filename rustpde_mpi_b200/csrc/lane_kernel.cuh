@@ -512,6 +512,10 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
   const double* sc = reinterpret_cast<const double*>(op.p1);
   double2* W2 = reinterpret_cast<double2*>(sv.W);
   const int psplit = (op.i2 & LD_PSPLIT) ? op.i1 : 0;   // rows < psplit of a plain source are stored parity-split
+  if (op.i2 & LD_AFTER_STORE) {   // the source was written by this CTA's bulk stores: wait until they have completed
+    if (threadIdx.x == 0) bulk_wait<0>();
+    __syncthreads();
+  }
   for (int p0 = threadIdx.x; p0 < npieces; p0 += U * T) {
     double2 v[U], u[U];
 #pragma unroll
