@@ -1,3 +1,5 @@
+# ncu captures behind profiles/r01 (ring-load kernel, DCT kernel, one C4 step, C2 launch list); CSV export happens on the box
+# because the .ncu-rep files exceed the 64 MiB gpurun_out budget.
 set -x
 cd /root/repo
 exp() { # name
