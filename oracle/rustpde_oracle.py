@@ -790,6 +790,49 @@ class Navier2D:
         self.temp.vhat = self.solver_hholtz[2].solve(rhs)
         self.time += dt
 
+    # -- diagnostics (src/navier_stokes/functions.rs:146-233, src/field/average.rs:26-62) -------
+    @staticmethod
+    def average_axis(field, axis):
+        """``FieldBase::average_axis``: dx-weighted mean along ``axis`` (src/field/average.rs:26-35)."""
+        length = abs(field.x[axis][-1] - field.x[axis][0])
+        w = field.dx[axis] / length
+        return np.tensordot(w, field.v, axes=(0, axis))
+
+    @classmethod
+    def average(cls, field):
+        """``FieldBase::average`` (src/field/average.rs:53-59)."""
+        length = abs(field.x[1][-1] - field.x[1][0])
+        return float(np.sum(cls.average_axis(field, 0) * field.dx[1] / length))
+
+    def eval_nu(self):
+        """Nusselt number from the heat flux at the plates (functions.rs:146-168)."""
+        f = self.field
+        f.vhat = self.temp.to_ortho() + self.tempbc.to_ortho()
+        f.vhat = f.gradient([0, 1], None) * (-2.0 / self.scale[1])
+        f.backward()
+        x_avg = self.average_axis(f, 0)
+        return float((x_avg[-1] + x_avg[0]) / 2.0)
+
+    def eval_nuvol(self):
+        """Volumetric Nusselt number (functions.rs:175-207)."""
+        f = self.field
+        f.vhat = self.temp.to_ortho() + self.tempbc.to_ortho()
+        f.backward()
+        self.vely.backward()
+        vely_temp = f.v * self.vely.v
+        f.vhat = f.gradient([0, 1], None) / (-self.scale[1])
+        f.backward()
+        f.v = (f.v + vely_temp / self.ka) * 2.0 * self.scale[1]
+        return self.average(f)
+
+    def eval_re(self):
+        """Reynolds number from the kinetic energy (functions.rs:215-233)."""
+        self.velx.backward()
+        self.vely.backward()
+        f = self.field
+        f.v = np.sqrt(self.velx.v ** 2 + self.vely.v ** 2) * (2.0 * self.scale[1] / self.nu)
+        return self.average(f)
+
     def state(self):
         return {k: np.array(getattr(self, k).vhat, copy=True) for k in ("temp", "velx", "vely", "pres")}
 

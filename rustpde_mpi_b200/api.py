@@ -496,8 +496,73 @@ class Navier2D:
         """navier.rs:482-489: break when |div| is NaN."""
         return bool(np.isnan(self.div_norm()))
 
-    def callback(self):
-        pass  # HDF5 snapshots / diagnostics are out of scope (SURVEY 2 rows 23, 28)
+    # diagnostics (SURVEY 8f item 1): the transforms / projections / derivatives run on the GPU through the C ABI,
+    # the dx-weighted means of src/field/average.rs are taken on the host from the downloaded physical field
+    # (callback-only work, once per save interval; single rank).
+    def _diag_field(self):
+        if self.nranks != 1:
+            raise B2Error("diagnostics are single-rank in this round (gather the state and use rank 0)")
+        if getattr(self, "_field", None) is None:
+            bx = fourier_r2c(self.nx) if self.periodic else chebyshev(self.nx)
+            self._field = Field2(Space2(bx, chebyshev(self.ny), ctx=self.ctx))
+            # the solver's own fields are borrowed handles without a standalone space: projections go through a twin
+            self._temp_twin = Field2(Space2(*self.temp.space.bases, ctx=self.ctx))
+            height = self.scale[1] * 2.0   # functions.rs:12-21
+            self.nu = float(np.sqrt(self.pr / (self.ra / height ** 3.0)))
+            self.ka = float(np.sqrt(1.0 / ((self.ra / height ** 3.0) * self.pr)))
+        return self._field
+
+    @staticmethod
+    def _average_axis(f, v, axis):   # src/field/average.rs:26-35
+        w = f.dx[axis] / abs(f.x[axis][-1] - f.x[axis][0])
+        return np.tensordot(w, v, axes=(0, axis))
+
+    @classmethod
+    def _average(cls, f, v):         # src/field/average.rs:53-59
+        return float(np.sum(cls._average_axis(f, v, 0) * f.dx[1] / abs(f.x[1][-1] - f.x[1][0])))
+
+    def _temp_ortho(self):
+        self._temp_twin.vhat = self.temp.vhat
+        return self._temp_twin.to_ortho().get() + self.tempbc.vhat   # tempbc lives in the orthonormal space already
+
+    def eval_nu(self):
+        """Nusselt number from the heat flux at the plates (functions.rs:146-168)."""
+        f = self._diag_field()
+        f.vhat = self._temp_ortho()
+        f.vhat = f.gradient([0, 1], None).get() * (-2.0 / self.scale[1])
+        f.backward()
+        x_avg = self._average_axis(f, f.v, 0)
+        return float((x_avg[-1] + x_avg[0]) / 2.0)
+
+    def eval_nuvol(self):
+        """Volumetric Nusselt number (functions.rs:175-207)."""
+        f = self._diag_field()
+        f.vhat = self._temp_ortho()
+        f.backward()
+        tphys = f.v
+        self.vely.backward()
+        vely_temp = tphys * self.vely.v
+        f.vhat = f.gradient([0, 1], None).get() / (-self.scale[1])
+        f.backward()
+        return self._average(f, (f.v + vely_temp / self.ka) * 2.0 * self.scale[1])
+
+    def eval_re(self):
+        """Reynolds number from the kinetic energy (functions.rs:215-233)."""
+        f = self._diag_field()
+        self.velx.backward()
+        self.vely.backward()
+        return self._average(f, np.sqrt(self.velx.v ** 2 + self.vely.v ** 2) * (2.0 * self.scale[1] / self.nu))
+
+    def callback(self, info_name=None):
+        """The I/O part of ``callback_from_filename`` (src/navier_stokes/navier_io.rs:122-147): print time, |div|, Nu,
+        Nuv, Re and append ``time nu nuv re`` to ``info_name``.  HDF5 snapshots / statistics are out of scope
+        (SURVEY 2 rows 23, 28)."""
+        div, nu, nuv, re = self.div_norm(), self.eval_nu(), self.eval_nuvol(), self.eval_re()
+        print(f"time = {self.get_time():4.2f}      |div| = {div:4.2e}     Nu = {nu:5.3e}     Nuv = {nuv:5.3e}    Re = {re:5.3e}")
+        if info_name:
+            with open(info_name, "a") as fh:
+                fh.write(f"{self.get_time()} {nu} {nuv} {re}\n")
+        return div, nu, nuv, re
 
     def set_mode(self, fused):
         check(lib().b2_navier_set_mode(self._h, int(fused)))

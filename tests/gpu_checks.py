@@ -142,3 +142,14 @@ def check_navier(nx, ny, steps, periodic=False, ra=1e5, dt=0.01, init="modes"):
         no.update()
     ng.update(steps)
     return navier_errors(no, ng)
+
+
+def check_diagnostics(nx, ny, steps, periodic=False):
+    """Nu, Nuvol, Re (src/navier_stokes/functions.rs:146-233) after a few steps: CUDA path vs oracle, relative."""
+    no, ng = make_navier_pair(nx, ny, 1e5, 1.0, 0.01, 1.0, periodic, "modes")
+    for _ in range(steps):
+        no.update()
+    ng.update(steps)
+    ref = (no.eval_nu(), no.eval_nuvol(), no.eval_re())
+    got = (ng.eval_nu(), ng.eval_nuvol(), ng.eval_re())
+    return max(abs(a - b) / abs(a) for a, b in zip(ref, got))

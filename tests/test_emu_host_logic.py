@@ -64,6 +64,8 @@ elif case == "variants":
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
+    e = g.check_diagnostics(65, 65, 1)
+    assert e < g.TOL, e
     errs = g.check_navier(64, 65, 2, True)
     assert max(errs.values()) < g.TOL, errs
 print("ok")

@@ -90,3 +90,9 @@ def test_navier_random_init_257():
 def test_navier_periodic_random_256x129():
     errs = g.check_navier(256, 129, 3, True, 1e7, 1e-3, "random")
     assert max(errs.values()) < g.TOL, errs
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_diagnostics_nu_nuvol_re(periodic):
+    """callback() diagnostics: transforms / projections / derivatives on the GPU, weighted means on the host."""
+    assert g.check_diagnostics(64 if periodic else 65, 65, 3, periodic) < 1e-10
