@@ -847,7 +847,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     }
     for (int k = 0; k < 2 && ok; k++) for (int r = 0; r < m0; r++) if (cls[r] == k) perm.push_back(r);
     int ne = 0; for (int r = 0; r < m0; r++) ne += (cls[r] == 0);
-    if (ok && ne == ce && (nr == 1 || ce % 2 == 0)) {   // multi-GPU: the odd block starts at column ce of the x-pencil operands (16-byte stores)
+    if (ok && ne == ce && (nr == 1 || (ce % 2 == 0 && sp->cfg[0].LN == 4 && sp->cfg[1].LN == 4))) {   // multi-GPU: the odd block starts at column ce of the x-pencil operands (16-byte stores)
       std::vector<double> fe((size_t)ce * ce), fo((size_t)co * co), be((size_t)ce * ce), bo((size_t)co * co), lam2(lam.size());
       for (int r = 0; r < ce; r++) for (int k = 0; k < ce; k++) { fe[(size_t)r * ce + k] = fwd[(size_t)perm[r] * m0 + 2 * k]; be[(size_t)k * ce + r] = bwd[(size_t)(2 * k) * m0 + perm[r]]; }
       for (int r = 0; r < co; r++) for (int k = 0; k < co; k++) { fo[(size_t)r * co + k] = fwd[(size_t)perm[ce + r] * m0 + 2 * k + 1]; bo[(size_t)k * co + r] = bwd[(size_t)(2 * k + 1) * m0 + perm[ce + r]]; }

@@ -66,7 +66,7 @@ elif case == "navier":
     assert max(errs.values()) < g.TOL, errs
     e = g.check_diagnostics(65, 65, 1)
     assert e < g.TOL, e
-    errs = g.check_navier(64, 65, 2, True)
+    errs = g.check_navier(64, 65, 1, True)
     assert max(errs.values()) < g.TOL, errs
 print("ok")
 ''' % ROOT
