@@ -20,6 +20,8 @@ def ngpus():
     (129, 129, 5, 0, 1, 29711), (128, 129, 5, 1, 1, 29712), (129, 129, 2, 0, 0, 29713), (257, 129, 3, 0, 1, 29714)])
 def test_navier_slabs_match_serial_oracle(nx, ny, steps, periodic, mode, port):
     world = min(ngpus(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs (a single rank is what tests/test_gpu_parity.py covers)")
     env = dict(os.environ, B2_TEST_EMU="0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")] + [str(a) for a in (nx, ny, steps, periodic, mode)]
