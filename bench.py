@@ -33,6 +33,7 @@ CONFIGS = {
     "C2": (1025, 1025, 1e7, 1e-3, False),
     "C3": (2048, 1025, 1e7, 1e-3, True),
     "C4": (4097, 4097, 1e9, 1e-4, False),
+    "C5": (8192, 4097, 1e10, 5e-5, True),   # BASELINE configs[4]; 8192-point Fourier lanes run 2 lanes per CTA (not measured in round 1)
 }
 
 
@@ -99,7 +100,7 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = args.config
-    n_steps = max(1, min(args.steps, 3 if cfg in ("C2", "C3") else (1 if cfg == "C4" else 20)))
+    n_steps = max(1, min(args.steps, 3 if cfg in ("C2", "C3") else (1 if cfg in ("C4", "C5") else 20)))
     v, t, cores = cpu_oracle_steps(cfg, n_steps, None if CONFIGS[cfg][4] or CONFIGS[cfg][0] < 1000 else "parity")
     line = {
         "impl": "reference", "metric": "Navier2D timesteps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
@@ -282,7 +283,7 @@ def main():
     # ---- CPU baseline (oracle port), bounded sample ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        n_cpu = 2 if cfg in ("C2", "C3") else (1 if cfg == "C4" else 10)
+        n_cpu = 2 if cfg in ("C2", "C3") else (1 if cfg in ("C4", "C5") else 10)
         eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
         v, t, cores = cpu_oracle_steps(cfg, n_cpu, eig)
         cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
