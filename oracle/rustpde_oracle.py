@@ -434,6 +434,57 @@ class Fdma:
                     self.up1 + other.up1 * lam, self.up2 + other.up2 * lam, sweep=False)
 
 
+class PdmaPlus2:
+    """Banded solve for diagonals at offsets -2..+4 (``PdmaPlus2``, src/solver/pdma_plus2.rs:19-157; used by the
+    ChebDirichletNeumann bases of bc = "hc", SURVEY 8a row M -- not on the GPU path yet).  Restated as what it is:
+    LU elimination without pivoting restricted to the band (two sub-diagonals, four super-diagonals), the factor
+    rows normalised by the pivot like the reference's al/be/ga/de, followed by forward and backward substitution."""
+
+    LOW, UP = 2, 4
+
+    def __init__(self, a):
+        a = np.asarray(a, dtype=float)
+        n = a.shape[0]
+        self.n = n
+        u = a.copy()                       # becomes the upper factor (rows divided by their pivot at the end)
+        low = np.zeros((n, self.LOW))      # multipliers of the rows below the pivot
+        for k in range(n):
+            for i in range(k + 1, min(n, k + self.LOW + 1)):
+                m = u[i, k] / u[k, k]
+                low[i, i - k - 1] = m
+                hi = min(n, k + self.UP + 1)
+                u[i, k:hi] -= m * u[k, k:hi]
+        self.piv = np.diag(u).copy()       # mu
+        self.up = np.zeros((n, self.UP))   # al, be, ga, de
+        for k in range(n):
+            for j in range(1, self.UP + 1):
+                if k + j < n:
+                    self.up[k, j - 1] = u[k, k + j] / self.piv[k]
+        self.low = low
+
+    @classmethod
+    def from_matrix(cls, a):
+        return cls(a)
+
+    def solve_lane(self, rhs):
+        n = self.n
+        z = np.array(rhs, dtype=np.result_type(rhs, float), copy=True)
+        for i in range(n):                 # forward: L z = rhs, then scale by the pivot
+            for j in range(1, self.LOW + 1):
+                if i - j >= 0:
+                    z[i] -= self.low[i, j - 1] * z[i - j] * self.piv[i - j]
+            z[i] = z[i] / self.piv[i]
+        x = z
+        for i in range(n - 1, -1, -1):     # backward with the normalised upper factor
+            for j in range(1, self.UP + 1):
+                if i + j < n:
+                    x[i] -= self.up[i, j - 1] * x[i + j]
+        return x
+
+    def solve(self, inp, axis):
+        return np.apply_along_axis(self.solve_lane, axis, inp)
+
+
 class MatVecFdma:
     """banded (n-2) x n mat-vec, src/solver/matvec.rs:161-228."""
 

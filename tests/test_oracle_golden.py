@@ -245,3 +245,43 @@ def test_split_bounds():
     b = o.split_bounds(10, 4)
     assert b == [(0, 1), (2, 3), (4, 6), (7, 9)]
     assert o.split_bounds(8, 2) == [(0, 3), (4, 7)]
+
+
+def _pdma_test_matrix(n):
+    """The matrix of the reference's own solver tests (src/solver/pdma_plus2.rs:209-245, test_pdma_dim1/dim2)."""
+    m = np.zeros((n, n))
+    for i in range(n):
+        j = i + 1.0
+        m[i, i] = 0.5 * j
+        if i > 1:
+            m[i, i - 2] = 10.0 * j
+        if i > 0:
+            m[i, i - 1] = 4.0 * j
+        if i < n - 1:
+            m[i, i + 1] = 1.5 * j
+        if i < n - 2:
+            m[i, i + 2] = 3.5 * j
+        if i < n - 3:
+            m[i, i + 3] = 4.5 * j
+        if i < n - 4:
+            m[i, i + 4] = 2.5 * j
+    return m
+
+
+@pytest.mark.parametrize("n", [6, 9, 33])
+def test_pdma_plus2_recovers_rhs_like_the_reference_test(n):
+    """Row M of SURVEY 8a (bc = "hc", not on the GPU path yet): the oracle's restatement passes the reference's
+    test_pdma_dim1 (matrix . solve(data) == data) and agrees with a dense solve."""
+    a = _pdma_test_matrix(n)
+    data = np.arange(n, dtype=float)
+    x = o.PdmaPlus2.from_matrix(a).solve_lane(data)
+    np.testing.assert_allclose(a @ x, data, atol=1e-10)
+    np.testing.assert_allclose(x, np.linalg.solve(a, data), rtol=1e-10, atol=1e-12)
+
+
+def test_pdma_plus2_dim2_along_axis0():
+    """test_pdma_dim2 (src/solver/pdma_plus2.rs:248-290): lanes along axis 0 of a 6 x 4 array."""
+    a = _pdma_test_matrix(6)
+    data = np.tile(np.arange(6.0), (4, 1)).T
+    x = o.PdmaPlus2(a).solve(data, 0)
+    np.testing.assert_allclose(a @ x, data, atol=1e-10)
