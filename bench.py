@@ -13,8 +13,11 @@ value  : steps/s with state resident in HBM, CUDA events on the library's stream
 e2e    : the same step through the public API with HOST state: every step uploads the four
          spectral state arrays from pinned host memory, steps, and downloads them again.
 roofline: HBM-bound lane kernels: algorithmic bytes per step (728 N) / time in lane kernels.
-cpu_baseline / --impl reference: the numpy oracle port of the reference's update() timed on the
-         host cores (the Rust reference cannot be built in this image: no cargo/rustc).
+cpu_baseline / --impl reference: the C++/OpenMP restatement of the reference's update() (oracle/cpu_restated.cpp: one
+         pass per reference call, lane-parallel, OpenBLAS DGEMM) timed on the host cores (the Rust reference cannot be
+         built in this image: no cargo/rustc).
+parity_check: 2 steps of a 257 x 129 problem on the same ranks against the numpy oracle; parity_check_workload: the
+         benchmarked configuration itself against the C++ restatement (1 GPU).
 """
 import argparse
 import json
@@ -33,8 +36,16 @@ CONFIGS = {
     "C2": (1025, 1025, 1e7, 1e-3, False),
     "C3": (2048, 1025, 1e7, 1e-3, True),
     "C4": (4097, 4097, 1e9, 1e-4, False),
-    "C5": (8192, 4097, 1e10, 5e-5, True),   # BASELINE configs[4]; 8192-point Fourier lanes run 2 lanes per CTA (not measured in round 1)
+    "C5": (8192, 4097, 1e10, 5e-5, True),   # BASELINE configs[4]
+    "C6": (8193, 8193, 1e10, 5e-5, False),  # north_star scaling case (8193^2 confined); host LAPACK setup takes minutes (cached via B2_EIG_CACHE)
 }
+
+
+def config_dict(cfg):
+    """`config` of the JSON line: identical in both arms (the repo arm's run details go to `run`)."""
+    nx, ny = CONFIGS[cfg][:2]
+    return {"workload": workload_name(cfg), "config": cfg,
+            "l2": "per-step working set (~30 arrays x 8N bytes) exceeds the 126 MB L2; no explicit flush" if nx * ny > 600000 else "fits L2"}
 
 
 def workload_name(cfg):
@@ -77,41 +88,85 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_steps(cfg, steps, eig=None):
-    """Time `steps` updates of the oracle port on the host.  Returns (steps/s, seconds, cores)."""
-    import numpy as np  # noqa: F401
-
-    from oracle import rustpde_oracle as o
+def cpu_restated(cfg, eig, threads=0):
+    """The C++/OpenMP restatement of the reference's update() (oracle/cpu_restated.cpp: one pass per reference call,
+    lane-parallel like rayon, OpenBLAS DGEMM) on the host cores, constructor defaults + init_random(0.1)."""
+    from oracle import cpu_restated as cr
 
     nx, ny, ra, dt, per = CONFIGS[cfg]
-    nav = o.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, pois_eig=eig)
+    nav = cr.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, pois_eig=eig, threads=threads)
     nav.init_random(0.1)
-    nav.update()  # warm-up (allocations, FFT plans)
+    return nav
+
+
+def time_cpu(nav, steps, warmup):
+    nav.update(max(1, warmup))
     t0 = time.perf_counter()
-    for _ in range(steps):
-        nav.update()
-    t = time.perf_counter() - t0
-    return steps / t, t, os.cpu_count()
+    nav.update(steps)
+    return (time.perf_counter() - t0) / steps
+
+
+def host_eig(cfg):
+    """Host LAPACK setup of the confined Poisson solver for the CPU arm (scipy, parity blocks; not timed)."""
+    nx, ny, ra, dt, per = CONFIGS[cfg]
+    if per:
+        return None
+    from oracle import rustpde_oracle as o
+
+    f = o.Field2(o.Space2(o.cheb_neumann(nx), o.cheb_neumann(ny)))
+    mass, lap, _, _ = f.ingredients_for_poisson(0)
+    lam, fwd, bwd = o.parity_eig(lap, mass)
+    if abs(lam[0]) < 1e-10:
+        lam = lam - 1e-10
+    return lam, fwd, bwd
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the box's host cores."""
+    """--impl reference: the reference's CPU algorithm on the box's host cores.  The Rust reference cannot be built in
+    this image (no cargo/rustc), so the arm is the C++/OpenMP restatement that keeps the reference's pass structure
+    (oracle/cpu_restated.cpp), all host threads, the driver's --steps / --warmup."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = args.config
-    n_steps = max(1, min(args.steps, 3 if cfg in ("C2", "C3") else (1 if cfg in ("C4", "C5") else 20)))
-    v, t, cores = cpu_oracle_steps(cfg, n_steps, None if CONFIGS[cfg][4] or CONFIGS[cfg][0] < 1000 else "parity")
+    nav = cpu_restated(cfg, host_eig(cfg))
+    sec = time_cpu(nav, args.steps, args.warmup)
+    v = 1.0 / sec
     line = {
         "impl": "reference", "metric": "Navier2D timesteps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": n_steps, "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "config": cfg},
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_steps} update() steps of the numpy oracle port (reference Rust toolchain absent)"},
+        "config": config_dict(cfg),
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": nav.threads, "kind": "port", "flavour": "restated-c++",
+                         "openblas_dgemm": nav.blas,
+                         "sample": f"{args.steps} full update() steps of the C++/OpenMP restatement of the reference's pass structure "
+                                   f"(reference Rust toolchain absent), {nav.threads} threads"},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_small(b2, ctx, dist):
+    """2 steps of a 257 x 129 confined problem on the SAME ranks / context as the timed run, gathered and compared with
+    the numpy oracle (navier.rs:438-466 / navier_stokes_mpi/navier.rs:497-522).  Cheap; runs before the timing."""
+    import numpy as np
+
+    from oracle import rustpde_oracle as o
+
+    nx, ny = 257, 129
+    eig = b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
+    ref = o.Navier2D(nx, ny, 1e5, 1.0, 1e-2, 1.0, "rbc", pois_eig=eig)
+    ref.init_random(0.1)
+    nav = b2.Navier2D(nx, ny, 1e5, 1.0, 1e-2, 1.0, "rbc", ctx=ctx, pois_eig=eig)
+    nav.init_random(0.1)
+    for _ in range(2):
+        ref.update()
+    nav.update(2)
+    got = nav.gather_state()
+    worst = max(float(np.abs(got[k] - v).max() / np.abs(v).max()) for k, v in ref.state().items())
+    nav.close()
+    assert worst < 1e-10, f"multi-rank parity check failed: {worst}"
+    return {"world": ctx.nranks, "config": "confined 257x129, 2 steps, random init, vs numpy oracle", "worst_rel_err": worst, "tol": 1e-10}
 
 
 def main():
@@ -123,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity checks (small multi-rank problem; workload vs CPU restatement)")
     ap.add_argument("--mode", type=int, default=1, help="1 fused+graph (default), 3 fused without graph, 0 one pass pair per reference call")
     args = ap.parse_args()
     if args.config is None:
@@ -163,8 +219,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None if args.no_parity else parity_small(b2, ctx, dist)   # same ranks, same context, before the timing
     t_setup = time.perf_counter()
-    nav = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, ctx=ctx)
+    eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
+    nav = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, ctx=ctx, pois_eig=eig)
     nav.init_random(0.1)
     nav.set_mode(args.mode)
     setup_s = time.perf_counter() - t_setup
@@ -218,11 +276,12 @@ def main():
     lane_ms = (ms - gemm_ms) / args.steps
     alg_bytes = 728.0 * N / world   # per GPU
     achieved = alg_bytes / (lane_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg, {}).get("dram_bytes_per_step")
-    except Exception:  # noqa: BLE001
-        pass
+    traffic = None   # only a capture of THIS config on ONE GPU counts (profiles/traffic.json is written by tools/gpu_profile.sh)
+    if world == 1:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg, {}).get("dram_bytes_per_step")
+        except Exception:  # noqa: BLE001
+            pass
     info = nav.info()
     if per:
         gemm_flop = 0.0
@@ -230,14 +289,36 @@ def main():
         gemm_flop = 2.0 * 2.0 * info["P1"] * (info["ce"] ** 2 + info["co"] ** 2) / world
     else:
         gemm_flop = 4.0 * info["m0"] ** 2 * info["P1"] / world
+    # FP64 GEMM denominator: a plain library DGEMM of the Poisson products' shape, measured here (MEASURED_PEAKS.json has none)
+    fp64_peak = None
+    if gemm_flop > 0:
+        try:
+            m = 2048
+            a = torch.randn(m, m, dtype=torch.float64, device="cuda"); bm = torch.randn(m, 4096, dtype=torch.float64, device="cuda")
+            torch.matmul(a, bm); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                torch.matmul(a, bm)
+            e1.record(); torch.cuda.synchronize()
+            fp64_peak = 5 * 2.0 * m * m * 4096 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            del a, bm
+        except Exception:  # noqa: BLE001
+            fp64_peak = None
+    gemm_tf = (gemm_flop / (gemm_ms / args.steps * 1e-3) / 1e12) if gemm_ms > 0 else None
+    t_hbm = alg_bytes / (peak * 1e9) * 1e3
+    t_gemm = (gemm_flop / (fp64_peak * 1e12) * 1e3) if (fp64_peak and gemm_flop) else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "kernel": "lane_kernel (all per-axis passes of one step)", "alg_bytes_per_step": alg_bytes,
                 "lane_ms_per_step": lane_ms, "gemm_ms_per_step": gemm_ms / args.steps,
-                "lane_ms_note": "step time minus the time inside the Poisson GEMMs (cuBLAS, FP64-peak-bound, measured with events in a separate un-captured pass)",
-                "gemm_tflops": (gemm_flop / (gemm_ms / args.steps * 1e-3) / 1e12) if gemm_ms > 0 else None,
-                "gemm_flop_per_step": gemm_flop, "parity_block_gemms": bool(info["parity_blocks"]),
-                "traffic_note": "dram__bytes_read+write summed over the lane-kernel launches of one step (ncu --set full), per GPU" if traffic else None}
+                "lane_ms_note": "step time minus the time inside the Poisson GEMMs (FP64-peak-bound, measured with events in a separate un-captured pass)",
+                "gemm": {"achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (gemm_tf / fp64_peak) if (gemm_tf and fp64_peak) else None,
+                         "peak_source": "library DGEMM 2048x2048x4096 (torch.matmul f64) timed in this run", "flop_per_step": gemm_flop,
+                         "parity_block_gemms": bool(info["parity_blocks"])},
+                "whole_step": {"bound_ms": t_hbm + t_gemm, "measured_ms": ms_per_step, "frac": (t_hbm + t_gemm) / ms_per_step,
+                               "note": "algorithmic bytes / measured HBM peak + GEMM flops / measured DGEMM rate, over the measured step"},
+                "traffic_note": "dram__bytes_read+write summed over the lane-kernel launches of one step (ncu --set full, this config, 1 GPU)" if traffic else None}
 
     # ---- end to end with host-resident state (pinned), copies inside the timed region ----
     e2e, e2e_error = None, None
@@ -280,24 +361,43 @@ def main():
         except Exception as ex:  # noqa: BLE001 - the device-resident line must still be printed
             e2e, e2e_error = None, repr(ex)
 
-    # ---- CPU baseline (oracle port), bounded sample ----
-    cpu = None
+    # ---- CPU baseline: the C++/OpenMP restatement of the reference's pass structure, bounded sample; the same run is the
+    # parity check of the BENCHMARKED configuration (k steps from the same synthetic initial state on both sides) ----
+    cpu, parity_workload = None, None
     if not args.no_cpu_baseline and world == 1:
-        n_cpu = 2 if cfg in ("C2", "C3") else (1 if cfg in ("C4", "C5") else 10)
-        eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
-        v, t, cores = cpu_oracle_steps(cfg, n_cpu, eig)
-        cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} update() steps of the numpy oracle port at the same config ({t:.1f} s)"}
+        n_cpu = {"C1": 20, "C2": 5, "C3": 5}.get(cfg, 3)
+        cnav = cpu_restated(cfg, eig)
+        sec = time_cpu(cnav, n_cpu, 1)
+        cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": cnav.threads, "kind": "port", "flavour": "restated-c++",
+               "openblas_dgemm": cnav.blas,
+               "sample": f"{n_cpu} full update() steps (after 1 warm-up) of the C++/OpenMP restatement of the reference's pass structure at the same config, {cnav.threads} threads ({sec * n_cpu:.1f} s)"}
+        if nx * ny <= 1100 * 1100:   # the 1-thread figure (README's OPENBLAS_NUM_THREADS=1 mode) where it costs seconds
+            c1 = cpu_restated(cfg, eig, threads=1)
+            cpu["value_1thread"] = 1.0 / time_cpu(c1, 2, 1)
+            del c1
+            cnav = cpu_restated(cfg, eig)
+            cnav.update(1 + n_cpu)
+        if not args.no_parity:
+            nav.init_random(0.1)
+            nav.pres.vhat = np.zeros_like(nav.pres.vhat)
+            nav.update(1 + n_cpu)
+            gs = nav.state()
+            worst = {k: float(np.abs(gs[k] - v).max() / np.abs(v).max()) for k, v in cnav.state().items()}
+            parity_workload = {"config": cfg, "steps": 1 + n_cpu, "against": "oracle/cpu_restated.cpp (checked against the numpy oracle in tests/)",
+                               "worst_rel_err": max(worst.values()), "per_field": worst, "tol": 1e-10,
+                               "note": "both sides get the same host eigendecomposition of the Poisson operator (DESIGN.md, Poisson parity)"}
+        del cnav
 
     line = {
         "metric": "Navier2D timesteps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "config": cfg, "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, slab decomposition, peer-store transposes over NVLink",
-                   "l2": "per-step working set (~30 arrays x 8N bytes) exceeds the 126 MB L2; no explicit flush" if N > 600000 else "fits L2",
-                   "schedule": {1: "fused, CUDA-graph replay", 3: "fused, no graph", 0: "one pass pair per reference call"}.get(args.mode, str(args.mode)),
-                   "launches_per_step": nav.launches_per_step(), "parallel_branches": bool(info["branches"])},
+        "config": config_dict(cfg),
+        "run": {"parallelism": "1 GPU" if world == 1 else f"{world} GPUs, slab decomposition, peer-store transposes over NVLink",
+                "schedule": {1: "fused, CUDA-graph replay", 3: "fused, no graph", 0: "one pass pair per reference call"}.get(args.mode, str(args.mode)),
+                "launches_per_step": nav.launches_per_step(), "parallel_branches": bool(info["branches"])},
         "clocks": clocks, "e2e": e2e, "e2e_error": e2e_error, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "parity_check": parity, "parity_check_workload": parity_workload,
         "setup_s": setup_s, "div_norm": div,
     }
     if rank == 0:

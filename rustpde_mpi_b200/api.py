@@ -4,6 +4,7 @@ calling the C ABI only.  numpy arrays cross the boundary; everything else stays 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -42,6 +43,13 @@ class Context:
         self._h = C.c_void_p()
         check(lib().b2_ctx_create(device, rank, nranks, heap_bytes, C.byref(self._h)))
         self.device, self.rank, self.nranks = device, rank, nranks
+
+    def close(self):
+        """Release the context (streams, events, workspaces, symmetric heap, IPC mappings).  Every object created on
+        it must be gone first; contexts are not destroyed implicitly."""
+        if self._h:
+            check(lib().b2_ctx_destroy(self._h))
+            self._h = None
 
     @classmethod
     def distributed(cls, device, heap_bytes):
@@ -137,6 +145,13 @@ class Space2:
         self._h = C.c_void_p()
         check(lib().b2_space2_create(self.ctx._h, base0[0], base0[1], base1[0], base1[1], C.byref(self._h)))
 
+    def close(self):
+        if getattr(self, "_h", None):
+            _release(lib().b2_space_destroy, self._h)
+            self._h = None
+
+    __del__ = close
+
     def shape(self, kind):
         r, c, cx = C.c_int(), C.c_int(), C.c_int()
         check(lib().b2_space_shape(self._h, kind, C.byref(r), C.byref(c), C.byref(cx)))
@@ -160,6 +175,14 @@ class Space2:
         return out
 
 
+def _release(fn, handle):
+    """Destroy a native object from close()/__del__: never raises (interpreter shutdown, already-destroyed context)."""
+    try:
+        fn(handle)
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def _host_dtype(space, kind):
     return np.complex128 if space.shape(kind)[1] else np.float64
 
@@ -175,6 +198,13 @@ class DeviceArray:
             check(lib().b2_array_create(space._h, kind, C.byref(self._h)))
         else:
             self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None) and self._owner:
+            _release(lib().b2_array_destroy, self._h)
+        self._h = None
+
+    __del__ = close
 
     def local_rows(self):
         """(first row, number of rows) of this rank's slab (axis 0 split; whole array with one rank)."""
@@ -206,9 +236,10 @@ class DeviceArray:
         return self
 
     def norm(self):
+        """L2 norm of the global array (functions.rs:24-35): local sum of squares, all-reduced over the ranks."""
         v = C.c_double()
-        check(lib().b2_array_norm2(self._h, C.byref(v)))
-        return v.value
+        check(lib().b2_array_sumsq_local(self._h, C.byref(v)))
+        return float(np.sqrt(self.space.ctx.all_reduce_sum(v.value)))
 
 
 class Field2:
@@ -225,6 +256,13 @@ class Field2:
             self._h = handle
         self.x = space.coords()
         self.dx = [self._get_dx(x, space.base_kind(i) == FOURIER_R2C) for i, x in enumerate(self.x)]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._owner:
+            _release(lib().b2_field_destroy, self._h)
+        self._h = None
+
+    __del__ = close
 
     @staticmethod
     def _get_dx(x, periodic):  # src/field.rs:135-163
@@ -299,16 +337,18 @@ class Field2:
     def backward(self):
         check(lib().b2_backward(self._h))
 
-    def to_ortho(self):
-        out = DeviceArray(self.space, ORTHO)
+    def to_ortho(self, out=None):
+        if out is None:
+            out = DeviceArray(self.space, ORTHO)
         check(lib().b2_to_ortho(self._h, out._h))
         return out
 
     def from_ortho(self, arr):
         check(lib().b2_from_ortho(self._h, arr._h))
 
-    def gradient(self, deriv, scale=None):
-        out = DeviceArray(self.space, ORTHO)
+    def gradient(self, deriv, scale=None, out=None):
+        if out is None:
+            out = DeviceArray(self.space, ORTHO)
         sc = None
         if scale is not None:
             sc = (C.c_double * 2)(float(scale[0]), float(scale[1]))
@@ -329,6 +369,13 @@ class _Solver:
 
     solve_par = solve
 
+    def close(self):
+        if getattr(self, "_h", None):
+            _release(lib().b2_solver_destroy, self._h)
+        self._h = None
+
+    __del__ = close
+
 
 class HholtzAdi(_Solver):
     """``HholtzAdi::new(&field, c)`` (src/solver/hholtz_adi.rs:48-76)."""
@@ -348,6 +395,20 @@ def _eig_sorted(x):
 
 
 def poisson_eig(kind0, n0, c0, parity_split=None):
+    if os.environ.get("B2_EIG_CACHE"):   # optional on-disk cache of the host LAPACK setup (minutes at n = 8193)
+        d = os.environ["B2_EIG_CACHE"]
+        f = os.path.join(d, f"eig_k{kind0}_n{n0}_c{float(c0)!r}_p{parity_split}.npz")
+        if os.path.exists(f):
+            z = np.load(f)
+            return z["lam"], z["fwd"], z["bwd"]
+        lam, fwd, bwd = _poisson_eig(kind0, n0, c0, parity_split)
+        os.makedirs(d, exist_ok=True)
+        np.savez(f, lam=lam, fwd=fwd, bwd=bwd)
+        return lam, fwd, bwd
+    return _poisson_eig(kind0, n0, c0, parity_split)
+
+
+def _poisson_eig(kind0, n0, c0, parity_split=None):
     """Host-side setup of ``FdmaTensor::from_matrix`` (src/solver/fdma_tensor.rs:117-129) + the
     singularity rule of ``Poisson::new`` (src/solver/poisson.rs:84-86):  X = C0^-1 A0 = Q L Q^-1,
     returns (lam, fwd = Q^-1 C0^-1, bwd = Q).  A0 and C0 only couple indices of equal parity, so
@@ -409,7 +470,10 @@ class Navier2D:
 
     FIELDS = {"temp": 0, "velx": 1, "vely": 2, "pres": 3, "pseu": 4, "tempbc": 5}
 
-    def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False, ctx=None):
+    def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False, ctx=None, pois_eig=None, init_random=True):
+        """``pois_eig``: optional (lam, fwd, bwd) of ``poisson_eig`` (the host LAPACK setup of the confined Poisson
+        solver) when the caller already has it.  ``init_random``: the reference constructors end with
+        ``init_random(0.1)`` (navier.rs:305,425); pass False to start from zero fields."""
         self.ctx = ctx or default_context()
         self.nx, self.ny, self.ra, self.pr, self.dt, self.aspect = nx, ny, ra, pr, dt, aspect
         self.periodic = periodic
@@ -418,7 +482,7 @@ class Navier2D:
         if periodic:
             args = (None, None, None)
         else:
-            lam, fwd, bwd = poisson_eig(CHEB_NEUMANN, nx, 1.0 / aspect ** 2)
+            lam, fwd, bwd = pois_eig if pois_eig is not None else poisson_eig(CHEB_NEUMANN, nx, 1.0 / aspect ** 2)
             args = (_dp(lam), _dp(fwd), _dp(bwd))
         check(lib().b2_navier2d_create(self.ctx._h, nx, ny, ra, pr, dt, aspect, bc.encode(), int(periodic), *args, C.byref(self._h)))
         bx = (lambda k: fourier_r2c(nx)) if periodic else (lambda k: (k, nx))
@@ -435,16 +499,29 @@ class Navier2D:
             if name in ("velx", "vely", "temp", "pres"):
                 f.scale(self.scale)
             setattr(self, name, f)
+        if init_random:
+            self.init_random(0.1)
+
+    def close(self):
+        """Free every device array, solver and space of this solver."""
+        if getattr(self, "_h", None):
+            for k in ("_field", "_temp_twin", "_diag_a", "_diag_b"):
+                if getattr(self, k, None) is not None:
+                    setattr(self, k, None)
+            _release(lib().b2_navier_destroy, self._h)
+        self._h = None
+
+    __del__ = close
 
     @classmethod
-    def new_confined(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None):
+    def new_confined(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None, **kw):
         """navier.rs:215-308."""
-        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=False, ctx=ctx)
+        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=False, ctx=ctx, **kw)
 
     @classmethod
-    def new_periodic(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None):
+    def new_periodic(cls, nx, ny, ra, pr, dt, aspect, bc="rbc", ctx=None, **kw):
         """navier.rs:336-428."""
-        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=True, ctx=ctx)
+        return cls(nx, ny, ra, pr, dt, aspect, bc, periodic=True, ctx=ctx, **kw)
 
     # initial conditions: navier.rs:156-182, functions.rs:85-140
     def _unit(self, f):
@@ -615,16 +692,25 @@ class _BorrowedSpace(Space2):
         return out
 
 
+MAX_TIMESTEP = 10_000_000
+
+
 def integrate(pde, max_time, save_intervall=None):
     """``integrate`` loop (src/lib.rs:187-219): update, callback at save intervals, stop at
     ``max_time`` or when ``exit()`` reports a NaN divergence."""
     eps_dt = pde.get_dt() * 1e-4
+    timestep = 0
     while True:
         pde.update()
+        timestep += 1
         t = pde.get_time()
-        if save_intervall is not None and (t + eps_dt) % save_intervall < pde.get_dt() / 2.0:
-            pde.callback()
+        if save_intervall is not None:   # lib.rs:197-199: both sides of the save time
+            r = t % save_intervall
+            if r < pde.get_dt() / 2.0 or r > save_intervall - pde.get_dt() / 2.0:
+                pde.callback()
         if t + eps_dt >= max_time:
+            break
+        if timestep >= MAX_TIMESTEP:   # lib.rs:23,209-212
             break
         if pde.exit():
             break

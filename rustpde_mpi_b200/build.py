@@ -5,7 +5,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "b200pde.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "lane_kernel.cuh"), os.path.join(HERE, "..", "include", "b200pde.h")]
+import glob
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(HERE, "..", "include", "b200pde.h")]
 OUT = os.path.join(HERE, "libb200pde.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -65,6 +65,8 @@ struct b2_ctx {
   // array has the same offset on every GPU and a peer's copy is peer_base[r] + offset
   char* heap = nullptr;
   size_t heap_bytes = 0, heap_used = 0;
+  std::vector<std::pair<size_t, size_t>> heap_free;   // (offset, bytes) blocks returned by ctx_free: every rank frees in the same order, so the heaps stay symmetric
+  std::map<void*, size_t> heap_live;                  // live blocks: pointer -> bytes
   double** d_peers = nullptr;  // device table of peer heap bases
   void* peer_base[B2_MAXPEERS] = {nullptr};
   bool attached = false;
@@ -76,12 +78,27 @@ static const size_t B2_HEAP_RESERVED = 4096;  // flags[0..nranks) + epoch counte
 static int ctx_alloc(b2_ctx* c, size_t bytes, double** out) {
   if (c->nranks == 1) { CK(cudaMalloc(out, bytes)); return B2_OK; }
   const size_t need = (bytes + 255) / 256 * 256;
+  for (size_t i = 0; i < c->heap_free.size(); i++)
+    if (c->heap_free[i].second == need) {   // exact-size reuse (arrays of a problem share one padded size)
+      *out = reinterpret_cast<double*>(c->heap + c->heap_free[i].first);
+      c->heap_free.erase(c->heap_free.begin() + i);
+      c->heap_live[*out] = need;
+      return B2_OK;
+    }
   if (c->heap_used + need > c->heap_bytes) return fail(B2_ERR_ARG, "symmetric heap exhausted: pass a larger heap_bytes to b2_ctx_create");
   *out = reinterpret_cast<double*>(c->heap + c->heap_used);
   c->heap_used += need;
+  c->heap_live[*out] = need;
   return B2_OK;
 }
-static void ctx_free(b2_ctx* c, void* p) { if (p && c->nranks == 1) cudaFree(p); }
+static void ctx_free(b2_ctx* c, void* p) {
+  if (!p) return;
+  if (c->nranks == 1) { cudaFree(p); return; }
+  auto it = c->heap_live.find(p);
+  if (it == c->heap_live.end()) return;
+  c->heap_free.emplace_back((size_t)(static_cast<char*>(p) - c->heap), it->second);
+  c->heap_live.erase(it);
+}
 
 // all-ranks barrier on the stream: signal every peer's flag slot, then wait for every peer's signal
 __global__ void k_barrier(unsigned long long* const* peers, int rank, int nranks) {
@@ -445,10 +462,11 @@ struct Prog {
 };
 
 template <int E, int LN, int TPLC> static int launch_ELT(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
-  static size_t set_smem = 0;
-  if (c.smem > set_smem) {
+  static size_t set_smem[64] = {0};   // per device: the attribute belongs to the (function, device) pair
+  size_t& have = set_smem[ctx->device & 63];
+  if (c.smem > have) {
     CK(cudaFuncSetAttribute(lane_kernel<E, LN, TPLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    set_smem = c.smem;
+    have = c.smem;
   }
   B2_LAUNCH((lane_kernel<E, LN, TPLC>), (c.groups / ctx->nranks) * (4 / c.LN), c.NT, c.smem, ctx->cur, p);
   CK(cudaGetLastError());
@@ -459,7 +477,7 @@ template <int E, int LN, int TPLC> static int launch_ELT(b2_ctx* ctx, const Pass
 static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 #define B2_INST(e, ln, tpl) if (c.fast && c.E == e && c.LN == ln && c.TPL == tpl) return launch_ELT<e, ln, tpl>(ctx, c, p);
   B2_INST(16, 4, 128) B2_INST(16, 4, 64) B2_INST(16, 4, 32) B2_INST(16, 4, 16) B2_INST(16, 4, 8)
-  B2_INST(16, 2, 256) B2_INST(16, 2, 128)
+  B2_INST(16, 2, 256) B2_INST(16, 2, 128) B2_INST(8, 4, 256)
   B2_INST(8, 4, 64) B2_INST(8, 4, 32) B2_INST(8, 4, 16) B2_INST(8, 4, 8) B2_INST(4, 4, 8)
 #undef B2_INST
   if (c.LN == 4) {
@@ -489,6 +507,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.NP = c.NP; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
   p.w_off = c.w_off; p.ld_off = c.ld_off; p.st_off = c.st_off;
   p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
+  p.l2pf = getenv("B2_PF") ? atoi(getenv("B2_PF")) : 0;
   {   // share of a direct load that the copy engine takes (percent, B2_SPLIT; the threads fetch the rest)
     int pct = 100;
     if (const char* e = getenv("B2_SPLIT")) pct = std::max(0, std::min(100, atoi(e)));
@@ -579,7 +598,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
     const int Nc = N / 2;
     for (int e = want; e >= 4; e /= 2) {
       const int tpl = Nc / e;
-      if (tpl >= 8 && (tpl * LN) % 32 == 0 && tpl * LN <= 512 && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
+      if (tpl >= 8 && (tpl * LN) % 32 == 0 && tpl * LN <= (getenv("B2_T1024") ? 1024 : 512) && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
     }
     return false;
   };
@@ -997,8 +1016,22 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (!c) return B2_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto& st : c->side) if (st) cudaStreamSynchronize(st);
   if (c->blas) cublasDestroy(c->blas);
+  for (auto e : c->gemm_events) cudaEventDestroy(e);
+  for (auto& e : c->evp) if (e) cudaEventDestroy(e);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (auto& st : c->side) if (st) cudaStreamDestroy(st);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->blas_ws) cudaFree(c->blas_ws);
+  if (c->stage) cudaFree(c->stage);
+  if (c->d_prof) cudaFree(c->d_prof);
+  if (c->d_peers) cudaFree(c->d_peers);
+#ifndef B2_EMU
+  for (int r = 0; r < c->nranks; r++) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->heap) cudaFree(c->heap);
+#endif
   delete c;
   return B2_OK;
 }
@@ -1199,10 +1232,11 @@ int b2_array_local_rows(const b2_array* a, int* row_start, int* row_count) {
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes) { return array_copy(a, const_cast<void*>(buf), bytes, 1); }
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes) { return array_copy(a, buf, bytes, 0); }
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
-  if (y->sp->elems() != x->sp->elems()) return fail(B2_ERR_SHAPE, "axpy: different spaces");
+  if (y->sp->elems() != x->sp->elems() || y->shape_kind != x->shape_kind) return fail(B2_ERR_SHAPE, "axpy: different spaces / shape kinds");
   const size_t n = y->sp->elems();
   B2_LAUNCH(k_axpby, ew_grid(n), 256, 0, y->sp->ctx->stream, n, y->d, alpha, x->d, 1.0);
   CK(cudaGetLastError());
+  y->sp->ctx->launches++;
   return B2_OK;
 }
 static int norm2_dev(b2_space* sp, const double* d, double* out) {
@@ -1751,7 +1785,7 @@ int b2_navier_update(b2_navier* nv, int nsteps) {
   for (int s = 0; s < nsteps; s++) {
 #ifndef B2_EMU
     // the fused step is a fixed launch sequence: capture it once into a CUDA graph and replay it
-    if (nv->fused && nv->use_graph && !ctx->profile && nv->warm_steps >= 1) {
+    if (nv->fused && nv->use_graph && !ctx->profile && !ctx->d_prof && nv->warm_steps >= 1) {
       if (!nv->graph) {
         cudaGraph_t g = nullptr;
         const long long l0 = ctx->launches;

@@ -33,7 +33,7 @@
 #define B2_MAXPEERS 8
 #define B2_ST_SLOTS 3    // store-staging slots (3: one CTA barrier per chunk, see store_staged)
 #define B2_MAXLD 8       // max load-ring slots
-#define B2_SCRATCH 8192  // bytes of scan scratch (16 warps x 4 lanes x (Aff2 map + state))
+#define B2_SCRATCH 16384 // bytes of scan scratch (32 warps x 4 lanes x (Aff2 map + state))
 #define B2_PROGCOPY 2048 // shared-memory copy of the program header + ops (everything of LaneProg in front of tm[])
 
 enum LaneOpCode {
@@ -95,6 +95,7 @@ struct LaneProg {
   int ld_tx;                  // bytes one ring box delivers ((CH+1) tiles x LN lanes x 32)
   int w_off, ld_off, st_off;  // byte offsets inside dynamic shared memory (128-aligned)
   int dsplit;                 // direct loads: tiles [0, dsplit) come by TMA, tiles [dsplit, in_tiles) by per-thread LDG at the same time
+  int l2pf;                   // number of load operands prefetched into L2 ahead of their op (0 = off)
   int bulk1d;                 // LN == 4: the slab is contiguous, so slab-shaped copies are plain 1-D bulk copies (no tensor map)
   unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
   LaneOp ops[B2_MAXOPS];
@@ -288,7 +289,7 @@ struct Aff2 {
 // SUFFIX: q' > q, highest applied first) applied to the zero state.  Threads of a lane sit LN apart in a warp
 // (32/LN of them per warp); warp totals go through shared memory and ONE thread per lane runs the short
 // serial recurrence over the warps (vector recurrence only -- no matrix products on the critical path).
-// scratch: >= 16 warps * LN lanes * (V + S).  All threads of the CTA must call.
+// scratch: >= 32 warps * LN lanes * (V + S).  All threads of the CTA must call.
 template <class M, bool SUFFIX, int LN>
 __device__ __forceinline__ typename M::S lane_scan_state(typename M::V mine, int TPL, void* scratch) {
   typedef typename M::V V;
@@ -311,7 +312,7 @@ __device__ __forceinline__ typename M::S lane_scan_state(typename M::V mine, int
   if (TPL <= QW) return M::apply(exc, M::zero());
   const int nw = TPL / QW, w = tid >> 5;
   V* tot = reinterpret_cast<V*>(scratch);                  // [warp][lane] warp totals
-  S* ent = reinterpret_cast<S*>(tot + 16 * LN);            // [warp][lane] state entering the warp
+  S* ent = reinterpret_cast<S*>(tot + 32 * LN);            // [warp][lane] state entering the warp
   if (SUFFIX ? (qi == 0) : (qi == QW - 1)) tot[w * LN + l] = inc;
   __syncthreads();
   if (tid < LN) {
@@ -371,6 +372,20 @@ struct Prefetch {             // producer state (thread 0) + the phase of the di
 __device__ __forceinline__ int next_ring_load(const LaneProg& P, int o) {
   while (o < P.nops && !(P.ops[o].code == OP_LOAD && (P.ops[o].i2 & LD_TMA))) o++;
   return o;
+}
+// L2 prefetch of the slab of the n-th tiled load op after op o (thread 0): the copy engine pulls the operand into L2 while
+// the warps are still working on the current one, so that the load itself runs at L2 latency instead of DRAM latency.
+__device__ __forceinline__ void prefetch_loads_l2(const LaneProg& P, int o, int nth, int gl) {
+  if (!P.bulk1d || !P.l2pf) return;
+  for (int k = o + 1; k < P.nops; k++) {
+    const LaneOp& op = P.ops[k];
+    if (op.code != OP_LOAD || (op.i2 & (LD_PLAIN | LD_AFTER_STORE))) continue;
+    if (--nth > 0) continue;
+    const char* src = static_cast<const char*>(op.p0) + (size_t)gl * P.in_tiles * 128;
+    const uint32_t bytes = (uint32_t)P.in_tiles * 128u;
+    for (uint32_t b = 0; b < bytes; b += 32768u) bulk_prefetch_l2(src + b, min(32768u, bytes - b));
+    return;
+  }
 }
 __device__ __forceinline__ int slot_next(int slot, int NP) { return slot + 1 == NP ? 0 : slot + 1; }   // chunk c lives in slot (3 + c) mod NP
 // Request the next chunk of the program if its slot is free (thread 0).  Chunk c of a load goes to slot
@@ -1094,7 +1109,10 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
 // TPLC = threads per lane as a compile-time constant for transform-sized lanes (N = 2*E*TPLC: the hot operators
 // then run their compile-time-geometry versions of lane_fast.cuh), 0 = generic geometry read from the program.
 template <int E, int LN, int TPLC>
-__global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneProg Pp) {
+#ifndef B2_LB
+#define B2_LB __launch_bounds__((LN * TPLC > 512) ? 1024 : 512)
+#endif
+__global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
   B2_DYN_SMEM(char, smem_raw);
   // The ops run as separate (non-inlined) functions that get the program by reference; a reference into
   // parameter space degrades to generic loads with global-memory latency, so the header and the op list are
@@ -1123,6 +1141,7 @@ __global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneP
         tmap_prefetch(&Pp.tm[o]);
     pf.op = next_ring_load(P, 0);
     while (prefetch_next(P, sv, pf, -1)) {}
+    for (int k = 2; k <= P.l2pf; k++) prefetch_loads_l2(P, -1, k, gl);   // the first load is issued right away
   }
   __syncthreads();
   unsigned cph = 0;   // per-slot parity of the next chunk to consume
@@ -1133,6 +1152,7 @@ __global__ void __launch_bounds__(512) lane_kernel(const __grid_constant__ LaneP
     if (P.prof) t0 = clock64();
     switch (op.code) {
       case OP_LOAD:
+        if (threadIdx.x == 0 && P.l2pf) prefetch_loads_l2(P, o, P.l2pf, gl);
         if (op.i2 & LD_DIRECT) load_direct<LN>(P, op, &Pp.tm[o], sv, pf);
         else if (op.i2 & LD_TMA) load_ring<LN>(P, op, o, sv, cph, pf);
         else load_threads<LN, (E == 16 ? 8 : 4)>(P, op, sv, gl, lb);

@@ -7,8 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "rustpde_mpi_b200", "csrc", "b200pde.cu")
 OUT = os.path.join(HERE, "libb200pde_emu.so")
-DEPS = [SRC, os.path.join(ROOT, "rustpde_mpi_b200", "csrc", "lane_kernel.cuh"), os.path.join(HERE, "cuda_emu.h"),
-        os.path.join(ROOT, "include", "b200pde.h")]
+import glob
+DEPS = sorted(glob.glob(os.path.join(ROOT, "rustpde_mpi_b200", "csrc", "*"))) + [os.path.join(HERE, "cuda_emu.h"),
+                                                                               os.path.join(ROOT, "include", "b200pde.h")]
 
 
 def build(force=False):
