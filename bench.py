@@ -378,14 +378,29 @@ def main():
             cnav = cpu_restated(cfg, eig)
             cnav.update(1 + n_cpu)
         if not args.no_parity:
+            def rel(gs, cs):
+                return {k: float(np.abs(gs[k] - v).max() / np.abs(v).max()) for k, v in cs.items()}
+
             nav.init_random(0.1)
             nav.pres.vhat = np.zeros_like(nav.pres.vhat)
             nav.update(1 + n_cpu)
-            gs = nav.state()
-            worst = {k: float(np.abs(gs[k] - v).max() / np.abs(v).max()) for k, v in cnav.state().items()}
-            parity_workload = {"config": cfg, "steps": 1 + n_cpu, "against": "oracle/cpu_restated.cpp (checked against the numpy oracle in tests/)",
-                               "worst_rel_err": max(worst.values()), "per_field": worst, "tol": 1e-10,
+            e_rand = rel(nav.state(), cnav.state())
+            del cnav
+            # the same configuration from the reference example's smooth state (examples/navier_rbc.rs:18-22): the strict bound
+            cnav = cpu_restated(cfg, eig)
+            cnav.set_velocity(0.2, 1.0, 1.0); cnav.set_temperature(0.2, 1.0, 1.0)
+            cnav.update(2)
+            nav.set_velocity(0.2, 1.0, 1.0); nav.set_temperature(0.2, 1.0, 1.0)
+            nav.pres.vhat = np.zeros_like(nav.pres.vhat)
+            nav.update(2)
+            e_smooth = rel(nav.state(), cnav.state())
+            parity_workload = {"config": cfg, "against": "oracle/cpu_restated.cpp (checked against the numpy oracle in tests/)",
+                               "smooth_state": {"steps": 2, "worst_rel_err": max(e_smooth.values()), "per_field": e_smooth, "tol": 1e-10},
+                               "random_state": {"steps": 1 + n_cpu, "worst_rel_err": max(e_rand.values()), "per_field": e_rand, "tol": 1e-6,
+                                                "note": "white-noise fields: the projection step cancels a large divergent part, two CPU restatements "
+                                                        "already differ by ~1e-8 on 1025^2 (tests/test_gpu_parity_large.py)"},
                                "note": "both sides get the same host eigendecomposition of the Poisson operator (DESIGN.md, Poisson parity)"}
+            assert max(e_smooth.values()) < 1e-10 and max(e_rand.values()) < 1e-6, parity_workload
         del cnav
 
     line = {

@@ -84,7 +84,7 @@ int b2_array_sumsq_local(const b2_array* a, double* out);
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes);
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes);
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x); /* y += alpha x (same shape kind) */
-int b2_array_norm2(const b2_array* a, double* out);              /* sqrt(sum |a|^2), functions.rs:24-35 */
+int b2_array_norm2(const b2_array* a, double* out);              /* sqrt(sum |a|^2) of the GLOBAL array (collective over the ranks), functions.rs:24-35 */
 
 /* ---- Field2 (src/field.rs:59-129) ---- */
 int b2_field_create(b2_space* sp, b2_field** out);                    /* Field2::new */
@@ -100,6 +100,7 @@ int b2_to_ortho(const b2_field* f, b2_array* out /* ORTHO */);        /* field.r
 int b2_from_ortho(b2_field* f, const b2_array* in /* ORTHO */);       /* field.rs:118-123 */
 int b2_gradient(const b2_field* f, int d0, int d1, const double* scale /* 2 values or NULL */,
                 b2_array* out /* ORTHO */);                           /* field.rs:127-129 */
+int b2_field_dealias(b2_field* f);   /* dealias(&mut field): 2/3 rule on vhat, src/navier_stokes/functions.rs:72-82 */
 
 /* ---- solvers (src/solver.rs:59-97 `Solve::solve(input, output, axis)`) ---- */
 /* HholtzAdi::new(&field, [c0, c1]), src/solver/hholtz_adi.rs:48-76 */
@@ -127,7 +128,7 @@ int b2_navier_destroy(b2_navier* nav);
 /* which: 0 temp, 1 velx, 2 vely, 3 pres, 4 pseu, 5 tempbc */
 int b2_navier_field(b2_navier* nav, int which, b2_field** out);
 int b2_navier_update(b2_navier* nav, int nsteps);            /* Integrate::update, navier.rs:438-466 */
-int b2_navier_div_norm(b2_navier* nav, double* out);         /* navier_eq.rs:32-49 (exit() NaN guard) */
+int b2_navier_div_norm(b2_navier* nav, double* out);         /* navier_eq.rs:32-49 (exit() NaN guard); the global norm on every rank */
 int b2_navier_get_time(const b2_navier* nav, double* t);
 int b2_navier_set_mode(b2_navier* nav, int mode);            /* bit0: fused schedule (default on); bit1: no CUDA-graph replay */
 /* schedule facts for bench.py: out[8] = {parity-block GEMMs, P0, P1, m0, ce, co, parallel branches, launches per step} */

@@ -83,6 +83,21 @@ class Navier2D:
         assert v.shape == (self.nx, self.ny)
         lib().rc_navier_set_v(self._h, FIELDS[name], v.ctypes.data_as(C.c_void_p))
 
+    def _unit(self):
+        """Unit coordinates of navier.rs:156-166 (functions.rs:85-125): (x - x0) / (x_last - x0) per axis."""
+        x = 2.0 * np.pi * np.arange(self.nx) / self.nx if self.periodic else -np.cos(np.pi * np.arange(self.nx) / (self.nx - 1))
+        y = -np.cos(np.pi * np.arange(self.ny) / (self.ny - 1))
+        return (x - x[0]) / (x[-1] - x[0]), (y - y[0]) / (y[-1] - y[0])
+
+    def set_velocity(self, amp, m, n):
+        x, y = self._unit()
+        self.set_v("velx", amp * np.outer(np.sin(np.pi * m * x), np.cos(np.pi * n * y)))
+        self.set_v("vely", -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y)))
+
+    def set_temperature(self, amp, m, n):
+        x, y = self._unit()
+        self.set_v("temp", -amp * np.outer(np.cos(np.pi * m * x), np.sin(np.pi * n * y)))
+
     def init_random(self, amp, seeds=(1, 2, 3)):
         for name, s in zip(("temp", "velx", "vely"), seeds):
             self.set_v(name, np.random.default_rng(s).uniform(-amp, amp, size=(self.nx, self.ny)))

@@ -56,6 +56,7 @@ SYMBOLS = {
     "b2_to_ortho": (_I, [_P, _P]),
     "b2_from_ortho": (_I, [_P, _P]),
     "b2_gradient": (_I, [_P, _I, _I, _DP, _P]),
+    "b2_field_dealias": (_I, [_P]),
     "b2_hholtz_adi_create": (_I, [_P, _D, _D, _PP]),
     "b2_poisson_create": (_I, [_P, _D, _D, _DP, _DP, _DP, _PP]),
     "b2_solver_destroy": (_I, [_P]),

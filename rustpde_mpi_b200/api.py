@@ -116,7 +116,9 @@ class Context:
         buf = (C.c_ulonglong * 64)()
         check(lib().b2_ctx_opprof(self._h, int(on), buf))
         names = {1: "load", 2: "store", 3: "band", 4: "deriv", 5: "fdma", 6: "dct", 7: "rfft", 8: "fdiff", 9: "scalevec",
-                 10: "zerotail", 11: "lanemask", 12: "zeroelem", 13: "scale"}
+                 10: "zerotail", 11: "lanemask", 12: "zeroelem", 13: "scale",
+                 16: "fdma.fwd_reduce", 17: "fdma.scan1", 18: "fdma.fwd_apply", 19: "fdma.compose", 20: "fdma.scan2", 21: "fdma.solve",
+                 22: "dct.pre", 23: "dct.fft", 24: "dct.post", 25: "st.fill", 26: "st.wait", 27: "ld.direct_first", 28: "ld.direct_later", 29: "ld.combine", 30: "ld.plain", 31: "ld.stencil"}
         return {names[c]: (buf[c], buf[32 + c]) for c in names if buf[32 + c]}
 
     def profile(self, on):
@@ -238,8 +240,8 @@ class DeviceArray:
     def norm(self):
         """L2 norm of the global array (functions.rs:24-35): local sum of squares, all-reduced over the ranks."""
         v = C.c_double()
-        check(lib().b2_array_sumsq_local(self._h, C.byref(v)))
-        return float(np.sqrt(self.space.ctx.all_reduce_sum(v.value)))
+        check(lib().b2_array_norm2(self._h, C.byref(v)))   # collective with several ranks (summed on the device)
+        return v.value
 
 
 class Field2:
@@ -336,6 +338,10 @@ class Field2:
 
     def backward(self):
         check(lib().b2_backward(self._h))
+
+    def dealias(self):
+        """``dealias(&mut field)`` (src/navier_stokes/functions.rs:72-82)."""
+        check(lib().b2_field_dealias(self._h))
 
     def to_ortho(self, out=None):
         if out is None:
@@ -564,9 +570,7 @@ class Navier2D:
 
     def div_norm(self):
         v = C.c_double()
-        check(lib().b2_navier_div_norm(self._h, C.byref(v)))
-        if self.ctx.nranks > 1:  # the library returns the local sum of squares; all_gather_sum of navier_eq.rs:51,64
-            return float(np.sqrt(self.ctx.all_reduce_sum(v.value)))
+        check(lib().b2_navier_div_norm(self._h, C.byref(v)))   # same value on every rank (all_gather_sum of navier_eq.rs:51,64)
         return v.value
 
     def exit(self):

@@ -122,7 +122,6 @@ static inline void bulk_reduce_add_1d(void* dst, const void* src, uint32_t bytes
   for (uint32_t i = 0; i < bytes / 8; i++) static_cast<double*>(dst)[i] += static_cast<const double*>(src)[i];
 }
 static inline void tmap_prefetch(const B2TMap*) {}
-static inline void bulk_prefetch_l2(const void*, uint32_t) {}
 static inline void bulk_commit() {}
 template <int N> static inline void bulk_wait_read() {}
 template <int N> static inline void bulk_wait() {}
@@ -211,9 +210,6 @@ __device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32
 __device__ __forceinline__ void bulk_reduce_add_1d(void* dst, const void* src, uint32_t bytes) {
   asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
                ::"l"(reinterpret_cast<uint64_t>(dst)), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {   // bytes: multiple of 16
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmap_prefetch(const B2TMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -101,7 +101,11 @@ static void ctx_free(b2_ctx* c, void* p) {
 }
 
 // all-ranks barrier on the stream: signal every peer's flag slot, then wait for every peer's signal
-__global__ void k_barrier(unsigned long long* const* peers, int rank, int nranks) {
+// `slot`: independent barrier lanes (one per stream / graph branch), 16 words each: flags[0..8) + the epoch counter
+__global__ void k_barrier(unsigned long long* const* peers_, int rank, int nranks, int slot) {
+  __shared__ unsigned long long* peers[B2_MAXPEERS];
+  if ((int)threadIdx.x < nranks) peers[threadIdx.x] = peers_[threadIdx.x] + 16 * slot;
+  __syncthreads();
   unsigned long long* mine = peers[rank];
   __shared__ unsigned long long epoch;
   if (threadIdx.x == 0) epoch = mine[B2_MAXPEERS] + 1;
@@ -116,10 +120,41 @@ __global__ void k_barrier(unsigned long long* const* peers, int rank, int nranks
   __syncthreads();
   if (threadIdx.x == 0) mine[B2_MAXPEERS] = e;
 }
+// sum of one double over the ranks, on the stream: every rank writes its term into every peer's slot, the flag exchange
+// of barrier lane 3 orders the writes, then everyone adds the nranks terms in rank order (same result on every rank).
+// Two value buffers alternate with the epoch so that a fast rank's next all-reduce cannot overwrite unread terms.
+__global__ void k_allreduce(unsigned long long* const* peers_, int rank, int nranks, const double* in, double* out) {
+  __shared__ unsigned long long* peers[B2_MAXPEERS];
+  if ((int)threadIdx.x < nranks) peers[threadIdx.x] = peers_[threadIdx.x] + 16 * 3;
+  __syncthreads();
+  unsigned long long* mine = peers[rank];
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) epoch = mine[B2_MAXPEERS] + 1;
+  __syncthreads();
+  const unsigned long long e = epoch;
+  const int buf = (int)(e & 1ull) * B2_MAXPEERS;
+  if ((int)threadIdx.x < nranks) {
+    volatile double* dst = reinterpret_cast<volatile double*>(peers_[threadIdx.x]) + 256 + buf + rank;
+    *dst = *in;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + rank) = e;
+    __threadfence_system();
+    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) {}
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const volatile double* v = reinterpret_cast<const volatile double*>(peers_[rank]) + 256 + buf;
+    double s = 0;
+    for (int r = 0; r < nranks; r++) s += v[r];
+    *out = s;
+    mine[B2_MAXPEERS] = e;
+  }
+}
 static int ctx_barrier(b2_ctx* c) {
   if (c->nranks == 1) return B2_OK;
   if (!c->attached) return fail(B2_ERR_ARG, "b2_ctx_attach_peers has not been called");
-  B2_LAUNCH(k_barrier, 1, 32, 0, c->stream, reinterpret_cast<unsigned long long* const*>(c->d_peers), c->rank, c->nranks);
+  const int slot = c->cur == c->side[0] ? 1 : (c->cur == c->side[1] ? 2 : 0);   // every stream has its own flags and epoch
+  B2_LAUNCH(k_barrier, 1, 32, 0, c->cur ? c->cur : c->stream, reinterpret_cast<unsigned long long* const*>(c->d_peers), c->rank, c->nranks, slot);
   CK(cudaGetLastError());
   c->barriers++;
   return B2_OK;
@@ -297,7 +332,7 @@ int Base1::init(int C, int TPL) {
 struct PassCfg {
   int in_tiles, out_tiles, LP, TPL, C, E, groups, LN;
   bool fast;   // transform-sized lane: N = 2*E*TPL and LP >= N + 4 (lane_fast.cuh)
-  int NT, CH, nch, NS, NP, CHD, nchd, ld_bytes, st_bytes, ld_tx, w_off, ld_off, st_off;   // TMA pipeline geometry (lane_kernel.cuh)
+  int NT, CHW, nsc, wslot_bytes, CHD, nchd, w_off, st_off;   // copy-pipeline geometry (lane_kernel.cuh)
   size_t smem;
 };
 
@@ -477,7 +512,7 @@ template <int E, int LN, int TPLC> static int launch_ELT(b2_ctx* ctx, const Pass
 static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 #define B2_INST(e, ln, tpl) if (c.fast && c.E == e && c.LN == ln && c.TPL == tpl) return launch_ELT<e, ln, tpl>(ctx, c, p);
   B2_INST(16, 4, 128) B2_INST(16, 4, 64) B2_INST(16, 4, 32) B2_INST(16, 4, 16) B2_INST(16, 4, 8)
-  B2_INST(16, 2, 256) B2_INST(16, 2, 128) B2_INST(8, 4, 256)
+  B2_INST(16, 2, 256) B2_INST(16, 2, 128)
   B2_INST(8, 4, 64) B2_INST(8, 4, 32) B2_INST(8, 4, 16) B2_INST(8, 4, 8) B2_INST(4, 4, 8)
 #undef B2_INST
   if (c.LN == 4) {
@@ -492,8 +527,8 @@ static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 
 static bool g_use_tma = getenv("B2_NOTMA") == nullptr;     // B2_NOTMA=1: every load/store on the per-thread LDG/STG path (A/B measurements)
 static bool g_use_direct = getenv("B2_NODIRECT") == nullptr; // B2_NODIRECT=1: plain loads/stores go through the ring / staging as well
-static bool g_use_ring = getenv("B2_RING") != nullptr;       // B2_RING=1: combining loads (accumulate / multiply / stencil) stream through the TMA ring;
-                                                             // default: per-thread LDGs (measured faster on C4: 64 KB in flight per SM vs the ring's chunk hand-offs)
+static bool g_use_ring = getenv("B2_LDTHREADS") == nullptr;  // combining loads (accumulate / multiply / stencil / scaled) stream through the warps' own
+                                                             // copy pipelines (load_warps); B2_LDTHREADS=1: per-thread 16-byte loads instead
 
 // orient 0: lanes along axis 1; orient 1: lanes along axis 0
 static int run_pass(b2_space* sp, int orient, Prog& pr) {
@@ -504,20 +539,29 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.LP = c.LP; p.in_tiles = c.in_tiles; p.out_tiles = c.out_tiles; p.TPL = c.TPL; p.C = c.C;
   p.group0 = ctx->rank * (c.groups / ctx->nranks); p.groups_per_rank = c.in_tiles / ctx->nranks; p.rank = ctx->rank;
   p.prof = ctx->d_prof; p.LN = c.LN;
-  p.NT = c.NT; p.CH = c.CH; p.nch = c.nch; p.NS = c.NS; p.NP = c.NP; p.CHD = c.CHD; p.nchd = c.nchd; p.ld_bytes = c.ld_bytes; p.st_bytes = c.st_bytes; p.ld_tx = c.ld_tx;
-  p.w_off = c.w_off; p.ld_off = c.ld_off; p.st_off = c.st_off;
+  p.NT = c.NT; p.CHW = c.CHW; p.nsc = c.nsc; p.wslot_bytes = c.wslot_bytes; p.CHD = c.CHD; p.nchd = c.nchd;
+  p.w_off = c.w_off; p.st_off = c.st_off;
   p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
-  p.l2pf = getenv("B2_PF") ? atoi(getenv("B2_PF")) : 0;
-  {   // share of a direct load that the copy engine takes (percent, B2_SPLIT; the threads fetch the rest)
-    int pct = 100;
-    if (const char* e = getenv("B2_SPLIT")) pct = std::max(0, std::min(100, atoi(e)));
-    p.dsplit = std::min(c.in_tiles, ((c.in_tiles * pct / 100 + c.CHD - 1) / c.CHD) * c.CHD);
-    if (pct == 0) p.dsplit = 0;
-  }
   bool exchange = false;
+  int npst = 0;
+  static const bool peer_tma = getenv("B2_PEER_THREADS") == nullptr;        // B2_PEER_THREADS=1: per-thread peer stores (round-1 path)
+  static const bool peer_acc_tma = getenv("B2_PEER_ACC_THREADS") == nullptr; // accumulating peer stores as bulk reductions over NVLink
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
       if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
+  }
+  // A tiled load followed by the composite -> orthonormal stencil (to_ortho: y_j = x_j + s_j x_{j-2}) becomes ONE load that
+  // applies the stencil on the fly (LD_STENCIL, per-thread 16-byte loads; the second operand x_{j-2} comes from the same
+  // lines): measured on C4 a direct load costs 9.5k cycles per lane group, a combining load 10.6k and the banded pass
+  // 7.1k, so the pair drops from 16.6k to ~10.6k.  B2_NOLDSTEN=1 keeps the two ops.
+  static const bool ld_sten = getenv("B2_NOLDSTEN") == nullptr;
+  for (int i = 0; ld_sten && i + 1 < p.nops; i++) {
+    LaneOp& lo = p.ops[i]; LaneOp& bo = p.ops[i + 1];
+    if (lo.code != OP_LOAD || (lo.i2 & (LD_PLAIN | LD_STENCIL | LD_ACC | LD_MUL)) || bo.code != OP_BAND) continue;
+    const int h0 = (int)(signed char)(bo.i1 & 0xff), h1 = (int)(signed char)((bo.i1 >> 8) & 0xff), h2 = (int)(signed char)((bo.i1 >> 16) & 0xff);
+    if (h0 != 0 || bo.p0 != nullptr || h1 != -2 || bo.p1 == nullptr || h2 != 127 || bo.i2 != lo.i0) continue;   // not to_ortho of what was loaded
+    lo.i2 |= LD_STENCIL; lo.p1 = bo.p1; lo.i0 = bo.i0;
+    bo.code = OP_PREBAND;   // no-op
   }
   // Fold a banded mat-vec into the LU solve that consumes it (forward offsets only, same output length; shared
   // coefficient vectors): the solve forms its right-hand side on the fly (lane_fast.cuh, fdma_fast_body<PREBAND>).
@@ -552,26 +596,43 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
       const bool direct = g_use_direct && !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
       for (int k = 0; k < i; k++)   // re-reading an array this program stored: the bulk stores have to be complete first
         if (p.ops[k].code == OP_STORE && p.ops[k].p0 == op.p0) op.i2 |= LD_AFTER_STORE;
-      if (!direct && !g_use_ring) continue;   // per-thread path
+      if (!direct && !g_use_ring) continue;   // per-thread path (B2_LDTHREADS=1)
       d.base = const_cast<void*>(op.p0); d.rank = 3;
       d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
       d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
-      d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CH + 1; d.box[2] = 1;
+      d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CHW + 1; d.box[2] = 1;
       op.i2 |= direct ? LD_DIRECT : LD_TMA;
+    } else if (op.code == OP_STORE && (op.i2 & ST_PEER) && !(op.i2 & ST_PLAIN)) {
+      // one transposed view per owner: rows = the tiles of the destination that live in that rank's slab
+      if (!peer_tma || ((op.i2 & ST_ACC) && !peer_acc_tma) || npst >= B2_MAXPST) continue;   // per-thread peer stores
+      const int gpr = c.in_tiles / ctx->nranks;
+      for (int o = 0; o < ctx->nranks; o++) {
+        B2TMapDesc dd; memset(&dd, 0, sizeof(dd));
+        dd.base = static_cast<char*>(ctx->peer_base[o]) + (static_cast<const char*>(op.p0) - static_cast<const char*>(ctx->peer_base[ctx->rank]));
+        dd.rank = 4;
+        dd.dim[0] = 4; dd.dim[1] = 4; dd.dim[2] = (uint64_t)c.out_tiles; dd.dim[3] = (uint64_t)gpr;
+        dd.stride[1] = 32; dd.stride[2] = 128; dd.stride[3] = (uint64_t)c.out_tiles * 128;
+        dd.box[0] = c.LN; dd.box[1] = 4; dd.box[2] = 1; dd.box[3] = c.CHW;
+        const int er = b2_encode_tmap(dd, &p.tmp[npst][o]);
+        if (er) return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a peer view (" + std::to_string(er) + ")");
+      }
+      op.i1 = npst++;
+      op.i2 |= ST_TMA;
+      continue;
     } else if (op.code == OP_STORE && !(op.i2 & (ST_PLAIN | ST_PEER))) {
       d.base = const_cast<void*>(op.p0);
       if (op.i2 & ST_TRANS) {
         d.rank = 4;
         d.dim[0] = 4; d.dim[1] = 4; d.dim[2] = (uint64_t)c.out_tiles; d.dim[3] = (uint64_t)c.in_tiles;
         d.stride[1] = 32; d.stride[2] = 128; d.stride[3] = (uint64_t)c.out_tiles * 128;
-        d.box[0] = c.LN; d.box[1] = 4; d.box[2] = 1; d.box[3] = c.CH;
+        d.box[0] = c.LN; d.box[1] = 4; d.box[2] = 1; d.box[3] = c.CHW;
         op.i2 |= ST_TMA;
       } else {
         const bool direct = g_use_direct && !(op.i2 & ST_ACC) && op.a == 1.0;
         d.rank = 3;
         d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
         d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
-        d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CH; d.box[2] = 1;
+        d.box[0] = 4 * c.LN; d.box[1] = direct ? c.CHD : c.CHW; d.box[2] = 1;
         op.i2 |= direct ? ST_DIRECT : ST_TMA;
       }
     } else continue;
@@ -598,7 +659,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
     const int Nc = N / 2;
     for (int e = want; e >= 4; e /= 2) {
       const int tpl = Nc / e;
-      if (tpl >= 8 && (tpl * LN) % 32 == 0 && tpl * LN <= (getenv("B2_T1024") ? 1024 : 512) && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
+      if (tpl >= 8 && (tpl * LN) % 32 == 0 && tpl * LN <= 512 && tpl <= 256 && 2 * (e + 1) * tpl >= Pl) { c->E = e; c->TPL = tpl; c->LN = LN; return true; }
     }
     return false;
   };
@@ -627,29 +688,26 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   c->NT = c->LN * c->TPL;
   c->fast = is_pow2(N) && N >= 64 && N == 2 * c->E * c->TPL && Pl >= N + 4 && getenv("B2_NOFAST") == nullptr;
   if (c->NT % 32) return fail(B2_ERR_UNSUPPORTED, "compute threads must fill whole warps");
-  // shared memory: [mbarriers 256][scratch][W][NS load slots of CH+1 tiles][3 store slots of CH tiles]
+  // shared memory: [mbarriers][program copy][scratch][W][per warp: 2 staging slots of CHW + 1 tiles]
   const int tile_bytes = c->LN * 32;
   c->nchd = (c->in_tiles + 255) / 256;                     // direct copies: boxes of <= 256 tiles straight into / out of W
   c->CHD = roundup((c->in_tiles + c->nchd - 1) / c->nchd, 4 / c->LN);   // box bytes multiple of 128: TMA shared-memory alignment
-  const size_t budget = 227 * 1024, fixed = 256 + B2_PROGCOPY + B2_SCRATCH;
+  const size_t budget = 227 * 1024, fixed = B2_BARBYTES + B2_PROGCOPY + B2_SCRATCH;
   const size_t wbytes = (size_t)roundup(c->nchd * c->CHD * tile_bytes, 128);   // the last direct box may overhang the lane by < nchd tiles
   if (fixed + wbytes > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
-  c->NS = 1;   // look-ahead slots (measured on C4: 1 beats 2 and 3 -- larger chunks, fewer per-chunk hand-offs)
-  if (const char* e = getenv("B2_NS")) { int v = atoi(e); if (v >= 1 && v <= B2_MAXLD - B2_ST_SLOTS) c->NS = v; }
   // short lanes: keep the CTA near 72 KB so that three fit on an SM; long lanes: one CTA owns the SM
   size_t room = budget - fixed - wbytes;
   if (wbytes <= 40 * 1024) room = std::min(room, std::max((size_t)8192, (size_t)72 * 1024 - std::min((size_t)72 * 1024, fixed + wbytes)));
-  int chmax = (int)(room / (size_t)(c->NS + B2_ST_SLOTS) / tile_bytes) - 2;
-  if (const char* e = getenv("B2_CH")) { int v = atoi(e); if (v >= 4) chmax = std::min(chmax, v); }
-  chmax = std::max(4, std::min(chmax, 254));
-  c->nch = (c->in_tiles + chmax - 1) / chmax;
-  c->CH = (c->in_tiles + c->nch - 1) / c->nch;
-  c->ld_tx = (c->CH + 1) * tile_bytes;
-  c->ld_bytes = roundup(c->ld_tx, 128);
-  c->st_bytes = c->ld_bytes;   // one pool of NP = 3 + NS slots: 0..2 stage stores, 3.. take look-ahead loads
-  c->NP = B2_ST_SLOTS + c->NS;
-  c->w_off = (int)fixed; c->ld_off = c->w_off + (int)wbytes; c->st_off = c->ld_off;
-  c->smem = (size_t)c->ld_off + (size_t)c->NP * c->ld_bytes;
+  const int nwarps = c->NT / 32;
+  int chw = (int)(room / ((size_t)nwarps * 2) / tile_bytes) - 1;   // one halo tile in front of every slot
+  if (const char* e = getenv("B2_CHW")) { int v = atoi(e); if (v >= 2) chw = std::min(chw, v); }
+  chw = std::max(2, std::min(chw, std::min(64, c->in_tiles)));
+  if (c->LN == 2 && (chw % 2 == 0)) chw--;                 // (CHW + 1) tiles of 64 bytes: a multiple of 128
+  c->CHW = chw;
+  c->nsc = (c->in_tiles + chw - 1) / chw;
+  c->wslot_bytes = roundup((chw + 1) * tile_bytes, 128);
+  c->w_off = (int)fixed; c->st_off = c->w_off + (int)wbytes;
+  c->smem = (size_t)c->st_off + (size_t)nwarps * 2 * c->wslot_bytes;
   if (c->smem > budget) return fail(B2_ERR_UNSUPPORTED, "lane group does not fit in shared memory");
   return B2_OK;
 }
@@ -1239,13 +1297,18 @@ int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
   y->sp->ctx->launches++;
   return B2_OK;
 }
-static int norm2_dev(b2_space* sp, const double* d, double* out) {
+static int norm2_dev(b2_space* sp, const double* d, double* out, bool global) {
   double* acc = nullptr;
   CK(cudaMalloc(&acc, sizeof(double)));
   CK(cudaMemsetAsync(acc, 0, sizeof(double), sp->ctx->stream));
   const size_t n = sp->elems();
   B2_LAUNCH(k_sumsq, ew_grid(n), 256, 0, sp->ctx->stream, n, d, acc);
   CK(cudaGetLastError());
+  if (global && sp->ctx->nranks > 1) {
+    if (!sp->ctx->attached) return fail(B2_ERR_ARG, "b2_ctx_attach_peers has not been called");
+    B2_LAUNCH(k_allreduce, 1, 32, 0, sp->ctx->stream, reinterpret_cast<unsigned long long* const*>(sp->ctx->d_peers), sp->ctx->rank, sp->ctx->nranks, acc, acc);
+    CK(cudaGetLastError());
+  }
   double h = 0;
   CK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
   CK(cudaStreamSynchronize(sp->ctx->stream));
@@ -1254,9 +1317,9 @@ static int norm2_dev(b2_space* sp, const double* d, double* out) {
   return B2_OK;
 }
 // sum |a|^2 over this rank's slab; with one rank b2_array_norm2 = sqrt of it (functions.rs:24-35)
-int b2_array_sumsq_local(const b2_array* a, double* out) { return norm2_dev(a->sp, a->d, out); }
+int b2_array_sumsq_local(const b2_array* a, double* out) { return norm2_dev(a->sp, a->d, out, false); }
 int b2_array_norm2(const b2_array* a, double* out) {
-  RET(norm2_dev(a->sp, a->d, out));
+  RET(norm2_dev(a->sp, a->d, out, true));   // all ranks: the norm of the global array (collective call)
   *out = std::sqrt(*out);
   return B2_OK;
 }
@@ -1294,6 +1357,18 @@ int b2_gradient(const b2_field* f, int d0, int d1, const double* scale, b2_array
   RET(need_kind(out, B2_SHAPE_ORTHO, "gradient"));
   if (d0 < 0 || d1 < 0 || d0 > 3 || d1 > 3) return fail(B2_ERR_ARG, "gradient: derivative order");
   return op_gradient(f->sp, f->vhat->d, d0, d1, scale, out->d);
+}
+
+// dealias(&mut field), src/navier_stokes/functions.rs:72-82: vhat[n_x.., ..] = 0 and vhat[.., n_y..] = 0 with
+// n = shape * 2 / 3 in integer arithmetic on the spectral shape (modes, not real rows)
+int b2_field_dealias(b2_field* f) {
+  b2_space* sp = f->sp;
+  const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  const int cut0 = (b0.m * 2 / 3) * (b0.cheb ? 1 : 2), cut1 = b1.m * 2 / 3;
+  Prog y; y.load(f->vhat->d, b1.rows_spec); y.zerotail(cut1); y.store(sp->tmp[0], b1.rows_spec, ST_TRANS);
+  RET(run_pass(sp, 0, y));
+  Prog x; x.load(sp->tmp[0], b0.rows_spec); x.zerotail(cut0); x.store(f->vhat->d, b0.rows_spec, ST_TRANS);
+  return run_pass(sp, 1, x);
 }
 
 int b2_hholtz_adi_create(const b2_field* f, double c0, double c1, b2_solver** out) { return hholtz_create(f->sp, c0, c1, out); }
@@ -1545,17 +1620,18 @@ static int nav_update_fused(b2_navier* nv) {
   const int P0 = so->P[0], P1 = so->P[1];
 
   // Independent passes run as parallel branches (three streams = three branches of the captured graph): a pass
-  // has ~P/4 CTAs, which fills the GPU only for the largest grids.  Single-GPU only: the multi-GPU flag
-  // barrier that follows every exchanging pass is one shared epoch counter.
-  const bool par = (ctx->nranks == 1) && nv->branches;
+  // has ~P/4 CTAs, which fills the GPU only for the largest grids.  With several GPUs every stream has its own
+  // barrier flags and epoch (ctx_barrier), so the branches stay independent across the exchange barriers too.
+  const bool par = nv->branches && (ctx->nranks == 1 || getenv("B2_NOBRANCH_MULTI") == nullptr);   // every stream has its own barrier flags
   auto on = [&](int k) { ctx->cur = par ? nav_stream(ctx, k) : ctx->stream; };
   auto after = [&](int k, int j) -> int { return par ? nav_after(ctx, k, j) : B2_OK; };
   RET(after(1, 0)); RET(after(2, 0));   // fork
   {  // branch 2 first: pressure gradient terms, Helmholtz-y of pres and of d/dy pres
     on(2);
     Prog y;
-    y.load(nv->pres->vhat->d, byo.rows_ortho); emit_hh_axis(y, nv->hh[0], 1); y.store(nv->PH, nv->sp_vel->b[1].m, ST_TRANS);
-    y.load(nv->pres->vhat->d, byo.rows_ortho); y.deriv_axis(byo, 1, sy); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->PHy, nv->sp_vel->b[1].m, ST_TRANS);
+    // (the factor -dt of the pressure-gradient terms rides on the transposing stores: the consumers' loads stay zero-copy)
+    y.load(nv->pres->vhat->d, byo.rows_ortho); emit_hh_axis(y, nv->hh[0], 1); y.store(nv->PH, nv->sp_vel->b[1].m, ST_TRANS, -dt);
+    y.load(nv->pres->vhat->d, byo.rows_ortho); y.deriv_axis(byo, 1, sy); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->PHy, nv->sp_vel->b[1].m, ST_TRANS, -dt);
     RET(run_pass(so, 0, y));
   }
   // ---- A: along y on the three advected fields: values, d/dy values, Helmholtz-y of the old field ----
@@ -1593,13 +1669,13 @@ static int nav_update_fused(b2_navier* nv) {
     x.load(nv->uyT, l, 1.0, LD_MUL);
     x.load(nv->cv[i], l, 1.0, LD_ACC);
     l = x.forward_ortho(bxo); x.zerotail(cut0);
-    x.store(nv->Cx[i], l, ST_TRANS);
+    x.store(nv->Cx[i], l, ST_TRANS, -dt);   // rhs -= dt * conv: the factor rides on the store
     RET(run_pass(so, 1, x));
   }
   // ---- C-y: forward along y, dealias columns, -dt, Helmholtz-y ----
   for (int i = 0; i < 3; i++) {
     on(i);
-    Prog y; y.load(nv->Cx[i], byo.rows_phys, -dt); y.forward_ortho(byo); y.zerotail(cut1);
+    Prog y; y.load(nv->Cx[i], byo.rows_phys); y.forward_ortho(byo); y.zerotail(cut1);
     emit_hh_axis(y, nv->hh[i], 1); y.store(nv->Zf[i], fld[i]->sp->b[1].m, ST_TRANS);
     RET(run_pass(so, 0, y));
   }
@@ -1609,7 +1685,7 @@ static int nav_update_fused(b2_navier* nv) {
     const Base1& bxv = nv->sp_vel->b[0]; const Base1& bxT = nv->sp_temp->b[0];
     on(0);
     Prog x;  // velx
-    x.load(nv->PH, bxo.rows_ortho, -dt); x.deriv_axis(bxo, 1, sx);
+    x.load(nv->PH, bxo.rows_ortho); x.deriv_axis(bxo, 1, sx);
     x.load(nv->Zf[0], bxo.rows_ortho, 1.0, LD_ACC);
     x.load_stencil(nv->V1[0], bxv, 1.0, true);
     emit_hh_axis(x, nv->hh[0], 0);
@@ -1617,7 +1693,7 @@ static int nav_update_fused(b2_navier* nv) {
     RET(run_pass(so, 1, x));
     on(1);
     Prog v;  // vely (+ buoyancy dt * (to_ortho(temp) + to_ortho(tempbc)))
-    v.load(nv->PHy, bxo.rows_ortho, -dt);
+    v.load(nv->PHy, bxo.rows_ortho);
     v.load(nv->Zf[1], bxo.rows_ortho, 1.0, LD_ACC);
     v.load_stencil(nv->V1[1], bxv, 1.0, true);
     v.load_stencil(nv->VTv, bxT, dt, true);
@@ -1815,8 +1891,8 @@ int b2_navier_update(b2_navier* nv, int nsteps) {
 int b2_navier_div_norm(b2_navier* nv, double* out) {
   RET(op_gradient(nv->sp_vel, nv->velx->vhat->d, 1, 0, nv->scale, nv->g1));
   RET(op_gradient(nv->sp_vel, nv->vely->vhat->d, 0, 1, nv->scale, nv->g1, 1.0, true));
-  RET(norm2_dev(nv->sp_ortho, nv->g1, out));   // multi-rank: local sum of squares; the host all-reduces
-  if (nv->ctx->nranks == 1) *out = std::sqrt(*out);
+  RET(norm2_dev(nv->sp_ortho, nv->g1, out, true));   // multi-rank: summed over the ranks on the device (peer heap)
+  *out = std::sqrt(*out);
   return B2_OK;
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
@@ -1833,7 +1909,7 @@ int b2_navier_info(const b2_navier* nv, long long* out) {
   const b2_solver* ps = nv->pois;
   out[0] = ps && ps->blocks; out[1] = nv->sp_ortho->P[0]; out[2] = nv->sp_ortho->P[1];
   out[3] = ps ? ps->m0 : 0; out[4] = ps ? ps->ce : 0; out[5] = ps ? ps->co : 0;
-  out[6] = nv->branches && nv->ctx->nranks == 1; out[7] = nv->launches_per_step;
+  out[6] = nv->branches && (nv->ctx->nranks == 1 || getenv("B2_NOBRANCH_MULTI") == nullptr); out[7] = nv->launches_per_step;
   return B2_OK;
 }
 int b2_navier_launch_count(const b2_navier* nv, long long* k) { *k = nv->launches_per_step; return B2_OK; }

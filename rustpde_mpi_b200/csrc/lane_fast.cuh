@@ -85,7 +85,8 @@ __device__ __forceinline__ void lane_fft_fast(double* __restrict__ W, int l, int
 // Chebyshev transform (see op_dct for the algorithm), N = 2*E*TPL.
 // ---------------------------------------------------------------------------------------------
 template <int E, int LN, int TPL>
-__device__ __noinline__ void dct_fast(const LaneOp& op, double* __restrict__ W, double* scratch) {
+__device__ __noinline__ void dct_fast(const LaneOp& op, double* __restrict__ W, double* scratch, unsigned long long* prof) {
+  PhaseClock pc(prof);
   constexpr int M = E * TPL, N = 2 * M, PS = POff<LN, TPL>::v, ES = EOff<LN, TPL>::v;
   const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
   const int mode = op.i1;
@@ -130,7 +131,9 @@ __device__ __noinline__ void dct_fast(const LaneOp& op, double* __restrict__ W, 
   }
   if (q0) w2[Lay<LN>::pix(M / 2)] = gmid;
   __syncthreads();
+  pc.mark(22);
   lane_fft_fast<E, LN, TPL>(W, l, q, tw);
+  pc.mark(23);
   // ---- post: Z (N reals) -> X (N+1), pairs (k, N-k), k = q + pi*TPL in [1, M-1] ----
   const double fs = (mode == 0) ? 1.0 / N : 0.5;
   const double sk = (mode == 0 && (q & 1)) ? -fs : fs;      // TPL and N are even: k, N-k and q have the same parity
@@ -149,6 +152,7 @@ __device__ __noinline__ void dct_fast(const LaneOp& op, double* __restrict__ W, 
     w[Lay<LN>::eix(M)] = w[Lay<LN>::eix(M)] * ((mode == 0 && (M & 1)) ? -fs : fs);
   }
   __syncthreads();
+  pc.mark(24);
 }
 
 // Real FFT (see op_rfft), n = 2*E*TPL.
@@ -356,6 +360,7 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
     if (t >= ty) v.y = 0.0;
     return v;
   };
+  PhaseClock pc(P.prof);
   // ---- forward elimination: y_p = b_p - fl_p y_{p-1} ----
   {
     double2 A = d2(1.0, 1.0), B = zero;
@@ -411,8 +416,10 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
         A = d2(-f.x * A.x, -f.y * A.y);
       }
     }
+    pc.mark(16);
     Aff1::V m; m.d[0] = A.x; m.d[1] = B.x; m.d[2] = A.y; m.d[3] = B.y;
     Aff1::S in = lane_scan_state<Aff1, false, LN>(m, TPL, scratch);
+    pc.mark(17);
     double2 y = d2(in.d[0], in.d[1]);   // y of the last pair before this chunk (the start state is 0)
     if (interior) {
 #pragma unroll
@@ -430,6 +437,7 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
       }
     }
   }
+  pc.mark(18);
   // every thread only touched its own chunk: no barrier needed before the back substitution
   // ---- back substitution: x_p = (y_p - u1_p x_{p+1} - u2_p x_{p+2}) id_p ----
   {
@@ -451,7 +459,9 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
 #pragma unroll
       for (int t = CP - 1; t >= 0; t--) compose(t, rdm(t));
     }
+    pc.mark(19);
     Aff2::S in = lane_scan_state<Aff2, true, LN>(m, TPL, scratch);
+    pc.mark(20);
     double2 s1 = d2(in.d[0], in.d[2]), s2 = d2(in.d[1], in.d[3]);   // x_{p+1}, x_{p+2} entering the chunk
     auto solve = [&](int t, double2 y) -> double2 {
       const double2 idv = ldg(cid + t * CS), u1 = ldg(cu1 + t * CS), u2 = nou2 ? zero : ldg(cu2 + t * CS);
@@ -468,6 +478,7 @@ __device__ __forceinline__ void fdma_fast_body(const LaneProg& P, const LaneOp& 
     }
   }
   __syncthreads();
+  pc.mark(21);
 }
 template <int E, int LN, int TPL>
 __device__ __noinline__ void fdma_fast(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int gl, int lb, void* scratch) {

@@ -31,9 +31,9 @@
 
 #define B2_MAXOPS 24
 #define B2_MAXPEERS 8
-#define B2_ST_SLOTS 3    // store-staging slots (3: one CTA barrier per chunk, see store_staged)
-#define B2_MAXLD 8       // max load-ring slots
-#define B2_SCRATCH 16384 // bytes of scan scratch (32 warps x 4 lanes x (Aff2 map + state))
+#define B2_MAXPST 6     // transposing stores per program that can go to peer GPUs through tensor maps
+#define B2_BARBYTES 512  // mbarriers at the start of dynamic shared memory: dfull + 2 per warp
+#define B2_SCRATCH 8192  // bytes of scan scratch (16 warps x 4 lanes x (Aff2 map + state))
 #define B2_PROGCOPY 2048 // shared-memory copy of the program header + ops (everything of LaneProg in front of tm[])
 
 enum LaneOpCode {
@@ -53,7 +53,7 @@ enum LaneOpCode {
   OP_PREBAND = 14, // an OP_BAND folded into the OP_FDMA that follows it (set by the launcher, fast geometry only): no-op here
 };
 enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
-       LD_TMA = 16,          // set by the launcher: the slab streams through the TMA ring (tensor map tm[op])
+       LD_TMA = 16,          // set by the launcher: the slab streams through the warps' staging slots (load_warps)
        LD_AFTER_STORE = 32,  // set by the launcher: the source was stored earlier in this program (flush stores first)
        LD_DIRECT = 64,       // set by the launcher: zero-copy TMA straight into W (plain load, a == 1)
        LD_PSPLIT = 128,      // plain sources: rows are stored parity-split (row r < i1 lives at r/2, odd rows after the even ones)
@@ -87,21 +87,39 @@ struct LaneProg {
   int rank;       // this GPU's rank (peer table index)
   int LN;         // lanes per CTA: 4 (a whole lane group) or 2 (half a group; grid = 2 x groups)
   int NT;         // threads per CTA = LN*TPL (multiple of 32)
-  // TMA pipeline geometry
-  int CH, nch, NS, NP;        // chunk pool: tiles per chunk, chunks per lane; NP = 3 + NS slots of CH+1 tiles (one halo tile in front):
-                              // slots 0..2 stage stores, slots 3.. take look-ahead loads, a load op in progress uses all NP
+  // copy-pipeline geometry
+  int CHW, nsc;               // per-warp sub-chunks: tiles per sub-chunk, sub-chunks per lane (warp w takes w, w + nwarps, ...)
+  int wslot_bytes;            // pitch of a warp's staging slot: (CHW + 1) tiles (one halo tile in front), multiple of 128
   int CHD, nchd;              // direct copies: tiles per box (<= 256), boxes per lane
-  int ld_bytes, st_bytes;     // slot pitch of the load ring / the store staging (multiples of 128)
-  int ld_tx;                  // bytes one ring box delivers ((CH+1) tiles x LN lanes x 32)
-  int w_off, ld_off, st_off;  // byte offsets inside dynamic shared memory (128-aligned)
-  int dsplit;                 // direct loads: tiles [0, dsplit) come by TMA, tiles [dsplit, in_tiles) by per-thread LDG at the same time
-  int l2pf;                   // number of load operands prefetched into L2 ahead of their op (0 = off)
+  int w_off, st_off;          // byte offsets inside dynamic shared memory (128-aligned)
   int bulk1d;                 // LN == 4: the slab is contiguous, so slab-shaped copies are plain 1-D bulk copies (no tensor map)
   unsigned long long* prof;   // optional per-op cycle counters (64 entries), null in production
   LaneOp ops[B2_MAXOPS];
   B2TMap tm[B2_MAXOPS];       // tensor map of op i (3-D slab view, or 4-D transposed view for transposing stores)
+  B2TMap tmp[B2_MAXPST][B2_MAXPEERS];   // multi-GPU transposing store k (op.i1 = k): the transposed view of the destination in every owner's slab
 };
 
+// sub-phase cycle marks of the per-op profiler (thread 0; slots 16..31 of LaneProg::prof, counts at +32): only active
+// while b2_ctx_opprof is on
+__device__ __forceinline__ long long b2_clock() {
+#if defined(__CUDA_ARCH__) || defined(B2_EMU)
+  return clock64();
+#else
+  return 0;
+#endif
+}
+struct PhaseClock {
+  unsigned long long* prof; long long t;
+  __device__ __forceinline__ explicit PhaseClock(unsigned long long* p) : prof(p), t(p ? b2_clock() : 0) {}
+  __device__ __forceinline__ void mark(int slot) {
+    if (prof && threadIdx.x == 0) {
+      const long long n = b2_clock();
+      atomicAdd(prof + slot, (unsigned long long)(n - t));
+      atomicAdd(prof + 32 + slot, 1ull);
+      t = n;
+    }
+  }
+};
 #ifdef B2_EMU
 template <class T> static inline T ldg(const T* p) { return *p; }
 #else
@@ -289,7 +307,7 @@ struct Aff2 {
 // SUFFIX: q' > q, highest applied first) applied to the zero state.  Threads of a lane sit LN apart in a warp
 // (32/LN of them per warp); warp totals go through shared memory and ONE thread per lane runs the short
 // serial recurrence over the warps (vector recurrence only -- no matrix products on the critical path).
-// scratch: >= 32 warps * LN lanes * (V + S).  All threads of the CTA must call.
+// scratch: >= 16 warps * LN lanes * (V + S).  All threads of the CTA must call.
 template <class M, bool SUFFIX, int LN>
 __device__ __forceinline__ typename M::S lane_scan_state(typename M::V mine, int TPL, void* scratch) {
   typedef typename M::V V;
@@ -312,7 +330,7 @@ __device__ __forceinline__ typename M::S lane_scan_state(typename M::V mine, int
   if (TPL <= QW) return M::apply(exc, M::zero());
   const int nw = TPL / QW, w = tid >> 5;
   V* tot = reinterpret_cast<V*>(scratch);                  // [warp][lane] warp totals
-  S* ent = reinterpret_cast<S*>(tot + 32 * LN);            // [warp][lane] state entering the warp
+  S* ent = reinterpret_cast<S*>(tot + 16 * LN);            // [warp][lane] state entering the warp
   if (SUFFIX ? (qi == 0) : (qi == QW - 1)) tot[w * LN + l] = inc;
   __syncthreads();
   if (tid < LN) {
@@ -344,96 +362,51 @@ __device__ __forceinline__ double lane_sum(double v, int TPL, double* scratch) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared memory: [mbarriers 256 B][scan scratch][W = LN lanes, slab layout][load ring][store staging]
-//   full[s] / empty[s] : load-ring slot s filled by the copy engine / drained by all warps
-//   dfull              : a direct (zero-copy) load has landed in W
-// Thread 0 is the producer: it walks the program's ring loads with a prefetch cursor and keeps the ring
-// full -- NS chunks are requested before the first op runs, and every drained chunk immediately requests
-// the next one, across op boundaries (the first chunks of the next operand arrive while the warps are still
-// transforming the current one).  Stores leave through bulk tensor stores (async-group completion), so no
-// warp ever waits for DRAM on the way out.
+// Shared memory: [mbarriers 512 B][program copy][scan scratch][W = LN lanes, slab layout][per-warp staging]
+//   dfull          : a direct (zero-copy) load has landed in W
+//   wbar[warp][s]  : sub-chunk slot s of a warp has been filled by the copy engine (combining loads)
+// Every warp owns two staging slots of CHW (+1 halo) tiles and runs its OWN copy pipeline: the lane is cut into
+// sub-chunks of CHW tiles, warp w takes sub-chunks w, w + nwarps, ...; lane 0 of the warp issues the bulk copies
+// (async-group / mbarrier accounting is per thread), the other lanes only see __syncwarp.  16 independent pipelines keep
+// ~80 KB in flight per SM without a single CTA barrier inside a load or a store (measured: the CTA-wide chunk loop
+// with one issuing thread spent as long in its per-chunk barriers and slot waits as in the copies themselves).
 // ---------------------------------------------------------------------------------------------
 struct SmemView {
-  uint64_t* full; uint64_t* empty; uint64_t* dfull;
-  void* scratch; double* W; char* ld; char* st;
+  uint64_t* dfull; uint64_t* wbar;
+  void* scratch; double* W; char* st;
 };
 __device__ __forceinline__ SmemView smem_view(const LaneProg& P, char* base) {
   SmemView v;
-  v.full = reinterpret_cast<uint64_t*>(base); v.empty = v.full + B2_MAXLD; v.dfull = v.full + 2 * B2_MAXLD;
-  v.scratch = base + 256 + B2_PROGCOPY; v.W = reinterpret_cast<double*>(base + P.w_off); v.ld = base + P.ld_off; v.st = base + P.st_off;
+  v.dfull = reinterpret_cast<uint64_t*>(base); v.wbar = v.dfull + 2;
+  v.scratch = base + B2_BARBYTES + B2_PROGCOPY; v.W = reinterpret_cast<double*>(base + P.w_off); v.st = base + P.st_off;
   return v;
 }
-struct Prefetch {             // producer state (thread 0) + the phase of the direct-load barrier (everyone)
-  int op, c, slot, gl, lb;    // cursor: next chunk (op, c) to request and its slot; this CTA's lane group / first lane
-  const B2TMap* tms;          // the tensor maps stay in parameter space (the program itself is read from its shared-memory copy)
-  unsigned pph, out;          // per-slot parity of the next request; slots whose chunk thread 0 has not consumed yet
-  unsigned dphase;
+struct Prefetch {             // per-thread pipeline state
+  int gl, lb;                 // this CTA's lane group / first lane
+  unsigned dphase;            // parity of the direct-load barrier
+  unsigned wph;               // parities of this warp's two slot barriers (bits 0, 1)
+  int ws;                     // the staging slot this warp's next store sub-chunk goes to (slots alternate across ops as well)
 };
-__device__ __forceinline__ int next_ring_load(const LaneProg& P, int o) {
-  while (o < P.nops && !(P.ops[o].code == OP_LOAD && (P.ops[o].i2 & LD_TMA))) o++;
-  return o;
-}
-// L2 prefetch of the slab of the n-th tiled load op after op o (thread 0): the copy engine pulls the operand into L2 while
-// the warps are still working on the current one, so that the load itself runs at L2 latency instead of DRAM latency.
-__device__ __forceinline__ void prefetch_loads_l2(const LaneProg& P, int o, int nth, int gl) {
-  if (!P.bulk1d || !P.l2pf) return;
-  for (int k = o + 1; k < P.nops; k++) {
-    const LaneOp& op = P.ops[k];
-    if (op.code != OP_LOAD || (op.i2 & (LD_PLAIN | LD_AFTER_STORE))) continue;
-    if (--nth > 0) continue;
-    const char* src = static_cast<const char*>(op.p0) + (size_t)gl * P.in_tiles * 128;
-    const uint32_t bytes = (uint32_t)P.in_tiles * 128u;
-    for (uint32_t b = 0; b < bytes; b += 32768u) bulk_prefetch_l2(src + b, min(32768u, bytes - b));
-    return;
-  }
-}
-__device__ __forceinline__ int slot_next(int slot, int NP) { return slot + 1 == NP ? 0 : slot + 1; }   // chunk c lives in slot (3 + c) mod NP
-// Request the next chunk of the program if its slot is free (thread 0).  Chunk c of a load goes to slot
-// (3 + c) mod NP.  Ahead of its own op (cur_op) a load may only use the look-ahead slots 3.. (its first NS
-// chunks), because slots 0..2 stage the stores of the ops in between; inside its op it uses the whole pool.
-// A load flagged LD_AFTER_STORE re-reads an array this CTA stored earlier in the program and is never
-// requested ahead of its op.
-__device__ __forceinline__ bool prefetch_next(const LaneProg& P, const SmemView& sv, Prefetch& pf, int cur_op) {
-  if (pf.op >= P.nops) return false;
-  if (pf.op != cur_op && ((P.ops[pf.op].i2 & LD_AFTER_STORE) || pf.c >= P.NS)) return false;
-  const int slot = pf.slot;
-  if (pf.out & (1u << slot)) return false;          // its previous chunk is still waiting for this very thread
-  if (slot < 3) bulk_wait_read<0>();                // a store may still be reading this staging slot
-  mbar_wait(&sv.empty[slot], ((pf.pph >> slot) & 1u) ^ 1u);   // every warp has released the previous chunk
-  char* dst = sv.ld + (size_t)slot * P.ld_bytes;
-  if (P.bulk1d) {   // contiguous slab: tiles [J0-1, J0+CH) clipped to the lane, no halo in front of the first chunk
-    const int J0 = pf.c * P.CH, t0 = J0 > 0 ? J0 - 1 : 0, t1 = min(J0 + P.CH, P.in_tiles);
-    const uint32_t bytes = (uint32_t)(t1 - t0) * 128u;
-    mbar_arrive_expect_tx(&sv.full[slot], bytes);
-    bulk_load_1d(dst + (size_t)(t0 - (J0 - 1)) * 128,
-                 static_cast<const char*>(P.ops[pf.op].p0) + ((size_t)pf.gl * P.in_tiles + t0) * 128, bytes, &sv.full[slot]);
-  } else {
-    mbar_arrive_expect_tx(&sv.full[slot], (uint32_t)P.ld_tx);
-    tma_load_3d(dst, pf.tms + pf.op, pf.lb * 4, pf.c * P.CH - 1, pf.gl, &sv.full[slot]);
-  }
-  pf.pph ^= 1u << slot; pf.out |= 1u << slot;
-  pf.slot = slot_next(slot, P.NP);
-  if (++pf.c == P.nch) { pf.c = 0; pf.slot = 3; pf.op = next_ring_load(P, pf.op + 1); }
-  return true;
+
+// every thread that issues bulk stores waits for its own groups (whole CTA must call)
+__device__ __forceinline__ void wait_all_stores_complete() {
+  if ((threadIdx.x & 31) == 0) bulk_wait<0>();
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
 // loads
 // ---------------------------------------------------------------------------------------------
 // W = src: the slab lands in W as it is (zero-copy); elements at and beyond len are cleared afterwards.
-// The copy engine alone keeps only a few tens of KB in flight per SM, so the tail of the slab (tiles >= dsplit)
-// is fetched by the threads at the same time (16-byte LDGs, 8 in flight each): both streams overlap.
 template <int LN>
 __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, Prefetch& pf) {
-  constexpr int LSH = Lay<LN>::LSH;
-  const int T1 = P.dsplit;   // multiple of CHD or == in_tiles
+  if (op.i2 & LD_AFTER_STORE) wait_all_stores_complete();   // the source was stored by this CTA earlier in the program
   if (threadIdx.x == 0) {
-    if (op.i2 & LD_AFTER_STORE) bulk_wait<0>();
     if (P.bulk1d) {
       const char* src = static_cast<const char*>(op.p0) + (size_t)pf.gl * P.in_tiles * 128;
-      mbar_arrive_expect_tx(sv.dfull, (uint32_t)T1 * 128u);
-      for (int t0 = 0; t0 < T1; t0 += P.CHD) {
-        const int t1 = min(t0 + P.CHD, T1);
+      mbar_arrive_expect_tx(sv.dfull, (uint32_t)P.in_tiles * 128u);
+      for (int t0 = 0; t0 < P.in_tiles; t0 += P.CHD) {
+        const int t1 = min(t0 + P.CHD, P.in_tiles);
         bulk_load_1d(reinterpret_cast<char*>(sv.W) + (size_t)t0 * 128, src + (size_t)t0 * 128, (uint32_t)(t1 - t0) * 128u, sv.dfull);
       }
     } else {
@@ -442,24 +415,9 @@ __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, co
         tma_load_3d(reinterpret_cast<char*>(sv.W) + (size_t)c * P.CHD * LN * 32, tm, pf.lb * 4, c * P.CHD, pf.gl, sv.dfull);
     }
   }
-  if (P.bulk1d && T1 < P.in_tiles) {
-    if ((op.i2 & LD_AFTER_STORE) && T1 == 0) { if (threadIdx.x == 0) bulk_wait<0>(); __syncthreads(); }
-    const double2* src = reinterpret_cast<const double2*>(op.p0) + (size_t)pf.gl * P.in_tiles * 8;
-    double2* W2 = reinterpret_cast<double2*>(sv.W);
-    const int npc = P.in_tiles << LSH;
-    constexpr int U = 8;
-    for (int p0 = (T1 << LSH) + threadIdx.x; p0 < npc; p0 += U * P.NT) {
-      double2 v[U];
-#pragma unroll
-      for (int k = 0; k < U; k++) { const int pc = p0 + k * P.NT; v[k] = (pc < npc) ? src[pc] : make_double2(0.0, 0.0); }
-#pragma unroll
-      for (int k = 0; k < U; k++) { const int pc = p0 + k * P.NT; if (pc < npc) W2[pc] = v[k]; }
-    }
-  }
-  if (!P.bulk1d || T1 > 0) mbar_wait(sv.dfull, pf.dphase);
-  if (!P.bulk1d || T1 > 0) pf.dphase ^= 1u;
+  mbar_wait(sv.dfull, pf.dphase);
+  pf.dphase ^= 1u;
   const int len = op.i0, ntail = P.LP - len;
-  if (P.bulk1d && T1 < P.in_tiles) __syncthreads();   // the threads' share has to be complete before the tail is cleared
   for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
     const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
     sv.W[4 * l + Lay<LN>::eix(e)] = 0.0;
@@ -467,33 +425,48 @@ __device__ __noinline__ void load_direct(const LaneProg& P, const LaneOp& op, co
   __syncthreads();
 }
 
-// W = [W +|*] a * src, src arriving through the ring.  Slot layout: [tile t = 0..CH][lane][4] -- the slab's own
-// layout, so the combine is elementwise; t = 0 is the halo tile in front of the chunk (the composite ->
-// orthonormal stencil needs element j-2 of the same lane).
+// W = [W +|*] a * src (tiled source, same orientation), optionally with the composite -> orthonormal stencil applied on
+// the way in (value_j = src_j + p1_j * src_{j-2}).  Per-warp pipeline: sub-chunk slot layout [tile t = 0..CHW][lane][4],
+// t = 0 being the halo tile in front of the sub-chunk (the stencil reaches two elements back).
 template <int LN>
-__device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int o, const SmemView& sv, unsigned& cph, Prefetch& pf) {
+__device__ __noinline__ void load_warps(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, Prefetch& pf) {
   constexpr int LSH = Lay<LN>::LSH;
-  const int NT = P.NT, len = op.i0;
+  const int len = op.i0, in_tiles = P.in_tiles, CHW = P.CHW, nsc = P.nsc, nw = P.NT >> 5;
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
   const double a = op.a;
   const bool acc = op.i2 & LD_ACC, mul = op.i2 & LD_MUL, sten = op.i2 & LD_STENCIL;
   const double* sc = reinterpret_cast<const double*>(op.p1);
   double2* W2 = reinterpret_cast<double2*>(sv.W);
-  if (threadIdx.x == 0) {
-    if (op.i2 & LD_AFTER_STORE) bulk_wait<0>();   // the stored data must have landed before it is read back
-    while (prefetch_next(P, sv, pf, o)) {}         // inside its own op a load may fill the whole pool
-  }
-  const int CH = P.CH, nch = P.nch, NP = P.NP, ld_bytes = P.ld_bytes, in_tiles = P.in_tiles;
-  const int npc = CH << LSH;
-  int slot = 3;
-  for (int c = 0; c < nch; c++, slot = slot_next(slot, NP)) {
-    mbar_wait(&sv.full[slot], (cph >> slot) & 1u);
-    cph ^= 1u << slot;
-    const double2* st = reinterpret_cast<const double2*>(sv.ld + (size_t)slot * ld_bytes) + (1 << LSH);
-    const int J0 = c * CH;
-#pragma unroll 2
-    for (int pc = threadIdx.x; pc < npc; pc += NT) {
+  char* slot0 = sv.st + (size_t)w * 2 * P.wslot_bytes;
+  uint64_t* bar = sv.wbar + 2 * w;
+  if (op.i2 & LD_AFTER_STORE) wait_all_stores_complete();
+  else if (ln == 0) bulk_wait_read<0>();   // this warp's earlier stores may still be reading the slots
+  auto request = [&](int c, int s) {       // lane 0: sub-chunk c -> slot s
+    const int J0 = c * CHW;
+    char* dst = slot0 + (size_t)s * P.wslot_bytes;
+    if (P.bulk1d) {   // contiguous slab: tiles [J0-1, J0+CHW) clipped to the lane
+      const int t0 = J0 > 0 ? J0 - 1 : 0, t1 = min(J0 + CHW, in_tiles);
+      const uint32_t bytes = (uint32_t)(t1 - t0) * 128u;
+      mbar_arrive_expect_tx(bar + s, bytes);
+      bulk_load_1d(dst + (size_t)(t0 - (J0 - 1)) * 128, static_cast<const char*>(op.p0) + ((size_t)pf.gl * in_tiles + t0) * 128, bytes, bar + s);
+    } else {
+      mbar_arrive_expect_tx(bar + s, (uint32_t)((CHW + 1) * LN * 32));
+      tma_load_3d(dst, tm, pf.lb * 4, J0 - 1, pf.gl, bar + s);
+    }
+  };
+  __syncwarp();
+  if (ln == 0) { if (w < nsc) request(w, 0); if (w + nw < nsc) request(w + nw, 1); }
+  const int npc = CHW << LSH;
+  int s = 0;
+  for (int c = w; c < nsc; c += nw, s ^= 1) {
+    mbar_wait(bar + s, (pf.wph >> s) & 1u);
+    pf.wph ^= 1u << s;
+    const double2* st = reinterpret_cast<const double2*>(slot0 + (size_t)s * P.wslot_bytes) + (1 << LSH);
+    const int J0 = c * CHW;
+#pragma unroll 3
+    for (int pc = ln; pc < npc; pc += 32) {
       const int J = J0 + (pc >> LSH), j0 = 4 * J + 2 * (pc & 1);
-      if (J >= in_tiles) continue;
+      if (J >= in_tiles) break;
       double2 v = st[pc];
       if (sten && j0 >= 2) {
         const double2 u = (pc & 1) ? st[pc - 1] : st[pc - (1 << LSH) + 1];
@@ -502,14 +475,13 @@ __device__ __noinline__ void load_ring(const LaneProg& P, const LaneOp& op, int 
       }
       v.x = (j0 < len) ? v.x * a : 0.0;
       v.y = (j0 + 1 < len) ? v.y * a : 0.0;
-      double2* w = W2 + ((size_t)J0 << LSH) + pc;
-      if (acc) { const double2 ov = *w; v.x += ov.x; v.y += ov.y; }
-      else if (mul) { const double2 ov = *w; v.x *= ov.x; v.y *= ov.y; }
-      *w = v;
+      double2* wp = W2 + ((size_t)J0 << LSH) + pc;
+      if (acc) { const double2 ov = *wp; v.x += ov.x; v.y += ov.y; }
+      else if (mul) { const double2 ov = *wp; v.x *= ov.x; v.y *= ov.y; }
+      *wp = v;
     }
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&sv.empty[slot]);
-    if (threadIdx.x == 0) { pf.out &= ~(1u << slot); while (prefetch_next(P, sv, pf, o)) {} }
+    if (ln == 0 && c + 2 * nw < nsc) request(c + 2 * nw, s);
   }
   __syncthreads();
 }
@@ -527,10 +499,7 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
   const double* sc = reinterpret_cast<const double*>(op.p1);
   double2* W2 = reinterpret_cast<double2*>(sv.W);
   const int psplit = (op.i2 & LD_PSPLIT) ? op.i1 : 0;   // rows < psplit of a plain source are stored parity-split
-  if (op.i2 & LD_AFTER_STORE) {   // the source was written by this CTA's bulk stores: wait until they have completed
-    if (threadIdx.x == 0) bulk_wait<0>();
-    __syncthreads();
-  }
+  if (op.i2 & LD_AFTER_STORE) wait_all_stores_complete();   // the source was written by this CTA's bulk stores
   for (int p0 = threadIdx.x; p0 < npieces; p0 += U * T) {
     double2 v[U], u[U];
 #pragma unroll
@@ -601,31 +570,31 @@ __device__ __noinline__ void store_direct(const LaneProg& P, const LaneOp& op, c
   __syncthreads();
 }
 
-// dst = [dst +] a * W through the staging slots and bulk tensor stores / reductions.  Slot k % 3 is rewritten
-// while the stores of chunks k-1 and k-2 may still be reading theirs: thread 0 waits (before the barrier of
-// chunk k) until at most one group is unread, i.e. chunk k-2 and older are done, which frees slot (k+1) % 3 for
-// everyone who passes that barrier -- one CTA barrier per chunk.
+// dst = [dst +] a * W through the warps' staging slots and bulk tensor stores / reductions.  Transposing stores transpose
+// each 4x4 tile on its way into the slot ([tile][jl][lane]) and leave as ONE 4-D tensor store per sub-chunk: full 128-byte
+// lines into the transposed array -- with several GPUs into the slab of the rank that owns those rows (the pencil
+// transpose), one tensor map per owner, sub-chunks that straddle two owners stored twice and clipped by the copy engine.
 template <int LN>
-__device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv,
-                                          int g, int gl, int lb, int& st_it) {
+__device__ __noinline__ void store_warps(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, int g, int gl, int lb, Prefetch& pf) {
   constexpr int LSH = Lay<LN>::LSH, HL = LN / 2;
-  const int NT = P.NT, len = op.i0, flags = op.i2;
+  const int len = op.i0, flags = op.i2, in_tiles = P.in_tiles, CHW = P.CHW, nsc = P.nsc, nw = P.NT >> 5;
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
   const double a = op.a;
   const double* W = sv.W;
   const double2* W2 = reinterpret_cast<const double2*>(sv.W);
-  const int CH = P.CH, nch = P.nch, st_bytes = P.st_bytes, in_tiles = P.in_tiles;
-  const bool bulk1d = P.bulk1d;
-  const int npc = CH << LSH;
-  for (int c = 0; c < nch; c++, st_it = (st_it + 1 == B2_ST_SLOTS ? 0 : st_it + 1)) {
-    double2* st = reinterpret_cast<double2*>(sv.st + (size_t)st_it * st_bytes);
-    const int J0 = c * CH;
-    if (threadIdx.x == 0) bulk_wait_read<B2_ST_SLOTS - 2>();
+  char* slot0 = sv.st + (size_t)w * 2 * P.wslot_bytes;
+  const int npc = CHW << LSH;
+  int s = pf.ws;
+  for (int c = w; c < nsc; c += nw, s ^= 1) {
+    double2* st = reinterpret_cast<double2*>(slot0 + (size_t)s * P.wslot_bytes);
+    const int J0 = c * CHW;
+    if (ln == 0) bulk_wait_read<1>();   // only the store of the OTHER slot may still be reading (slots alternate, across ops too)
+    __syncwarp();
     if (flags & ST_TRANS) {
-      // slot layout [tile][jl][lane]: each 4x4 tile transposed.  Piece (tile, jl, lane pair lp) = elements
-      // (2lp, jl), (2lp+1, jl); odd tiles read the two in the opposite order so that the 16 threads of a
-      // half-warp touch 16 different 8-byte banks.
-#pragma unroll 2
-      for (int pc = threadIdx.x; pc < npc; pc += NT) {
+      // piece (tile, jl, lane pair lp) = elements (2lp, jl), (2lp+1, jl); odd tiles read the two in the opposite order so
+      // that the 16 threads of a half-warp touch 16 different 8-byte banks
+#pragma unroll 3
+      for (int pc = ln; pc < npc; pc += 32) {
         const int lp = pc & (HL - 1), jl = (pc / HL) & 3, tt = pc >> LSH;
         const int j = 4 * (J0 + tt) + jl, sw = tt & 1;
         double2 v = make_double2(0.0, 0.0);
@@ -637,25 +606,30 @@ __device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, c
         st[pc] = v;
       }
     } else {                  // slot layout [tile][lane][4]: the slab itself
-#pragma unroll 2
-      for (int pc = threadIdx.x; pc < npc; pc += NT) {
+#pragma unroll 3
+      for (int pc = ln; pc < npc; pc += 32) {
         const int j0 = 4 * (J0 + (pc >> LSH)) + 2 * (pc & 1);
         double2 v = make_double2(0.0, 0.0);
         if (j0 < len) {
-          const double2 w = W2[((size_t)J0 << LSH) + pc];
-          v.x = a * w.x; v.y = (j0 + 1 < len) ? a * w.y : 0.0;
+          const double2 wv = W2[((size_t)J0 << LSH) + pc];
+          v.x = a * wv.x; v.y = (j0 + 1 < len) ? a * wv.y : 0.0;
         }
         st[pc] = v;
       }
     }
     fence_proxy_async();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (flags & ST_TRANS) {
+    __syncwarp();
+    if (ln == 0) {
+      if ((flags & ST_TRANS) && (flags & ST_PEER)) {
+        const int gpr = P.groups_per_rank, Jl = min(J0 + CHW, in_tiles) - 1;
+        for (int o = J0 / gpr; o <= Jl / gpr; o++) {
+          if (flags & ST_ACC) tma_reduce_add_4d(tm + o, lb, 0, g, J0 - o * gpr, st); else tma_store_4d(tm + o, lb, 0, g, J0 - o * gpr, st);
+        }
+      } else if (flags & ST_TRANS) {
         if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);
-      } else if (bulk1d) {
+      } else if (P.bulk1d) {
         char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + ((size_t)gl * in_tiles + J0) * 128;
-        const uint32_t bytes = (uint32_t)(min(J0 + CH, in_tiles) - J0) * 128u;
+        const uint32_t bytes = (uint32_t)(min(J0 + CHW, in_tiles) - J0) * 128u;
         if (flags & ST_ACC) bulk_reduce_add_1d(dst, st, bytes); else bulk_store_1d(dst, st, bytes);
       } else {
         if (flags & ST_ACC) tma_reduce_add_3d(tm, lb * 4, J0, gl, st); else tma_store_3d(tm, lb * 4, J0, gl, st);
@@ -663,6 +637,8 @@ __device__ __noinline__ void store_staged(const LaneProg& P, const LaneOp& op, c
       bulk_commit();
     }
   }
+  pf.ws = s;
+  __syncthreads();   // every warp has read its part of W
 }
 
 // Per-thread path: row-major "plain" destinations (GEMM operands), peer GPUs' slabs, TMA switched off.
@@ -1110,7 +1086,7 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
 // then run their compile-time-geometry versions of lane_fast.cuh), 0 = generic geometry read from the program.
 template <int E, int LN, int TPLC>
 #ifndef B2_LB
-#define B2_LB __launch_bounds__((LN * TPLC > 512) ? 1024 : 512)
+#define B2_LB __launch_bounds__(512)
 #endif
 __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
   B2_DYN_SMEM(char, smem_raw);
@@ -1120,46 +1096,43 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
   static_assert(offsetof(LaneProg, tm) <= B2_PROGCOPY, "program copy area too small");
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&Pp);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + 256);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + B2_BARBYTES);
     for (int i = threadIdx.x; i < (int)(offsetof(LaneProg, tm) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const LaneProg& P = *reinterpret_cast<const LaneProg*>(smem_raw + 256);
+  const LaneProg& P = *reinterpret_cast<const LaneProg*>(smem_raw + B2_BARBYTES);
   const SmemView sv = smem_view(P, smem_raw);
   double* W = sv.W;
   void* scratch = sv.scratch;
   const int gl = blockIdx.x / (4 / LN);   // local lane group (addresses this GPU's slab)
   const int g = P.group0 + gl;            // global lane group (mode indices, transposed stores)
   const int lb = (blockIdx.x & ((4 / LN) - 1)) * LN;
-  Prefetch pf; pf.c = 0; pf.slot = 3; pf.gl = gl; pf.lb = lb; pf.op = P.nops; pf.pph = 0; pf.out = 0; pf.dphase = 0; pf.tms = Pp.tm;
+  Prefetch pf; pf.gl = gl; pf.lb = lb; pf.dphase = 0; pf.wph = 0; pf.ws = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.NP; i++) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], P.NT / 32); }
     mbar_init(sv.dfull, 1);
+    for (int i = 0; i < 2 * (P.NT >> 5); i++) mbar_init(&sv.wbar[i], 1);
     mbar_fence_init();
     for (int o = 0; o < P.nops; o++)
-      if ((P.ops[o].code == OP_LOAD && (P.ops[o].i2 & (LD_TMA | LD_DIRECT))) || (P.ops[o].code == OP_STORE && (P.ops[o].i2 & (ST_TMA | ST_DIRECT))))
+      if ((P.ops[o].code == OP_LOAD && (P.ops[o].i2 & (LD_TMA | LD_DIRECT))) || (P.ops[o].code == OP_STORE && (P.ops[o].i2 & (ST_TMA | ST_DIRECT)) && !(P.ops[o].i2 & ST_PEER)))
         tmap_prefetch(&Pp.tm[o]);
-    pf.op = next_ring_load(P, 0);
-    while (prefetch_next(P, sv, pf, -1)) {}
-    for (int k = 2; k <= P.l2pf; k++) prefetch_loads_l2(P, -1, k, gl);   // the first load is issued right away
   }
   __syncthreads();
-  unsigned cph = 0;   // per-slot parity of the next chunk to consume
-  int st_it = 0;
   for (int o = 0; o < P.nops; o++) {
     const LaneOp& op = P.ops[o];
     long long t0 = 0;
     if (P.prof) t0 = clock64();
     switch (op.code) {
-      case OP_LOAD:
-        if (threadIdx.x == 0 && P.l2pf) prefetch_loads_l2(P, o, P.l2pf, gl);
+      case OP_LOAD: {
+        PhaseClock pc(P.prof);
         if (op.i2 & LD_DIRECT) load_direct<LN>(P, op, &Pp.tm[o], sv, pf);
-        else if (op.i2 & LD_TMA) load_ring<LN>(P, op, o, sv, cph, pf);
+        else if (op.i2 & LD_TMA) load_warps<LN>(P, op, &Pp.tm[o], sv, pf);
         else load_threads<LN, (E == 16 ? 8 : 4)>(P, op, sv, gl, lb);
+        pc.mark((op.i2 & LD_DIRECT) ? (o == 0 ? 27 : 28) : ((op.i2 & LD_PLAIN) ? 30 : ((op.i2 & LD_STENCIL) ? 31 : 29)));
+      }
         break;
       case OP_STORE:
         if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &Pp.tm[o], sv, gl, lb);
-        else if (op.i2 & ST_TMA) store_staged<LN>(P, op, &Pp.tm[o], sv, g, gl, lb, st_it);
+        else if (op.i2 & ST_TMA) store_warps<LN>(P, op, (op.i2 & ST_PEER) ? &Pp.tmp[op.i1][0] : &Pp.tm[o], sv, g, gl, lb, pf);
         else store_threads<LN>(P, op, sv, g, gl, lb);
         break;
       case OP_BAND:
@@ -1172,7 +1145,7 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
         if constexpr (TPLC > 0) fdma_fast<E, LN, TPLC>(P, op, W, gl, lb, scratch); else op_fdma<E + 1, LN>(P, op, W, gl, lb, scratch);
         break;
       case OP_DCT:
-        if constexpr (TPLC > 0) dct_fast<E, LN, TPLC>(op, W, (double*)scratch); else op_dct<E, LN>(P, op, W, (double*)scratch);
+        if constexpr (TPLC > 0) dct_fast<E, LN, TPLC>(op, W, (double*)scratch, P.prof); else op_dct<E, LN>(P, op, W, (double*)scratch);
         break;
       case OP_RFFT:
         if constexpr (TPLC > 0) rfft_fast<E, LN, TPLC>(P, op, W); else op_rfft<E, LN>(P, op, W);
@@ -1185,5 +1158,5 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
       atomicAdd(P.prof + 32 + op.code, 1ull);
     }
   }
-  if (threadIdx.x == 0) bulk_wait<0>();   // shared memory must outlive the bulk stores that read it
+  if ((threadIdx.x & 31) == 0) bulk_wait<0>();   // shared memory must outlive the bulk stores that read it (every issuing lane waits for its own)
 }

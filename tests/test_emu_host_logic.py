@@ -78,10 +78,10 @@ def test_emulated_host_logic(case):
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
 
 
-@pytest.mark.parametrize("env", [{"B2_RING": "1", "B2_CH": "5"},          # combining loads through the TMA ring, 4 chunks per lane
+@pytest.mark.parametrize("env", [{"B2_LDTHREADS": "1", "B2_CHW": "3"},     # combining loads on the per-thread path, 3-tile sub-chunks
                                  {"B2_NOTMA": "1", "B2_NOBLOCKS": "1"},   # per-thread loads/stores only, dense Poisson GEMMs
                                  {"B2_NOFAST": "1", "B2_NODIRECT": "1"}], # generic-geometry operators, staged (not zero-copy) plain copies
-                         ids=["ring", "threads-dense", "generic-staged"])
+                         ids=["ldthreads-smallchunks", "threads-dense", "generic-staged"])
 def test_emulated_path_variants(env):
     """The tuning switches select alternative implementations of the same operators; each must give the same step."""
     r = subprocess.run([sys.executable, "-c", SCRIPT, "variants"], capture_output=True, text=True, timeout=900, cwd=ROOT,

@@ -37,7 +37,7 @@ for v in variants:
         if prof:
             nav.set_mode(3); nav.update(1)
             ctx.opprof(True); nav.update(2); p = ctx.opprof(False)
-            line += "  | " + " ".join(f"{k}={c / n / 1e3:.1f}k" for k, (c, n) in sorted(p.items(), key=lambda kv: -kv[1][0])[:7])
+            line += "  | " + " ".join(f"{k}={c / n / 1e3:.1f}k" for k, (c, n) in sorted(p.items(), key=lambda kv: -kv[1][0]))
         print(line, flush=True)
         nav.close()
     except Exception as e:  # noqa: BLE001
