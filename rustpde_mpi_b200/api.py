@@ -116,7 +116,7 @@ class Context:
         buf = (C.c_ulonglong * 64)()
         check(lib().b2_ctx_opprof(self._h, int(on), buf))
         names = {1: "load", 2: "store", 3: "band", 4: "deriv", 5: "fdma", 6: "dct", 7: "rfft", 8: "fdiff", 9: "scalevec",
-                 10: "zerotail", 11: "lanemask", 12: "zeroelem", 13: "scale",
+                 10: "zerotail", 11: "lanemask", 12: "zeroelem", 13: "scale", 15: "bandc",
                  16: "fdma.fwd_reduce", 17: "fdma.scan1", 18: "fdma.fwd_apply", 19: "fdma.compose", 20: "fdma.scan2", 21: "fdma.solve",
                  22: "dct.pre", 23: "dct.fft", 24: "dct.post", 25: "st.fill", 26: "st.wait", 27: "ld.direct_first", 28: "ld.direct_later", 29: "ld.combine", 30: "ld.plain", 31: "ld.stencil"}
         return {names[c]: (buf[c], buf[32 + c]) for c in names if buf[32 + c]}

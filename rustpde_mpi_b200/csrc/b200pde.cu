@@ -6,6 +6,7 @@
 // src/field.rs:195-249 + src/solver/*.rs define them, (b) strings lane programs together and
 // (c) owns device memory.  There is NO CPU fallback: every entry point needs a CUDA device.
 #include "lane_kernel.cuh"
+#include "gemm_f64.cuh"
 #include "../../include/b200pde.h"
 
 #ifndef B2_EMU
@@ -212,7 +213,7 @@ struct Base1 {
   int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
   DVecD d_sten2, d_sten2s, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
-  DVecD d_s2_sc, d_bd_sc, d_bu1_sc, d_bu2_sc;   // scan-layout copies for band ops folded into an LU solve (see run_pass)
+  DVecD d_s2_sc, d_bd_sc, d_bu1_sc, d_bu2_sc, d_sten2s_sc;   // scan-layout copies for band ops folded into an LU solve (see run_pass)
 
   // B2 = laplace_inv; pv(i, off) = (laplace_inv_eye . laplace_inv)[i, i+off]
   double pv(int i, int off) const {
@@ -256,9 +257,9 @@ struct Base1 {
     return o;
   }
   void release() {
-    const void* keys[] = {d_bd.d, d_bu1.d, d_bu2.d, d_s2.d};
+    const void* keys[] = {d_bd.d, d_bu1.d, d_bu2.d, d_s2.d, d_sten2s.d};
     for (auto k : keys) if (k) scan_of().erase(k);
-    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc};
+    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc, &d_sten2s_sc};
     for (auto* v : all) v->release();
   }
 };
@@ -315,6 +316,7 @@ int Base1::init(int C, int TPL) {
     RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
     RET(d_bd_sc.upload(scan_layout(bd))); RET(d_bu1_sc.upload(scan_layout(bu1))); RET(d_bu2_sc.upload(scan_layout(bu2))); RET(d_s2_sc.upload(scan_layout(s2v)));
     scan_of()[d_bd.d] = d_bd_sc.d; scan_of()[d_bu1.d] = d_bu1_sc.d; scan_of()[d_bu2.d] = d_bu2_sc.d; scan_of()[d_s2.d] = d_s2_sc.d;
+    RET(d_sten2s_sc.upload(scan_layout(sten2))); scan_of()[d_sten2s.d] = d_sten2s_sc.d;
   }
   // transform tables (only when the size is one the FFT core handles)
   if (is_pow2(N) && N >= 64) {
@@ -359,6 +361,13 @@ struct b2_field {
   b2_array* vhat;
 };
 
+// One product of gemm_f64.cuh: the packed operand(s) and the launch geometry (B / C are bound at run time).
+struct GemmPlan {
+  DVecD A[2];
+  GemmParams p;
+  int grid = 0;
+};
+
 struct b2_solver {
   b2_space* sp = nullptr;
   int type = 0;  // 0 hholtz_adi, 1 poisson
@@ -376,6 +385,9 @@ struct b2_solver {
   DVecD fe, fo, be, bo;     // fwd_e (ce x ce), fwd_o (co x co), bwd_e, bwd_o, row-major
   DVecD qfl, qid, qu1, qu2; // per-lane LU for the parity-grouped mode order
   double* plain[2] = {nullptr, nullptr};
+  // own FP64 GEMM on the tiled arrays (gemm_f64.cuh): forward (x -> eigenmodes) and backward products
+  GemmPlan gf, gb;
+  bool own_gemm = false;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -549,13 +561,17 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
       if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
+      else if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_COLSPLIT)) { p.ops[i].p1 = ctx->d_peers; exchange = true; }
+  } else {
+    for (int i = 0; i < p.nops; i++) if (p.ops[i].code == OP_STORE) p.ops[i].i2 &= ~ST_COLSPLIT;   // one GPU: a plain same-orientation store
   }
   // A tiled load followed by the composite -> orthonormal stencil (to_ortho: y_j = x_j + s_j x_{j-2}) becomes ONE load that
   // applies the stencil on the fly (LD_STENCIL, per-thread 16-byte loads; the second operand x_{j-2} comes from the same
   // lines): measured on C4 a direct load costs 9.5k cycles per lane group, a combining load 10.6k and the banded pass
   // 7.1k, so the pair drops from 16.6k to ~10.6k.  B2_NOLDSTEN=1 keeps the two ops.
   static const bool ld_sten = getenv("B2_NOLDSTEN") == nullptr;
-  for (int i = 0; ld_sten && i + 1 < p.nops; i++) {
+  static const bool bandc = getenv("B2_NOBANDC") == nullptr;   // chunk-streaming band ops (band_chunk) on transform-sized lanes
+  for (int i = 0; ld_sten && !(c.fast && bandc) && i + 1 < p.nops; i++) {
     LaneOp& lo = p.ops[i]; LaneOp& bo = p.ops[i + 1];
     if (lo.code != OP_LOAD || (lo.i2 & (LD_PLAIN | LD_STENCIL | LD_ACC | LD_MUL)) || bo.code != OP_BAND) continue;
     const int h0 = (int)(signed char)(bo.i1 & 0xff), h1 = (int)(signed char)((bo.i1 >> 8) & 0xff), h2 = (int)(signed char)((bo.i1 >> 16) & 0xff);
@@ -582,6 +598,30 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
       }
       if (!ok) continue;
       bo.code = OP_PREBAND; bo.p0 = sc[0]; bo.p1 = sc[1]; bo.p2 = sc[2]; fo.i2 |= FD_PREBAND;
+    }
+  }
+  // Remaining banded mat-vecs on transform-sized lanes run in chunk-streaming form (band_chunk: one read and one write
+  // traversal of the lane group): pair offsets {0, +1, +2} or {0, -1}, vector coefficients through their scan-layout copies.
+  if (c.fast && bandc) {
+    for (int i = 0; i < p.nops; i++) {
+      LaneOp& bo = p.ops[i];
+      if (bo.code != OP_BAND) continue;
+      const void* nat[3] = {bo.p0, bo.p1, bo.p2};
+      const void* slot[3] = {nullptr, nullptr, nullptr};
+      int flag[3] = {0, 0, 0};
+      bool ok = true, anyvec = false, fwd = false, bwd = false;
+      for (int m = 0; m < 3 && ok; m++) {
+        const int h = (int)(signed char)((bo.i1 >> (8 * m)) & 0xff);
+        if (h == 127) continue;
+        int k;
+        if (h == 0) k = 0; else if (h == 2) { k = 1; fwd = true; } else if (h == 4) { k = 2; fwd = true; } else if (h == -2) { k = 1; bwd = true; } else { ok = false; break; }
+        if (flag[k]) { ok = false; break; }
+        if (nat[m]) { auto it = scan_of().find(nat[m]); if (it == scan_of().end()) { ok = false; break; } slot[k] = it->second; flag[k] = 2; anyvec = true; }
+        else flag[k] = 1;
+      }
+      if (!ok || !anyvec || (fwd && bwd)) continue;
+      bo.code = OP_BANDC; bo.p0 = slot[0]; bo.p1 = slot[1]; bo.p2 = slot[2];
+      bo.i1 = (bwd ? 1 : 0) | (flag[0] << 2) | (flag[1] << 4) | (flag[2] << 6);
     }
   }
   // TMA views.  Arrays are 4x4-tiled: tile (I, J) at ((I * tiles_per_row) + J) * 128 bytes, element [i][j] inside.
@@ -629,6 +669,10 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
         op.i2 |= ST_TMA;
       } else {
         const bool direct = g_use_direct && !(op.i2 & ST_ACC) && op.a == 1.0;
+        if (op.i2 & ST_COLSPLIT) {   // zero-copy runs per owner (contiguous slabs only), else per-thread peer stores
+          if (direct && p.bulk1d) op.i2 |= ST_DIRECT;
+          continue;
+        }
         d.rank = 3;
         d.dim[0] = 16; d.dim[1] = (uint64_t)c.in_tiles; d.dim[2] = (uint64_t)groups_local;
         d.stride[1] = 128; d.stride[2] = (uint64_t)c.in_tiles * 128;
@@ -698,6 +742,10 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   // short lanes: keep the CTA near 72 KB so that three fit on an SM; long lanes: one CTA owns the SM
   size_t room = budget - fixed - wbytes;
   if (wbytes <= 40 * 1024) room = std::min(room, std::max((size_t)8192, (size_t)72 * 1024 - std::min((size_t)72 * 1024, fixed + wbytes)));
+  if (const char* e = getenv("B2_SMEMCAP")) {   // tuning knob: total dynamic shared memory per CTA in KB (e.g. 113 = two CTAs per SM)
+    const size_t cap = (size_t)atoi(e) * 1024;
+    if (cap > fixed + wbytes + 4096) room = std::min(room, cap - fixed - wbytes);
+  }
   const int nwarps = c->NT / 32;
   int chw = (int)(room / ((size_t)nwarps * 2) / tile_bytes) - 1;   // one halo tile in front of every slot
   if (const char* e = getenv("B2_CHW")) { int v = atoi(e); if (v >= 2) chw = std::min(chw, v); }
@@ -849,6 +897,71 @@ static int hholtz_solve(b2_solver* s, const double* in, double* out) {
 }
 
 // laplacian / mass of axis ax as in Poisson::new (src/solver/poisson.rs:65-74)
+// ------------------------------------------------------------------------------------------------
+// FP64 GEMM on the tiled arrays (gemm_f64.cuh): host side
+// ------------------------------------------------------------------------------------------------
+// A (row-major, M x K, leading dimension ld) -> fragment order [slice mt][k stage][k4 step][8-row fragment][lane]:
+// slice mt holds the global rows mt * mstep + row0 + [0, 64); zero outside M x K.
+static std::vector<double> pack_gemm_a(const double* A, int M, int K, int ld, int nmt, int nks, int mstep, int row0) {
+  std::vector<double> out((size_t)nmt * nks * 512, 0.0);
+  for (int mt = 0; mt < nmt; mt++)
+    for (int ks = 0; ks < nks; ks++)
+      for (int kk = 0; kk < 2; kk++)
+        for (int mf = 0; mf < 8; mf++)
+          for (int lane = 0; lane < 32; lane++) {
+            const int m = mt * mstep + row0 + 8 * mf + (lane >> 2), k = 8 * ks + 4 * kk + (lane & 3);
+            if (m < M && k < K) out[((((size_t)mt * nks + ks) * 2 + kk) * 8 + mf) * 32 + lane] = A[(size_t)m * ld + k];
+          }
+  return out;
+}
+// Parity-block product: blocks (Ae: Me x Ke, Ao: Mo x Ko); dense product (Ao == nullptr): one M x K matrix run as two
+// 64-row halves of 128-row slices over the same rows of B.
+static int gemm_plan_create(b2_space* sp, GemmPlan* g, const double* Ae, int Me, int Ke, const double* Ao, int Mo, int Ko,
+                            bool b_interleaved, bool c_interleaved) {
+  GemmParams& p = g->p;
+  memset(&p, 0, sizeof(p));
+  const int Kmax = std::max(Ke, Ko);
+  p.nks = (Kmax + 7) / 8;
+  if (Ao) {
+    p.mstep = 64; p.bshift = 0; p.nmt = (std::max(Me, Mo) + 63) / 64;
+    p.Mb[0] = Me; p.Mb[1] = Mo;
+    RET(g->A[0].upload(pack_gemm_a(Ae, Me, Ke, Ke, p.nmt, p.nks, 64, 0)));
+    RET(g->A[1].upload(pack_gemm_a(Ao, Mo, Ko, Ko, p.nmt, p.nks, 64, 0)));
+    if (b_interleaved) { p.offB[0] = 0; p.offB[1] = 1; p.strB = 2; } else { p.offB[0] = 0; p.offB[1] = Ke; p.strB = 1; }
+    if (c_interleaved) { p.offC[0] = 0; p.offC[1] = 1; p.strC = 2; } else { p.offC[0] = 0; p.offC[1] = Me; p.strC = 1; }
+    if ((!b_interleaved && Ke % 4) || (!c_interleaved && Me % 4)) return fail(B2_ERR_UNSUPPORTED, "parity-block GEMM: the odd block must start on a tile row");
+  } else {
+    p.mstep = 128; p.bshift = 64; p.nmt = (Me + 127) / 128;
+    p.Mb[0] = Me; p.Mb[1] = Me;
+    RET(g->A[0].upload(pack_gemm_a(Ae, Me, Ke, Ke, p.nmt, p.nks, 128, 0)));
+    RET(g->A[1].upload(pack_gemm_a(Ae, Me, Ke, Ke, p.nmt, p.nks, 128, 64)));
+    p.offB[0] = p.offB[1] = 0; p.strB = 1; p.offC[0] = p.offC[1] = 0; p.strC = 1;
+  }
+  p.A[0] = g->A[0].d; p.A[1] = g->A[1].d;
+  // B = this rank's [all rows][local columns] array, C = rows distributed over the ranks, all columns (one GPU: the same thing)
+  const int nr = sp->ctx->nranks;
+  p.TJc = sp->P[1] / 4; p.TJb = p.TJc / nr; p.rowsB = sp->P[0] / 4; p.jc0 = sp->ctx->rank * p.TJb;
+  p.ncb = (p.TJb + 31) / 32;
+  p.rows_per_rank = sp->P[0] / nr;
+  p.peers = nr > 1 ? reinterpret_cast<double* const*>(sp->ctx->d_peers) : nullptr; p.c_off = 0;
+  g->grid = p.nmt * p.ncb;
+  return B2_OK;
+}
+static int gemm_run(b2_ctx* ctx, const GemmPlan& g, const double* B, double* C) {
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    CK(cudaFuncSetAttribute(gemm_pb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  GemmParams p = g.p;
+  p.B = B; p.C = C;
+  if (ctx->nranks > 1) p.c_off = reinterpret_cast<const char*>(C) - static_cast<const char*>(ctx->peer_base[ctx->rank]);
+  B2_LAUNCH(gemm_pb_kernel, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return ctx->nranks > 1 ? ctx_barrier(ctx) : B2_OK;   // the epilogue wrote into the peers' slabs
+}
+
 static void poisson_axis(const Base1& b, double c, Diags* lap, Diags* mass) {
   Diags a = b.mat_a(), bm = b.mat_b();
   *mass = a;
@@ -924,7 +1037,8 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     }
     for (int k = 0; k < 2 && ok; k++) for (int r = 0; r < m0; r++) if (cls[r] == k) perm.push_back(r);
     int ne = 0; for (int r = 0; r < m0; r++) ne += (cls[r] == 0);
-    if (ok && ne == ce && (nr == 1 || (ce % 2 == 0 && sp->cfg[0].LN == 4 && sp->cfg[1].LN == 4))) {   // multi-GPU: the odd block starts at column ce of the x-pencil operands (16-byte stores)
+    const bool own = getenv("B2_CUBLAS") == nullptr;   // B2_CUBLAS=1: library DGEMM on row-major copies (A/B measurements only)
+    if (ok && ne == ce && (own ? (ce % 4 == 0) : (nr == 1 || (ce % 2 == 0 && sp->cfg[0].LN == 4 && sp->cfg[1].LN == 4)))) {   // the odd block starts on a tile row (own GEMM) / at an even column of the x-pencil operands (library path)
       std::vector<double> fe((size_t)ce * ce), fo((size_t)co * co), be((size_t)ce * ce), bo((size_t)co * co), lam2(lam.size());
       for (int r = 0; r < ce; r++) for (int k = 0; k < ce; k++) { fe[(size_t)r * ce + k] = fwd[(size_t)perm[r] * m0 + 2 * k]; be[(size_t)k * ce + r] = bwd[(size_t)(2 * k) * m0 + perm[r]]; }
       for (int r = 0; r < co; r++) for (int k = 0; k < co; k++) { fo[(size_t)r * co + k] = fwd[(size_t)perm[ce + r] * m0 + 2 * k + 1]; bo[(size_t)k * co + r] = bwd[(size_t)(2 * k + 1) * m0 + perm[ce + r]]; }
@@ -932,7 +1046,17 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
       RET(s->fe.upload(fe)); RET(s->fo.upload(fo)); RET(s->be.upload(be)); RET(s->bo.upload(bo));
       RET(build_lanes(lam2, &s->qfl, &s->qid, &s->qu1, &s->qu2));
       s->blocks = true; s->ce = ce; s->co = co;
+      if (own) {   // own GEMM straight on the tiled arrays
+        RET(gemm_plan_create(sp, &s->gf, fe.data(), ce, ce, fo.data(), co, co, true, false));
+        RET(gemm_plan_create(sp, &s->gb, be.data(), ce, ce, bo.data(), co, co, false, true));
+        s->own_gemm = true;
+      }
     }
+  }
+  if (s->dense && !s->own_gemm && getenv("B2_CUBLAS") == nullptr) {   // dense decomposition: full products, natural mode order
+    RET(gemm_plan_create(sp, &s->gf, fwd, s->m0, s->m0, nullptr, 0, 0, false, false));
+    RET(gemm_plan_create(sp, &s->gb, bwd, s->m0, s->m0, nullptr, 0, 0, false, false));
+    s->own_gemm = true; s->blocks = false;
   }
   *out = s;
   return B2_OK;
@@ -947,12 +1071,47 @@ static int gemm_mark(b2_ctx* ctx) {
   return B2_OK;
 }
 
+// Eigen-transform core of the confined Poisson solve (src/solver/poisson.rs:213-235) on the tiled arrays, shared by the
+// fused step and Poisson::solve.  src: right-hand side in the y-lane orientation (rows = x index), already multiplied by the
+// x-axis preconditioner; matvec_y: apply the y-axis one here.  gx: [all x rows][local y columns] scratch (the GEMM operand:
+// the contraction runs over x; with several GPUs the lane passes scatter their column blocks to the owners -- ST_COLSPLIT --
+// and the GEMM epilogue scatters its row blocks back, so both exchanges ride on a kernel that runs anyway), y1: slab scratch.
+static int poisson_core(b2_solver* s, b2_space* rs, const double* src, bool matvec_y, double* gx, double* y1, double* out, bool zero00) {
+  b2_ctx* ctx = rs->ctx;
+  const Base1& b1 = s->sp->b[1];
+  Prog y; y.load(src, matvec_y ? b1.rows_ortho : b1.m);
+  if (matvec_y) y.matvec(b1);
+  y.store(gx, b1.m, ST_COLSPLIT);
+  RET(run_pass(rs, 0, y));
+  RET(gemm_mark(ctx));
+  RET(gemm_run(ctx, s->gf, gx, y1));   // forward: x index -> eigenmodes (parity blocks: modes grouped by class, the order of q*)
+  RET(gemm_mark(ctx));
+  Prog y2; y2.load(y1, b1.m);
+  if (s->blocks) y2.fdma(b1.m, s->qfl.d, s->qid.d, s->qu1.d, s->qu2.d, FD_PERLANE);
+  else y2.fdma(b1.m, s->pfl.d, s->pid.d, s->pu1.d, s->pu2.d, FD_PERLANE);
+  y2.store(gx, b1.m, ST_COLSPLIT);
+  RET(run_pass(rs, 0, y2));
+  RET(gemm_mark(ctx));
+  RET(gemm_run(ctx, s->gb, gx, out));  // backward: eigenmodes -> x index (natural order)
+  RET(gemm_mark(ctx));
+  if (zero00 && ctx->rank == 0) CK(cudaMemsetAsync(out, 0, sizeof(double), ctx->cur));   // element (0, 0) of tile (0, 0) (navier_eq.rs:161)
+  return B2_OK;
+}
+
 // Poisson::solve_par, src/solver/poisson.rs:195-236
 static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero00) {
   b2_space* sp = s->sp;
   b2_ctx* ctx = sp->ctx;
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
   const int P0 = sp->P[0], P1 = sp->P[1];
+  if (s->dense && s->own_gemm) {
+    // matvec along y and x (two transposing passes: back in the y-lane orientation, rows = x index), then the core
+    Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1); y.store(sp->tmp[0], l, ST_TRANS);
+    RET(run_pass(sp, 0, y));
+    Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0); x.store(sp->tmp[1], l, ST_TRANS);
+    RET(run_pass(sp, 1, x));
+    return poisson_core(s, sp, sp->tmp[1], false, sp->tmp[0], sp->tmp[2], out, zero00);
+  }
   if (s->dense) {
     // matvec along y, transpose
     Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1); y.store(sp->tmp[0], l, ST_TRANS);
@@ -1734,7 +1893,12 @@ static int nav_update_fused(b2_navier* nv) {
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
   const double* pseu_src; int pseu_flags, pseu_i1 = 0;
-  if (ps->dense && ctx->nranks > 1 && ps->blocks) {
+  if (ps->dense && ps->own_gemm) {
+    // own FP64 GEMMs on the tiled arrays (gemm_f64.cuh): no row-major copies, every load / store of the lane passes
+    // around them is a zero-copy slab copy; with several GPUs the exchanges ride on those stores and on the GEMM epilogue
+    RET(poisson_core(ps, so, nv->R0, true, nv->G0, nv->G1, nv->pseu->vhat->d, true));
+    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
+  } else if (ps->dense && ctx->nranks > 1 && ps->blocks) {
     // slabs + parity blocks: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y,
     // row-major, x contiguous); the x index is stored parity-split (ST_PSPLITC / LD_PSPLITC), the modes parity-grouped
     const double one = 1.0, zero = 0.0;

@@ -299,6 +299,71 @@ template <int LN> struct ChunkAddr {
   __device__ __forceinline__ int at(int t) const { return ((t & 1) ? bo : be) + Lay<LN>::pix(t); }
 };
 
+// Banded mat-vec with chunk ownership, streamed in place (OP_BANDC, set by the launcher): thread q owns the pairs
+// p0 + t like the recurrences below, reads every pair of W once and writes it once -- one read and one write traversal
+// of the lane group instead of one read per term plus the write of band_fast (the lane operators are bound by
+// shared-memory bandwidth, 128 B/clk: ~1k cycles per traversal of a 131 KB group).
+//   forward type  (i1 bit 0 = 0): y_p = k0 x_p + k1 x_{p+1} + k2 x_{p+2}   (pair offsets 0, +1, +2: S^T, MatVecFdma)
+//   backward type (i1 bit 0 = 1): y_p = k0 x_p + k1 x_{p-1}                (to_ortho stencil)
+// term flags, 2 bits each from bit 2: 0 absent, 1 unit coefficient, 2 scan-layout vector ([t][q]) in p0 / p1 / p2.
+template <int E, int LN, int TPL>
+__device__ __noinline__ void band_chunk(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  constexpr int CP = E + 1;
+  const int HP = P.LP >> 1;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  double2* w2 = reinterpret_cast<double2*>(W) + 2 * l;
+  const int p0 = q * CP;
+  const ChunkAddr<LN> ca(p0);
+  const int tmax = HP - p0;                                     // t < tmax: the pair exists in W
+  const int len_out = op.i0;
+  const int tx = (len_out - 2 * p0 + 1) >> 1, ty = (len_out - 2 * p0) >> 1;   // t < tx: element 2p < len_out; t < ty: 2p+1 < len_out
+  const double2 zero = d2(0.0, 0.0);
+  const double2* cp[3] = {(const double2*)op.p0, (const double2*)op.p1, (const double2*)op.p2};
+  const double2* any = cp[0] ? cp[0] : (cp[1] ? cp[1] : cp[2]);
+  double wl[3], ad[3];                                          // coefficient = loaded * wl + ad (loads stay unconditional)
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const int f = (op.i1 >> (2 + 2 * m)) & 3;
+    wl[m] = (f == 2) ? 1.0 : 0.0; ad[m] = (f == 1) ? 1.0 : 0.0;
+    cp[m] = ((f == 2) ? cp[m] : any) + q;
+  }
+  if (!(op.i1 & 1)) {
+    const double2 hA = (CP < tmax) ? w2[ca.at(CP)] : zero, hB = (CP + 1 < tmax) ? w2[ca.at(CP + 1)] : zero;
+    __syncthreads();
+    double2 x0 = (0 < tmax) ? w2[ca.at(0)] : zero, x1 = (1 < tmax) ? w2[ca.at(1)] : zero;
+#pragma unroll
+    for (int t = 0; t < CP; t++) {
+      const double2 x2 = (t + 2 < CP) ? ((t + 2 < tmax) ? w2[ca.at(t + 2 < CP ? t + 2 : 0)] : zero) : (t + 2 == CP ? hA : hB);
+      const double2 l0 = ldg(cp[0] + t * TPL), l1 = ldg(cp[1] + t * TPL), l2 = ldg(cp[2] + t * TPL);
+      const double2 k0 = d2(fma(l0.x, wl[0], ad[0]), fma(l0.y, wl[0], ad[0]));
+      const double2 k1 = d2(fma(l1.x, wl[1], ad[1]), fma(l1.y, wl[1], ad[1]));
+      const double2 k2 = d2(fma(l2.x, wl[2], ad[2]), fma(l2.y, wl[2], ad[2]));
+      double2 b = d2fma(k0, x0, d2fma(k1, x1, d2(k2.x * x2.x, k2.y * x2.y)));
+      if (t >= tx) b.x = 0.0;
+      if (t >= ty) b.y = 0.0;
+      if (t < tmax) w2[ca.at(t)] = b;
+      x0 = x1; x1 = x2;
+    }
+  } else {
+    const double2 hP = (q > 0 && 0 <= tmax) ? w2[Lay<LN>::pix(p0 - 1)] : zero;   // the pair in front of the chunk
+    __syncthreads();
+    double2 x0 = (CP - 1 < tmax) ? w2[ca.at(CP - 1)] : zero;
+#pragma unroll
+    for (int t = CP - 1; t >= 0; t--) {
+      const double2 xm = (t > 0) ? ((t - 1 < tmax) ? w2[ca.at(t > 0 ? t - 1 : 0)] : zero) : hP;
+      const double2 l0 = ldg(cp[0] + t * TPL), l1 = ldg(cp[1] + t * TPL);
+      const double2 k0 = d2(fma(l0.x, wl[0], ad[0]), fma(l0.y, wl[0], ad[0]));
+      const double2 k1 = d2(fma(l1.x, wl[1], ad[1]), fma(l1.y, wl[1], ad[1]));
+      double2 b = d2fma(k0, x0, d2(k1.x * xm.x, k1.y * xm.y));
+      if (t >= tx) b.x = 0.0;
+      if (t >= ty) b.y = 0.0;
+      if (t < tmax) w2[ca.at(t)] = b;
+      x0 = xm;
+    }
+  }
+  __syncthreads();
+}
+
 template <int E, int LN, int TPL>
 __device__ __noinline__ void deriv_fast(const LaneProg& P, const LaneOp& op, double* __restrict__ W, void* scratch) {
   constexpr int CP = E + 1;

@@ -51,6 +51,7 @@ enum LaneOpCode {
   OP_ZEROELEM = 12,// W[lane i0][pos i1] = 0 (global lane index)
   OP_SCALE = 13,   // W *= a
   OP_PREBAND = 14, // an OP_BAND folded into the OP_FDMA that follows it (set by the launcher, fast geometry only): no-op here
+  OP_BANDC = 15,   // an OP_BAND in chunk-streaming form (set by the launcher, fast geometry only): see band_chunk
 };
 enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
        LD_TMA = 16,          // set by the launcher: the slab streams through the warps' staging slots (load_warps)
@@ -62,7 +63,10 @@ enum { ST_ACC = 1, ST_PLAIN = 2, ST_TRANS = 8, ST_PEER = 16,
        ST_TMA = 32,          // set by the launcher: staged, bulk tensor store / reduction
        ST_DIRECT = 64,       // set by the launcher: zero-copy TMA straight from W (same orientation, a == 1, no accumulate)
        ST_PSPLIT = 128,      // plain destinations, same orientation: store row r < i1 at r/2 (even) or ceil(i1/2) + r/2 (odd)
-       ST_PSPLITC = 256 };   // plain transposing stores: lane index (= column) c <= i1 goes to c/2 (even) or ceil(i1/2) + c/2 (odd)
+       ST_PSPLITC = 256,     // plain transposing stores: lane index (= column) c <= i1 goes to c/2 (even) or ceil(i1/2) + c/2 (odd)
+       ST_COLSPLIT = 512 };  // several GPUs, same orientation: the positions along the lane are distributed over the ranks -- tile J of global
+                             // lane group g goes to rank J / groups_per_rank, tile (g, J mod groups_per_rank) of its [all rows][local columns] array
+                             // (operand of the eigen-transform GEMM, whose contraction runs over the rows); p1 = peer table
 enum { FD_PERLANE = 1, FD_NOU2 = 2,
        FD_PREBAND = 4 };   // the right-hand side is the banded mat-vec described by the preceding OP_PREBAND op
 
@@ -545,7 +549,7 @@ __device__ __noinline__ void load_threads(const LaneProg& P, const LaneOp& op, c
 // ---------------------------------------------------------------------------------------------
 // dst = W, same orientation: W leaves as it is (zero-copy) once its tail (>= len) is cleared.
 template <int LN>
-__device__ __noinline__ void store_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, int gl, int lb) {
+__device__ __noinline__ void store_direct(const LaneProg& P, const LaneOp& op, const B2TMap* tm, const SmemView& sv, int g, int gl, int lb) {
   const int len = op.i0, ntail = P.LP - len;
   for (int i = threadIdx.x; i < ntail * LN; i += P.NT) {
     const int l = i & (LN - 1), e = len + (i >> Lay<LN>::LOG);
@@ -554,7 +558,16 @@ __device__ __noinline__ void store_direct(const LaneProg& P, const LaneOp& op, c
   fence_proxy_async();
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (P.bulk1d) {
+    if (op.i2 & ST_COLSPLIT) {   // (bulk1d only) one run of tiles per owner, straight from W into the owner's array
+      const int tpr = P.groups_per_rank;
+      char* const* peers = reinterpret_cast<char* const*>(op.p1);
+      const size_t off = static_cast<const char*>(op.p0) - peers[P.rank];
+      for (int o = 0; o * tpr < P.in_tiles; o++)
+        for (int t0 = o * tpr; t0 < (o + 1) * tpr; t0 += P.CHD) {
+          const int t1 = min(t0 + P.CHD, (o + 1) * tpr);
+          bulk_store_1d(peers[o] + off + ((size_t)g * tpr + (t0 - o * tpr)) * 128, reinterpret_cast<const char*>(sv.W) + (size_t)t0 * 128, (uint32_t)(t1 - t0) * 128u);
+        }
+    } else if (P.bulk1d) {
       char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + (size_t)gl * P.in_tiles * 128;
       for (int c = 0; c < P.nchd; c++) {
         const int t0 = c * P.CHD, t1 = min(t0 + P.CHD, P.in_tiles);
@@ -694,6 +707,13 @@ __device__ __noinline__ void store_threads(const LaneProg& P, const LaneOp& op, 
       }
       int row = 4 * gl + lb + l;
       if ((flags & ST_PSPLIT) && row < op.i1) row = (row & 1) ? ((op.i1 + 1) >> 1) + (row >> 1) : (row >> 1);
+      if (flags & ST_COLSPLIT) {   // tile J of global group g -> owner J / tpr, tile (g, J mod tpr) of its [all rows][local columns] array
+        const int tpr = P.groups_per_rank, o = J / tpr;
+        char* const* peers = reinterpret_cast<char* const*>(op.p1);
+        double2* d = reinterpret_cast<double2*>(peers[o] + (static_cast<const char*>(op.p0) - peers[P.rank]));
+        d[((size_t)g * tpr + (J - o * tpr)) * 8 + (lb + l) * 2 + (pc & 1)] = v;
+        continue;
+      }
       size_t idx = (flags & ST_PLAIN) ? (((size_t)row * P.in_tiles * 4 + j0) >> 1)
                                       : (slab + (size_t)J * 8 + (lb + l) * 2 + (pc & 1));
       if (flags & ST_ACC) { double2 ov = dst[idx]; v.x += ov.x; v.y += ov.y; }
@@ -1131,7 +1151,7 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
       }
         break;
       case OP_STORE:
-        if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &Pp.tm[o], sv, gl, lb);
+        if (op.i2 & ST_DIRECT) store_direct<LN>(P, op, &Pp.tm[o], sv, g, gl, lb);
         else if (op.i2 & ST_TMA) store_warps<LN>(P, op, (op.i2 & ST_PEER) ? &Pp.tmp[op.i1][0] : &Pp.tm[o], sv, g, gl, lb, pf);
         else store_threads<LN>(P, op, sv, g, gl, lb);
         break;
@@ -1151,6 +1171,9 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
         if constexpr (TPLC > 0) rfft_fast<E, LN, TPLC>(P, op, W); else op_rfft<E, LN>(P, op, W);
         break;
       case OP_PREBAND: break;
+      case OP_BANDC:
+        if constexpr (TPLC > 0) band_chunk<E, LN, TPLC>(P, op, W);
+        break;
       default: op_pointwise<LN>(P, op, W, g, lb); break;
     }
     if (P.prof && threadIdx.x == 0) {
