@@ -111,6 +111,11 @@ int b2_hholtz_adi_create(const b2_field* f, double c0, double c1, b2_solver** ou
  * poisson.rs:84-86), fwd[m0*m0] = Q^-1 C0^-1, bwd[m0*m0] = Q, row-major.  NULL for a Fourier axis 0. */
 int b2_poisson_create(const b2_field* f, double c0, double c1, const double* lam, const double* fwd,
                       const double* bwd, b2_solver** out);
+/* Hholtz::new(&field, [c0, c1]), src/solver/hholtz.rs:66-101: (I - c D2) vhat = A f through the same FdmaTensor as
+ * Poisson (laplacian = -c * mat_b, mass = mat_a, alpha = 1, no singularity shift); lam / fwd / bwd = eigendecomposition of
+ * C0^-1 (-c0 B0) as for b2_poisson_create (NULL for a Fourier axis 0). */
+int b2_hholtz_create(const b2_field* f, double c0, double c1, const double* lam, const double* fwd,
+                     const double* bwd, b2_solver** out);
 int b2_solver_destroy(b2_solver* s);
 /* solver.solve(&input [ORTHO], &mut output [SPECTRAL], 0) */
 int b2_solve(b2_solver* s, const b2_array* in, b2_array* out);

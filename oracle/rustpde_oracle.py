@@ -661,6 +661,37 @@ class Poisson:
         return self.solver.solve(rhs)
 
 
+class Hholtz:
+    """src/solver/hholtz.rs:66-101,153-176: (I - c D2) vhat = A f via the eigendecomposition of axis 0 (FdmaTensor, alpha = 1)."""
+
+    def __init__(self, field, c, eig=None):
+        nd = len(c)
+        lap, mass, isd, self.matvec = [], [], [], []
+        for axis in range(nd):
+            mat_a, mat_b, pre, is_diag = field.ingredients_for_poisson(axis) if nd == 2 else _ingredients_1d(field, axis) + (False,)
+            mass.append(mat_a)
+            lap.append(-1.0 * mat_b * c[axis])
+            self.matvec.append(MatVecFdma(pre) if pre is not None else None)
+            isd.append(is_diag)
+        if eig is not None and nd == 2 and not isd[0]:
+            t = FdmaTensor.__new__(FdmaTensor)
+            t.ndim, t.alpha, t.n = 2, 1.0, lap[-1].shape[0]
+            t.lam = [np.array(eig[0], copy=True)]
+            t.fwd = [np.array(eig[1], copy=True)]
+            t.bwd = [np.array(eig[2], copy=True)]
+            t.fdma = [Fdma.from_matrix_raw(lap[-1]), Fdma.from_matrix_raw(mass[-1])]
+            self.solver = t
+            return
+        self.solver = FdmaTensor(lap, mass, isd, 1.0)
+
+    def solve(self, inp):
+        rhs = inp
+        for ax in range(len(self.matvec)):
+            if self.matvec[ax] is not None:
+                rhs = self.matvec[ax].solve(rhs, ax)
+        return self.solver.solve(rhs)
+
+
 class Space1:
     def __init__(self, b0):
         self.bases = (b0,)

@@ -59,6 +59,7 @@ SYMBOLS = {
     "b2_field_dealias": (_I, [_P]),
     "b2_hholtz_adi_create": (_I, [_P, _D, _D, _PP]),
     "b2_poisson_create": (_I, [_P, _D, _D, _DP, _DP, _DP, _PP]),
+    "b2_hholtz_create": (_I, [_P, _D, _D, _DP, _DP, _DP, _PP]),
     "b2_solver_destroy": (_I, [_P]),
     "b2_solve": (_I, [_P, _P, _P]),
     "b2_poisson_axis0_matrices": (_I, [_P, _D, _DP, _DP]),

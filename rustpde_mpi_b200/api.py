@@ -392,6 +392,28 @@ class HholtzAdi(_Solver):
         check(lib().b2_hholtz_adi_create(field._h, float(c[0]), float(c[1]), C.byref(self._h)))
 
 
+class Hholtz(_Solver):
+    """``Hholtz::new(&field, c)`` (src/solver/hholtz.rs:66-101): ``(I - c D2) vhat = A f`` through the eigendecomposition
+    of axis 0 (``FdmaTensor`` with alpha = 1) instead of the ADI factorisation."""
+
+    def __init__(self, field, c):
+        self.field = field
+        self._h = C.c_void_p()
+        kind0, n0 = field.space.bases[0]
+        if kind0 in (CHEB_DIRICHLET, CHEB_NEUMANN):
+            lam, fwd, bwd = hholtz_eig(kind0, n0, c[0])
+            check(lib().b2_hholtz_create(field._h, float(c[0]), float(c[1]), _dp(lam), _dp(fwd), _dp(bwd), C.byref(self._h)))
+        else:
+            check(lib().b2_hholtz_create(field._h, float(c[0]), float(c[1]), None, None, None, C.byref(self._h)))
+
+
+def hholtz_eig(kind0, n0, c0, parity_split=None):
+    """Eigendecomposition of ``C0^-1 (-c0 B0)`` for ``Hholtz`` (src/solver/hholtz.rs:79-81 + fdma_tensor.rs:117-129): the
+    Poisson routine with the sign of the Laplacian flipped (its eigenvalues are then >= 0, so the singularity shift of
+    ``Poisson::new`` never triggers -- ``Hholtz`` has none)."""
+    return poisson_eig(kind0, n0, -float(c0), parity_split)
+
+
 def _eig_sorted(x):
     """src/solver/utils.rs:67-100: LAPACK dgeev, real parts, eigenvalues sorted descending."""
     ev, evec = np.linalg.eig(x)

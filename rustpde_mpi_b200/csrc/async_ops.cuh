@@ -76,6 +76,10 @@ static inline void mbar_wait(uint64_t* bar, unsigned parity) {   // returns once
   emu::MBar& b = emu::mbars()[bar];
   emu::g_mbar_cv.wait(lk, [&] { return b.phase != parity; });
 }
+static inline bool mbar_test(uint64_t* bar, unsigned parity) {   // non-blocking: has the phase with this parity completed?
+  std::lock_guard<std::mutex> lk(emu::g_mbar_mutex);
+  return emu::mbars()[bar].phase != parity;
+}
 static inline void emu_tx_done(uint64_t* bar, long long bytes) {
   std::lock_guard<std::mutex> lk(emu::g_mbar_mutex);
   emu::MBar& b = emu::mbars()[bar]; b.tx -= bytes; emu::mbar_complete_locked(b);
@@ -169,6 +173,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {   // non-blocking: has the phase with this parity completed?
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const B2TMap* m, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"

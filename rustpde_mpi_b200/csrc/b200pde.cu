@@ -649,10 +649,17 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
       for (int o = 0; o < ctx->nranks; o++) {
         B2TMapDesc dd; memset(&dd, 0, sizeof(dd));
         dd.base = static_cast<char*>(ctx->peer_base[o]) + (static_cast<const char*>(op.p0) - static_cast<const char*>(ctx->peer_base[ctx->rank]));
-        dd.rank = 4;
-        dd.dim[0] = 4; dd.dim[1] = 4; dd.dim[2] = (uint64_t)c.out_tiles; dd.dim[3] = (uint64_t)gpr;
-        dd.stride[1] = 32; dd.stride[2] = 128; dd.stride[3] = (uint64_t)c.out_tiles * 128;
-        dd.box[0] = c.LN; dd.box[1] = 4; dd.box[2] = 1; dd.box[3] = c.CHW;
+        if (c.LN == 4) {   // whole tiles: [16 doubles of a tile][tile column g][tile row J]
+          dd.rank = 3;
+          dd.dim[0] = 16; dd.dim[1] = (uint64_t)c.out_tiles; dd.dim[2] = (uint64_t)gpr;
+          dd.stride[1] = 128; dd.stride[2] = (uint64_t)c.out_tiles * 128;
+          dd.box[0] = 16; dd.box[1] = 1; dd.box[2] = c.CHW;
+        } else {
+          dd.rank = 4;
+          dd.dim[0] = 4; dd.dim[1] = 4; dd.dim[2] = (uint64_t)c.out_tiles; dd.dim[3] = (uint64_t)gpr;
+          dd.stride[1] = 32; dd.stride[2] = 128; dd.stride[3] = (uint64_t)c.out_tiles * 128;
+          dd.box[0] = c.LN; dd.box[1] = 4; dd.box[2] = 1; dd.box[3] = c.CHW;
+        }
         const int er = b2_encode_tmap(dd, &p.tmp[npst][o]);
         if (er) return fail(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed for a peer view (" + std::to_string(er) + ")");
       }
@@ -662,10 +669,17 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
     } else if (op.code == OP_STORE && !(op.i2 & (ST_PLAIN | ST_PEER))) {
       d.base = const_cast<void*>(op.p0);
       if (op.i2 & ST_TRANS) {
-        d.rank = 4;
-        d.dim[0] = 4; d.dim[1] = 4; d.dim[2] = (uint64_t)c.out_tiles; d.dim[3] = (uint64_t)c.in_tiles;
-        d.stride[1] = 32; d.stride[2] = 128; d.stride[3] = (uint64_t)c.out_tiles * 128;
-        d.box[0] = c.LN; d.box[1] = 4; d.box[2] = 1; d.box[3] = c.CHW;
+        if (c.LN == 4) {   // whole tiles: [16 doubles of a tile][tile column g][tile row J], 128-byte rows
+          d.rank = 3;
+          d.dim[0] = 16; d.dim[1] = (uint64_t)c.out_tiles; d.dim[2] = (uint64_t)c.in_tiles;
+          d.stride[1] = 128; d.stride[2] = (uint64_t)c.out_tiles * 128;
+          d.box[0] = 16; d.box[1] = 1; d.box[2] = c.CHW;
+        } else {
+          d.rank = 4;
+          d.dim[0] = 4; d.dim[1] = 4; d.dim[2] = (uint64_t)c.out_tiles; d.dim[3] = (uint64_t)c.in_tiles;
+          d.stride[1] = 32; d.stride[2] = 128; d.stride[3] = (uint64_t)c.out_tiles * 128;
+          d.box[0] = c.LN; d.box[1] = 4; d.box[2] = 1; d.box[3] = c.CHW;
+        }
         op.i2 |= ST_TMA;
       } else {
         const bool direct = g_use_direct && !(op.i2 & ST_ACC) && op.a == 1.0;
@@ -903,14 +917,14 @@ static int hholtz_solve(b2_solver* s, const double* in, double* out) {
 // A (row-major, M x K, leading dimension ld) -> fragment order [slice mt][k stage][k4 step][8-row fragment][lane]:
 // slice mt holds the global rows mt * mstep + row0 + [0, 64); zero outside M x K.
 static std::vector<double> pack_gemm_a(const double* A, int M, int K, int ld, int nmt, int nks, int mstep, int row0) {
-  std::vector<double> out((size_t)nmt * nks * 512, 0.0);
+  std::vector<double> out((size_t)nmt * nks * G_ACHUNK, 0.0);
   for (int mt = 0; mt < nmt; mt++)
     for (int ks = 0; ks < nks; ks++)
-      for (int kk = 0; kk < 2; kk++)
+      for (int kk = 0; kk < G_KK; kk++)
         for (int mf = 0; mf < 8; mf++)
           for (int lane = 0; lane < 32; lane++) {
-            const int m = mt * mstep + row0 + 8 * mf + (lane >> 2), k = 8 * ks + 4 * kk + (lane & 3);
-            if (m < M && k < K) out[((((size_t)mt * nks + ks) * 2 + kk) * 8 + mf) * 32 + lane] = A[(size_t)m * ld + k];
+            const int m = mt * mstep + row0 + 8 * mf + (lane >> 2), k = 4 * G_KK * ks + 4 * kk + (lane & 3);
+            if (m < M && k < K) out[((((size_t)mt * nks + ks) * G_KK + kk) * 8 + mf) * 32 + lane] = A[(size_t)m * ld + k];
           }
   return out;
 }
@@ -921,7 +935,7 @@ static int gemm_plan_create(b2_space* sp, GemmPlan* g, const double* Ae, int Me,
   GemmParams& p = g->p;
   memset(&p, 0, sizeof(p));
   const int Kmax = std::max(Ke, Ko);
-  p.nks = (Kmax + 7) / 8;
+  p.nks = (Kmax + 4 * G_KK - 1) / (4 * G_KK);
   if (Ao) {
     p.mstep = 64; p.bshift = 0; p.nmt = (std::max(Me, Mo) + 63) / 64;
     p.Mb[0] = Me; p.Mb[1] = Mo;
@@ -969,7 +983,11 @@ static void poisson_axis(const Base1& b, double c, Diags* lap, Diags* mass) {
   for (int i = 0; i < b.m; i++) { lap->low[i] = bm.low[i] * c; lap->dia[i] = bm.dia[i] * c; lap->up1[i] = bm.up1[i] * c; lap->up2[i] = bm.up2[i] * c; }
 }
 
-static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_in, const double* fwd, const double* bwd, b2_solver** out) {
+// hholtz = true: Hholtz::new (src/solver/hholtz.rs:66-101) -- the same FdmaTensor with laplacian = -c * mat_b, alpha = 1 and
+// no singularity shift: (I - c D2) vhat = A f
+static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_in, const double* fwd, const double* bwd, b2_solver** out, bool hholtz = false) {
+  const double alpha = hholtz ? 1.0 : 0.0;
+  if (hholtz) { c0 = -c0; c1 = -c1; }
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
   if (!b1.composite) return fail(B2_ERR_UNSUPPORTED, "Poisson needs a composite Chebyshev axis 1");
   b2_solver* s = new b2_solver();
@@ -989,8 +1007,9 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     lanes = 2 * b0.m;
     lam.resize(lanes);
     for (int k = 0; k < b0.m; k++) lam[2 * k] = lam[2 * k + 1] = -(double)k * k * c0;
-    if (std::fabs(lam[0]) < 1e-10) for (auto& v : lam) v -= 1e-10;
+    if (!hholtz && std::fabs(lam[0]) < 1e-10) for (auto& v : lam) v -= 1e-10;
   } else { delete s; return fail(B2_ERR_UNSUPPORTED, "Poisson axis-0 base"); }
+  for (auto& v : lam) v += alpha;   // FdmaTensor::solve: (A1 + (lam_i + alpha) C1), src/solver/fdma_tensor.rs:277
   // per-lane LU of (lap1 + lam_i mass1), src/solver/poisson.rs:222-229, in scan layout [group][t][q][lane]
   Diags lap1, mass1;
   poisson_axis(b1, c1, &lap1, &mass1);
@@ -1533,6 +1552,9 @@ int b2_field_dealias(b2_field* f) {
 int b2_hholtz_adi_create(const b2_field* f, double c0, double c1, b2_solver** out) { return hholtz_create(f->sp, c0, c1, out); }
 int b2_poisson_create(const b2_field* f, double c0, double c1, const double* lam, const double* fwd, const double* bwd, b2_solver** out) {
   return poisson_create(f->sp, c0, c1, lam, fwd, bwd, out);
+}
+int b2_hholtz_create(const b2_field* f, double c0, double c1, const double* lam, const double* fwd, const double* bwd, b2_solver** out) {
+  return poisson_create(f->sp, c0, c1, lam, fwd, bwd, out, true);
 }
 int b2_solver_destroy(b2_solver* s) {
   if (!s) return B2_OK;

@@ -9,20 +9,23 @@
 //   rowX(b, t) = offX[b] + t * strX      interleaved (natural x order: off = {0, 1}, str = 2)  or
 //                                        grouped     (eigenmode order: off = {0, ce}, str = 1)
 // B and C are tiled arrays (tile (I, J) at ((I * TJ) + J) * 128 bytes, element [i][j] inside): a tile row segment
-// is contiguous, so a k-stage of B (16 natural rows = 4 tile rows x <= 32 tiles) is four 1-D bulk copies
+// is contiguous, so a k-stage of B (32 natural rows = 8 tile rows x <= 32 tiles) is eight 1-D bulk copies
 // (cp.async.bulk) -- no tensor map, no layout pass -- and a 4x4 tile IS the 4-wide k-slice a DMMA.8x8x4 fragment
 // wants: thread (k = lane % 4, n = lane / 4) reads element [row(k)][n % 4] of tile n / 4, conflict-free with a 32-byte
 // skew between tile-row slots.  A_b is packed on the host in fragment order ([m tile][k stage][k4 step][8-row
-// fragment][lane]), one 4 KB bulk copy per block and stage.  Arithmetic: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05
-// has no FP64 path), 16 warps x (32 x 32) outputs, accumulators in registers, a 4-stage mbarrier pipeline.
+// fragment][lane]), one 8 KB bulk copy per block and stage.  Arithmetic: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05
+// has no FP64 path), 16 warps x (32 x 32) outputs, accumulators in registers, a 4-stage full/empty mbarrier pipeline
+// without CTA barriers (one thread refills a buffer as soon as all warps have released it).
 // The epilogue writes 16-byte pieces (full 32-byte sectors per quad pair) straight into the tiled destination --
 // with several GPUs into the slab of the rank that owns the output rows (the pencil exchange rides on the epilogue).
 #pragma once
 #include "async_ops.cuh"
 
 #define G_NSTAGE 4
+#define G_KK 4                                           // k4 steps per stage: a stage holds 16 k per block
 #define G_SLOT_PITCH (32 * 16 + 4)                       // doubles per tile-row slot of B: 32 tiles + 32 bytes of skew
-#define G_STAGE_DOUBLES (4 * G_SLOT_PITCH + 2 * 512)     // 4 B slots + two packed A chunks (64 rows x 8 k)
+#define G_ACHUNK (G_KK * 8 * 32)                         // packed A per block and stage: 64 rows x 16 k
+#define G_STAGE_DOUBLES (2 * G_KK * G_SLOT_PITCH + 2 * G_ACHUNK)   // 8 B slots + the two A chunks
 #define G_SMEM_BYTES (128 + G_NSTAGE * G_STAGE_DOUBLES * 8)
 
 struct GemmParams {
@@ -35,13 +38,12 @@ struct GemmParams {
   int rowsB;                // tile rows of B (rows beyond are never read: the stage row is clamped, A is zero there)
   int jc0;                  // tile column of C that column 0 of B maps to (rank * TJb with several GPUs)
   int nmt, ncb;             // 64-row slices per block, column blocks; grid = nmt * ncb
-  int nks;                  // k stages of 8 per block
+  int nks;                  // k stages of 16 per block
   int Mb[2];                // valid rows per block
   int mstep, bshift;        // global row of (block b, slice mt, local row r) = mt * mstep + b * bshift + r
   int offB[2], strB;        // natural B row of (b, k) = offB[b] + k * strB   (strB = 2: offB = {0, 1})
   int offC[2], strC;        // natural C row of (b, m)
   int rows_per_rank;        // C rows owned by one rank (multiple of 4); >= all rows on one GPU
-  int nblk;                 // 2; (a dense product runs as two 64-row halves of a 128-row slice over the same B rows)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -59,16 +61,18 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ GemmParams P) {
   B2_DYN_SMEM(char, gsm);
-  uint64_t* full = reinterpret_cast<uint64_t*>(gsm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gsm);       // stage s has landed (bulk copies, transaction count)
+  uint64_t* empty = full + G_NSTAGE;                       // all 16 warps have finished reading stage s
   double* stage0 = reinterpret_cast<double*>(gsm + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = warp >> 3, wm = (warp >> 2) & 1, wn = warp & 3;
   const int mt = blockIdx.x % P.nmt, cb = blockIdx.x / P.nmt;
-  const int tc0 = (int)((long long)cb * P.TJb / P.ncb), tc1 = (int)((long long)(cb + 1) * P.TJb / P.ncb), ntc = tc1 - tc0;
+  // column blocks of 32 tiles, the remainder last: the (cheap) narrow blocks fill the tail of the last wave
+  const int tc0 = cb * 32, ntc = min(32, P.TJb - tc0);
   const int nks = P.nks;
   const bool inter = (P.strB == 2);
   if (tid == 0) {
-    for (int s = 0; s < G_NSTAGE; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < G_NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 16); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -76,34 +80,34 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
     const int s = ks % G_NSTAGE;
     double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
     const uint32_t rowbytes = (uint32_t)ntc * 128u;
-    mbar_arrive_expect_tx(&full[s], 4u * rowbytes + 2u * 4096u);
-    for (int sl = 0; sl < 4; sl++) {
-      int trow = inter ? 4 * ks + sl : (P.offB[sl >> 1] >> 2) + 2 * ks + (sl & 1);
+    mbar_arrive_expect_tx(&full[s], 2u * G_KK * rowbytes + 2u * G_ACHUNK * 8u);
+    for (int sl = 0; sl < 2 * G_KK; sl++) {
+      int trow = inter ? 2 * G_KK * ks + sl : (P.offB[sl / G_KK] >> 2) + G_KK * ks + (sl % G_KK);
       trow = min(trow, P.rowsB - 1);   // beyond the array: any finite data (the packed A is zero there)
       bulk_load_1d(st + sl * G_SLOT_PITCH, P.B + ((size_t)trow * P.TJb + tc0) * 16, rowbytes, &full[s]);
     }
     for (int bb = 0; bb < 2; bb++)
-      bulk_load_1d(st + 4 * G_SLOT_PITCH + bb * 512, P.A[bb] + ((size_t)mt * nks + ks) * 512, 4096u, &full[s]);
+      bulk_load_1d(st + 2 * G_KK * G_SLOT_PITCH + bb * G_ACHUNK, P.A[bb] + ((size_t)mt * nks + ks) * G_ACHUNK, G_ACHUNK * 8u, &full[s]);
   };
-  if (tid == 0) for (int ks = 0; ks < G_NSTAGE - 1 && ks < nks; ks++) issue(ks);
+  int issued = 0;
+  if (tid == 0) for (; issued < G_NSTAGE && issued < nks; issued++) issue(issued);
 
   // fragment addresses inside a stage (doubles)
   const int k = lane & 3, n8 = lane >> 2;
-  int boff[2];
+  int boff[G_KK];
 #pragma unroll
-  for (int kk = 0; kk < 2; kk++) {
-    const int slot = inter ? 2 * kk + (k >> 1) : 2 * b + kk;
+  for (int kk = 0; kk < G_KK; kk++) {
+    const int slot = inter ? 2 * kk + (k >> 1) : G_KK * b + kk;
     const int row = inter ? 2 * (k & 1) + b : k;
     boff[kk] = slot * G_SLOT_PITCH + (8 * wn + (n8 >> 2)) * 16 + row * 4 + (n8 & 3);
   }
-  const int aoff = 4 * G_SLOT_PITCH + b * 512 + (4 * wm) * 32 + lane;
+  const int aoff = 2 * G_KK * G_SLOT_PITCH + b * G_ACHUNK + (4 * wm) * 32 + lane;
   // rows / columns this warp owns; fragments completely outside the valid range are skipped (warp-uniform)
   const int mrow0 = mt * P.mstep + b * P.bshift + 32 * wm;          // global row of fragment 0, row 0
   const int Mv = P.Mb[b];
   const int ncols = 4 * ntc - 32 * wn;                              // valid columns from this warp's first one
   int mf_n = 0, nf_n = 0;
   for (int i = 0; i < 4; i++) { if (mrow0 + 8 * i < Mv) mf_n = i + 1; if (8 * i < ncols) nf_n = i + 1; }
-  if (P.nblk == 1 && b == 1 && P.bshift == 0) mf_n = 0;
 
   double acc[4][4][2];
 #pragma unroll
@@ -112,14 +116,21 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
     for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   for (int ks = 0; ks < nks; ks++) {
-    __syncthreads();                                   // everybody has finished stage ks - 1: its buffer is free
-    if (tid == 0 && ks + G_NSTAGE - 1 < nks) issue(ks + G_NSTAGE - 1);
     const int s = ks % G_NSTAGE;
+    if (tid == 0) {
+      // refill every buffer that all warps have released (no CTA barrier in this loop: the warps drift apart by up to
+      // a stage, which keeps the DMMA pipe fed across stage boundaries); stage ks itself must be on its way before
+      // anybody waits for it
+      while (issued < nks && (issued <= ks || mbar_test(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1)))) {
+        if (issued >= G_NSTAGE) mbar_wait(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1));
+        issue(issued); issued++;
+      }
+    }
     mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
     const double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
     if (mf_n > 0 && nf_n > 0) {
 #pragma unroll
-      for (int kk = 0; kk < 2; kk++) {
+      for (int kk = 0; kk < G_KK; kk++) {
         double a[4], bf[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i] = st[aoff + (kk * 8 + i) * 32];
@@ -139,6 +150,8 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
   // epilogue: thread holds C[8 i + lane / 4][8 j + 2 (lane % 4) + {0, 1}] of its 32 x 32 block
 #pragma unroll

@@ -633,13 +633,17 @@ __device__ __noinline__ void store_warps(const LaneProg& P, const LaneOp& op, co
     fence_proxy_async();
     __syncwarp();
     if (ln == 0) {
+      // whole lane groups (LN == 4): a destination tile is 128 contiguous bytes, and the view says so ([16][tile column][tile
+      // row]: one 128-byte row per tile -- the copy engine works row by row, and 32-byte rows made this store 4x slower)
       if ((flags & ST_TRANS) && (flags & ST_PEER)) {
         const int gpr = P.groups_per_rank, Jl = min(J0 + CHW, in_tiles) - 1;
         for (int o = J0 / gpr; o <= Jl / gpr; o++) {
-          if (flags & ST_ACC) tma_reduce_add_4d(tm + o, lb, 0, g, J0 - o * gpr, st); else tma_store_4d(tm + o, lb, 0, g, J0 - o * gpr, st);
+          if (LN == 4) { if (flags & ST_ACC) tma_reduce_add_3d(tm + o, 0, g, J0 - o * gpr, st); else tma_store_3d(tm + o, 0, g, J0 - o * gpr, st); }
+          else if (flags & ST_ACC) tma_reduce_add_4d(tm + o, lb, 0, g, J0 - o * gpr, st); else tma_store_4d(tm + o, lb, 0, g, J0 - o * gpr, st);
         }
       } else if (flags & ST_TRANS) {
-        if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);
+        if (LN == 4) { if (flags & ST_ACC) tma_reduce_add_3d(tm, 0, g, J0, st); else tma_store_3d(tm, 0, g, J0, st); }
+        else if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);
       } else if (P.bulk1d) {
         char* dst = static_cast<char*>(const_cast<void*>(op.p0)) + ((size_t)gl * in_tiles + J0) * 128;
         const uint32_t bytes = (uint32_t)(min(J0 + CHW, in_tiles) - J0) * 128u;

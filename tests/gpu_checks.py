@@ -114,6 +114,19 @@ def check_poisson(k0, n0, k1, n1, c=(1.0, 1.0), seed=7):
     return relerr(xg, xo)
 
 
+def check_hholtz_tensor(k0, n0, k1, n1, c=(0.37, 1.3), seed=9):
+    """Hholtz (eigendecomposition form, src/solver/hholtz.rs) against the oracle; both sides get the same decomposition."""
+    fo, fg = mk(k0, n0, k1, n1)
+    eig = b2.hholtz_eig(k0, n0, c[0]) if k0 in (1, 2) else None
+    ho = o.Hholtz(fo, list(c), eig=eig); hg = b2.Hholtz(fg, list(c))
+    sh = fo.space.to_ortho(fo.vhat).shape
+    rng = np.random.default_rng(seed)
+    rhs = rng.standard_normal(sh)
+    if fo.vhat.dtype == np.complex128:
+        rhs = rhs + 1j * rng.standard_normal(sh)
+    return relerr(hg.solve(rhs).get(), ho.solve(rhs))
+
+
 def make_navier_pair(nx, ny, ra, pr, dt, aspect, periodic, init="modes"):
     eig = None if periodic else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0 / aspect ** 2)
     no = o.Navier2D(nx, ny, ra, pr, dt, aspect, "rbc", periodic=periodic, pois_eig=eig)

@@ -32,6 +32,8 @@ if case == "ops":
 elif case == "poisson":
     for sp in [(2, 65, 2, 65), (4, 64, 2, 65)]:
         e = g.check_poisson(*sp); assert e < g.TOL, (sp, e)
+    for sp in [(1, 65, 1, 65), (4, 64, 2, 65)]:
+        e = g.check_hholtz_tensor(*sp); assert e < g.TOL, ("hholtz", sp, e)
 elif case == "golden":
     # reference goldens through the C ABI: src/solver/hholtz_adi.rs:215-246 and poisson.rs:295-325
     f = b2.Field2(b2.Space2(b2.cheb_dirichlet(7), b2.cheb_dirichlet(7)))

@@ -40,6 +40,12 @@ def test_poisson(sp):
     assert g.check_poisson(*sp) < g.TOL
 
 
+@pytest.mark.parametrize("sp", [(1, 65, 1, 65), (2, 129, 1, 65), (1, 257, 2, 257), (4, 64, 1, 65), (4, 256, 2, 129)])
+def test_hholtz_tensor(sp):
+    """Hholtz (src/solver/hholtz.rs:66-101): the eigendecomposition form of the Helmholtz solve (own FP64 GEMM path)."""
+    assert g.check_hholtz_tensor(*sp) < g.TOL
+
+
 def test_reference_goldens_through_cuda():
     import rustpde_mpi_b200 as b2
     from tests.test_oracle_golden import GOLD_P2D
