@@ -598,7 +598,7 @@ class HholtzAdi:
             if kind in (CHEBYSHEV, CHEB_DIRICHLET, CHEB_NEUMANN):
                 self.solver.append(Fdma.from_matrix(mat))
             elif kind == CHEB_DIRICHLET_NEUMANN:
-                raise NotImplementedError("PdmaPlus2 (bc='hc') is SURVEY 8f item 2")
+                self.solver.append(PdmaPlus2.from_matrix(mat))   # hholtz_adi.rs:64
             else:
                 self.solver.append(Sdma(mat))
             self.matvec.append(MatVecFdma(pre) if pre is not None else None)
@@ -743,11 +743,26 @@ def bc_rbc(b0, ny):
     return f
 
 
+def bc_hc(b0, ny, periodic=False):
+    """src/navier_stokes/boundary_conditions.rs:103-135 (confined) / :165-195 (periodic): T = -0.5 cos(2 pi (x - x0) / L)
+    at the bottom, T = T' = 0 at the top, a parabola in y with its vertex at the top wall."""
+    f = Field2(Space2(b0, chebyshev(ny)))
+    x, y = f.x
+    x0, length = x[0], x[-1] - x[0]   # (periodic: the Fourier grid stops one point short of 2 pi; the reference uses x[last] all the same)
+    f_x = -0.5 * np.cos(2.0 * np.pi * (x - x0) / length)
+    yl, yr = y[0], y[-1]
+    f.v[:, :] = (f_x / (yl - yr) ** 2)[:, None] * ((y - yr) ** 2)[None, :]
+    f.forward()
+    f.backward()
+    return f
+
+
 class Navier2D:
-    """``Navier2D`` with bc = "rbc", src/navier_stokes/navier.rs:49-466."""
+    """``Navier2D`` with bc = "rbc" or "hc", src/navier_stokes/navier.rs:49-466."""
 
     def __init__(self, nx, ny, ra, pr, dt, aspect, bc="rbc", periodic=False, pois_eig=None):
-        assert bc == "rbc", "bc='hc' is SURVEY 8f item 2"
+        assert bc in ("rbc", "hc"), f"Boundary condition type {bc!r} not recognized!"
+        self.bc = bc
         self.periodic = periodic
         self.scale = [aspect, 1.0]
         self.nu = get_nu(ra, pr, self.scale[1] * 2.0)
@@ -757,16 +772,16 @@ class Navier2D:
             bx = lambda: fourier_r2c(nx)
             self.velx = Field2(Space2(bx(), cheb_dirichlet(ny)))
             self.vely = Field2(Space2(bx(), cheb_dirichlet(ny)))
-            self.temp = Field2(Space2(bx(), cheb_dirichlet(ny)))
-            self.tempbc = bc_rbc(bx(), ny)
+            self.temp = Field2(Space2(bx(), cheb_dirichlet(ny) if bc == "rbc" else cheb_dirichlet_neumann(ny)))
+            self.tempbc = bc_rbc(bx(), ny) if bc == "rbc" else bc_hc(bx(), ny, True)
             self.pres = Field2(Space2(bx(), chebyshev(ny)))
             self.pseu = Field2(Space2(bx(), cheb_neumann(ny)))
             self.field = Field2(Space2(bx(), chebyshev(ny)))
         else:  # navier.rs:215-308
             self.velx = Field2(Space2(cheb_dirichlet(nx), cheb_dirichlet(ny)))
             self.vely = Field2(Space2(cheb_dirichlet(nx), cheb_dirichlet(ny)))
-            self.temp = Field2(Space2(cheb_neumann(nx), cheb_dirichlet(ny)))
-            self.tempbc = bc_rbc(chebyshev(nx), ny)
+            self.temp = Field2(Space2(cheb_neumann(nx), cheb_dirichlet(ny) if bc == "rbc" else cheb_dirichlet_neumann(ny)))
+            self.tempbc = bc_rbc(chebyshev(nx), ny) if bc == "rbc" else bc_hc(chebyshev(nx), ny)
             self.pres = Field2(Space2(chebyshev(nx), chebyshev(ny)))
             self.pseu = Field2(Space2(cheb_neumann(nx), cheb_neumann(ny)))
             self.field = Field2(Space2(chebyshev(nx), chebyshev(ny)))

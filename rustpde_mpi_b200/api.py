@@ -28,6 +28,10 @@ def cheb_neumann(n):
     return (CHEB_NEUMANN, n)
 
 
+def cheb_dirichlet_neumann(n):
+    return (CHEB_DIRICHLET_NEUMANN, n)
+
+
 def fourier_r2c(n):
     return (FOURIER_R2C, n)
 
@@ -514,7 +518,8 @@ class Navier2D:
             args = (_dp(lam), _dp(fwd), _dp(bwd))
         check(lib().b2_navier2d_create(self.ctx._h, nx, ny, ra, pr, dt, aspect, bc.encode(), int(periodic), *args, C.byref(self._h)))
         bx = (lambda k: fourier_r2c(nx)) if periodic else (lambda k: (k, nx))
-        kinds = {"temp": (bx(CHEB_DIRICHLET if periodic else CHEB_NEUMANN), cheb_dirichlet(ny)),
+        self.bc = bc
+        kinds = {"temp": (bx(CHEB_DIRICHLET if periodic else CHEB_NEUMANN), cheb_dirichlet(ny) if bc == "rbc" else cheb_dirichlet_neumann(ny)),
                  "velx": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)), "vely": (bx(CHEB_DIRICHLET), cheb_dirichlet(ny)),
                  "pres": (bx(CHEBYSHEV), chebyshev(ny)), "pseu": (bx(CHEB_NEUMANN), cheb_neumann(ny)),
                  "tempbc": (bx(CHEBYSHEV), chebyshev(ny))}

@@ -203,16 +203,42 @@ static LuVecs sweep(const Diags& a) {
   return r;
 }
 
+// PdmaPlus2::from_matrix (src/solver/pdma_plus2.rs:45-121): LU sweep of a matrix with diagonals at offsets -2..+4, packed for
+// OP_PDMA as [l2 shifted | ka | 1/mu | al | be | ga | de], each L doubles (zero tails).  d[k] = diagonal at offset k - 2,
+// indexed by the row for k >= 2 and by the column for the two sub-diagonals (ndarray `diag`).
+static std::vector<double> pdma_sweep(int n, const std::vector<double> (&d)[7], int L) {
+  const std::vector<double>&l2 = d[0], &l1 = d[1], &d0 = d[2], &u1 = d[3], &u2 = d[4], &u3 = d[5], &u4 = d[6];
+  std::vector<double> al(n, 0.0), be(n, 0.0), ga(n, 0.0), de(n, 0.0), ka(n, 0.0), mu(n, 0.0);
+  for (int i = 0; i < n; i++) {
+    const double l2i = i >= 2 ? l2[i - 2] : 0.0;
+    ka[i] = (i >= 1 ? l1[i - 1] : 0.0) - (i >= 2 ? al[i - 2] * l2i : 0.0);
+    mu[i] = d0[i] - (i >= 2 ? be[i - 2] * l2i : 0.0) - (i >= 1 ? al[i - 1] * ka[i] : 0.0);
+    if (i + 1 < n) al[i] = (u1[i] - (i >= 2 ? ga[i - 2] * l2i : 0.0) - (i >= 1 ? be[i - 1] * ka[i] : 0.0)) / mu[i];
+    if (i + 2 < n) be[i] = (u2[i] - (i >= 2 ? de[i - 2] * l2i : 0.0) - (i >= 1 ? ga[i - 1] * ka[i] : 0.0)) / mu[i];
+    if (i + 3 < n) ga[i] = (u3[i] - (i >= 1 ? de[i - 1] * ka[i] : 0.0)) / mu[i];
+    if (i + 4 < n) de[i] = u4[i] / mu[i];
+  }
+  std::vector<double> out((size_t)7 * L, 0.0);
+  for (int i = 0; i < n; i++) {
+    out[i] = i >= 2 ? l2[i - 2] : 0.0; out[(size_t)L + i] = ka[i]; out[(size_t)2 * L + i] = 1.0 / mu[i];
+    out[(size_t)3 * L + i] = al[i]; out[(size_t)4 * L + i] = be[i]; out[(size_t)5 * L + i] = ga[i]; out[(size_t)6 * L + i] = de[i];
+  }
+  return out;
+}
+
 // natural-order band coefficient vector -> its scan-layout copy (same chunking as the LU coefficients of that axis)
 static std::map<const void*, const void*>& scan_of() { static std::map<const void*, const void*> m; return m; }
 
 struct Base1 {
   int kind = 0, n = 0, m = 0;
-  bool cheb = false, composite = false;
+  bool cheb = false, composite = false;   // composite: ChebDirichlet / ChebNeumann (stencil at even offsets: pair-structured lane operators)
+  bool cdn = false;                        // ChebDirichletNeumann (bc = "hc"): three-term stencil, PdmaPlus2 solves
   int rows_phys = 0, rows_spec = 0, rows_ortho = 0;  // real rows along this axis (complex => 2 per mode)
   int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
   DVecD d_sten2, d_sten2s, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
+  std::vector<double> ca, cb;                         // cdn stencil: ortho_k = c_k + ca[k-1] c_{k-1} + cb[k-2] c_{k-2}
+  DVecD d_ca, d_cb, d_pent; int pent_L = 0;            // cdn: stencil vectors, packed PdmaPlus2 LU of S^T S (from_ortho)
   DVecD d_s2_sc, d_bd_sc, d_bu1_sc, d_bu2_sc, d_sten2s_sc;   // scan-layout copies for band ops folded into an LU solve (see run_pass)
 
   // B2 = laplace_inv; pv(i, off) = (laplace_inv_eye . laplace_inv)[i, i+off]
@@ -242,6 +268,20 @@ struct Base1 {
     }
     return b;
   }
+  // cdn: the seven diagonals (offsets -2..+4) of mat_a - c * mat_b = (pinv - c * peye) . S of src/field.rs:204-208,
+  // S[k][k] = 1, S[k+1][k] = ca[k], S[k+2][k] = cb[k]
+  void cdn_hholtz_diags(double c, std::vector<double> (&d)[7]) const {
+    auto S = [&](int r, int j) -> double { if (j < 0 || j >= m) return 0.0; return r == j ? 1.0 : (r == j + 1 ? ca[j] : (r == j + 2 ? cb[j] : 0.0)); };
+    for (int k = 0; k < 7; k++) d[k].assign(m, 0.0);
+    for (int i = 0; i < m; i++)
+      for (int off = -2; off <= 4; off++) {
+        const int j = i + off;
+        if (j < 0 || j >= m) continue;
+        const double a = pv(i, 0) * S(i, j) + pv(i, 2) * S(i + 2, j) + pv(i, 4) * S(i + 4, j);
+        const double v = a - c * S(i + 2, j);
+        d[off + 2][off >= 0 ? i : j] = v;
+      }
+  }
   int init_host(int kind_, int n_);
   int init(int C, int TPL);   // device vectors; (C, TPL) = chunking of the passes whose lanes run along this axis
   int lay_C = 1, lay_TPL = 1;
@@ -259,7 +299,7 @@ struct Base1 {
   void release() {
     const void* keys[] = {d_bd.d, d_bu1.d, d_bu2.d, d_s2.d, d_sten2s.d};
     for (auto k : keys) if (k) scan_of().erase(k);
-    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc, &d_sten2s_sc};
+    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc, &d_sten2s_sc, &d_ca, &d_cb, &d_pent};
     for (auto* v : all) v->release();
   }
 };
@@ -270,17 +310,22 @@ int Base1::init_host(int kind_, int n_) {
   kind = kind_; n = n_;
   cheb = (kind <= B2_CHEB_DIRICHLET_NEUMANN);
   composite = (kind == B2_CHEB_DIRICHLET || kind == B2_CHEB_NEUMANN);
-  if (kind == B2_CHEB_DIRICHLET_NEUMANN || kind == B2_FOURIER_C2C)
-    return fail(B2_ERR_UNSUPPORTED, "base kind not built yet (bc=\"hc\" / c2c: SURVEY 8f)");
+  cdn = (kind == B2_CHEB_DIRICHLET_NEUMANN);
+  if (kind == B2_FOURIER_C2C)
+    return fail(B2_ERR_UNSUPPORTED, "fourier_c2c is not built (no Navier2D configuration uses it)");
   if (kind < 0 || kind > B2_FOURIER_C2C) return fail(B2_ERR_ARG, "bad base kind");
   if (n < 5) return fail(B2_ERR_ARG, "n too small");
   if (cheb) {
-    m = composite ? n - 2 : n;
+    m = (composite || cdn) ? n - 2 : n;
     rows_phys = n; rows_spec = m; rows_ortho = n; N = n - 1;
   } else {
     if (n % 2) return fail(B2_ERR_UNSUPPORTED, "fourier_r2c needs even n");
     m = n / 2 + 1;
     rows_phys = n; rows_spec = 2 * m; rows_ortho = 2 * m; N = n;
+  }
+  if (cdn) {   // a_k = ((k+2)^2 - k^2) / ((k+1)^2 + (k+2)^2), b_k = a_k - 1
+    ca.assign(m, 0.0); cb.assign(m, 0.0);
+    for (int k = 0; k < m; k++) { const double kd = k; ca[k] = ((kd + 2) * (kd + 2) - kd * kd) / ((kd + 1) * (kd + 1) + (kd + 2) * (kd + 2)); cb[k] = ca[k] - 1.0; }
   }
   if (composite) {
     s2.assign(m, 0.0);
@@ -317,6 +362,31 @@ int Base1::init(int C, int TPL) {
     RET(d_bd_sc.upload(scan_layout(bd))); RET(d_bu1_sc.upload(scan_layout(bu1))); RET(d_bu2_sc.upload(scan_layout(bu2))); RET(d_s2_sc.upload(scan_layout(s2v)));
     scan_of()[d_bd.d] = d_bd_sc.d; scan_of()[d_bu1.d] = d_bu1_sc.d; scan_of()[d_bu2.d] = d_bu2_sc.d; scan_of()[d_s2.d] = d_s2_sc.d;
     RET(d_sten2s_sc.upload(scan_layout(sten2))); scan_of()[d_sten2s.d] = d_sten2s_sc.d;
+  }
+  if (cdn) {
+    std::vector<double> a(L, 0.0), b(L, 0.0);
+    for (int k = 0; k < m; k++) { a[k] = ca[k]; b[k] = cb[k]; }
+    RET(d_ca.upload(a)); RET(d_cb.upload(b));
+    // from_ortho: (S^T S) c = S^T o, pentadiagonal (funspace); solved with the PdmaPlus2 recurrences (outer diagonals zero)
+    std::vector<double> d[7];
+    for (int k = 0; k < 7; k++) d[k].assign(m, 0.0);
+    for (int j = 0; j < m; j++) {
+      d[2][j] = 1.0 + ca[j] * ca[j] + cb[j] * cb[j];
+      if (j + 1 < m) { d[3][j] = ca[j] + cb[j] * ca[j + 1]; d[1][j] = d[3][j]; }
+      if (j + 2 < m) { d[4][j] = cb[j]; d[0][j] = cb[j]; }
+    }
+    pent_L = L;
+    RET(d_pent.upload(pdma_sweep(m, d, L)));
+    // MatVecFdma of the preconditioner pinv (the same for every composite base)
+    std::vector<double> bd(L, 0.0), bu1(L, 0.0), bu2(L, 0.0);
+    for (int i = 0; i < m; i++) {
+      bd[i] = pv(i, 0);
+      if (i < m - 2) bu1[i] = pv(i, 2);
+      if (i < m - 4) bu2[i] = pv(i, 4);
+    }
+    RET(d_bd.upload(bd)); RET(d_bu1.upload(bu1)); RET(d_bu2.upload(bu2));
+    RET(d_bd_sc.upload(scan_layout(bd))); RET(d_bu1_sc.upload(scan_layout(bu1))); RET(d_bu2_sc.upload(scan_layout(bu2)));
+    scan_of()[d_bd.d] = d_bd_sc.d; scan_of()[d_bu1.d] = d_bu1_sc.d; scan_of()[d_bu2.d] = d_bu2_sc.d;
   }
   // transform tables (only when the size is one the FFT core handles)
   if (is_pow2(N) && N >= 64) {
@@ -372,7 +442,8 @@ struct b2_solver {
   b2_space* sp = nullptr;
   int type = 0;  // 0 hholtz_adi, 1 poisson
   // per axis: banded LU (Chebyshev) or reciprocal diagonal (Fourier)
-  DVecD fl[2], id[2], u1[2], u2[2], sd[2];
+  DVecD fl[2], id[2], u1[2], u2[2], sd[2], pd[2];   // pd: packed PdmaPlus2 LU (ChebDirichletNeumann axis)
+  int pd_L[2] = {0, 0};
   // poisson
   bool dense = false;
   int m0 = 0;
@@ -471,11 +542,15 @@ struct Prog {
 
   // ---- per-axis operator chains (funspace semantics) ----
   // returns the new valid length along the lane
+  void sten3(int len_out, int mode, const Base1& b) { LaneOp* o = add(OP_STEN3); o->i0 = len_out; o->i1 = mode; o->p0 = b.d_ca.d; o->p1 = b.d_cb.d; }
+  void pdma(int n, const double* packed, int L) { LaneOp* o = add(OP_PDMA); o->i0 = n; o->i1 = L; o->p0 = packed; }
   int to_ortho(const Base1& b) {
     if (b.composite) { band(b.n, b.m, 0, nullptr, -2, b.d_sten2s.d); return b.n; }
+    if (b.cdn) { sten3(b.n, 0, b); return b.n; }
     return b.rows_ortho;
   }
   int from_ortho(const Base1& b) {
+    if (b.cdn) { sten3(b.m, 1, b); pdma(b.m, b.d_pent.d, b.pent_L); return b.m; }
     if (b.composite) {
       band(b.m, b.n, 0, nullptr, 2, b.d_s2.d);
       fdma(b.m, b.d_tfl.d, b.d_tid.d, b.d_tu1.d, nullptr, FD_NOU2);
@@ -499,11 +574,12 @@ struct Prog {
   void load_stencil(const double* src, const Base1& b, double a, bool acc) {  // W [+]= a * to_ortho(src) along the lane
     LaneOp* o = add(OP_LOAD); o->p0 = src; o->a = a;
     o->i0 = b.rows_ortho;
+    if (b.cdn) err = fail(B2_ERR_UNSUPPORTED, "stencil-on-load is pair-structured (ChebDirichletNeumann uses OP_STEN3)");
     o->i2 = (acc ? LD_ACC : 0) | (b.composite ? LD_STENCIL : 0);
     o->p1 = b.d_sten2.d;
   }
   int matvec(const Base1& b) {          // MatVecFdma with pinv (Chebyshev axes only)
-    if (b.composite) { band(b.m, b.n, 0, b.d_bd.d, 2, b.d_bu1.d, 4, b.d_bu2.d); return b.m; }
+    if (b.composite || b.cdn) { band(b.m, b.n, 0, b.d_bd.d, 2, b.d_bu1.d, 4, b.d_bu2.d); return b.m; }
     return b.rows_spec;
   }
 };
@@ -881,6 +957,11 @@ static int hholtz_create(b2_space* sp, double c0, double c1, b2_solver** out) {
         mat.up2[i] = a.up2[i] - bm.up2[i] * c[ax];
       }
       RET(upload_lu(sweep(mat), b, &s->fl[ax], &s->id[ax], &s->u1[ax], &s->u2[ax]));
+    } else if (b.cdn) {  // PdmaPlus2::from_matrix(mat), src/solver/hholtz_adi.rs:64
+      std::vector<double> d[7];
+      b.cdn_hholtz_diags(c[ax], d);
+      s->pd_L[ax] = L;
+      RET(s->pd[ax].upload(pdma_sweep(b.m, d, L)));
     } else if (!b.cheb) {  // Sdma: dia = 1 - c * (-k^2), src/solver/sdma.rs:37-46
       std::vector<double> sd(L, 0.0);
       for (int k = 0; k < b.m; k++) sd[k] = 1.0 / (1.0 - (-(double)k * k) * c[ax]);
@@ -894,19 +975,16 @@ static int hholtz_create(b2_space* sp, double c0, double c1, b2_solver** out) {
   return B2_OK;
 }
 
+static void emit_hh_axis(Prog& p, const b2_solver* s, int ax);
 // HholtzAdi::solve_par, src/solver/hholtz_adi.rs:149-169 (axis operators commute; y first here)
 static int hholtz_solve(b2_solver* s, const double* in, double* out) {
   b2_space* sp = s->sp;
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
-  Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1);
-  if (b1.composite) y.fdma(b1.m, s->fl[1].d, s->id[1].d, s->u1[1].d, s->u2[1].d, 0);
-  else y.scalevec(b1.rows_spec, s->sd[1].d, 1);
-  y.store(sp->tmp[0], l, ST_TRANS);
+  Prog y; y.load(in, b1.rows_ortho); emit_hh_axis(y, s, 1);
+  y.store(sp->tmp[0], b1.rows_spec, ST_TRANS);
   RET(run_pass(sp, 0, y));
-  Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0);
-  if (b0.composite) x.fdma(b0.m, s->fl[0].d, s->id[0].d, s->u1[0].d, s->u2[0].d, 0);
-  else x.scalevec(b0.rows_spec, s->sd[0].d, 1);
-  x.store(out, l, ST_TRANS);
+  Prog x; x.load(sp->tmp[0], b0.rows_ortho); emit_hh_axis(x, s, 0);
+  x.store(out, b0.rows_spec, ST_TRANS);
   return run_pass(sp, 1, x);
 }
 
@@ -1175,6 +1253,7 @@ static void emit_hh_axis(Prog& p, const b2_solver* s, int ax) {
   const Base1& b = s->sp->b[ax];
   p.matvec(b);
   if (b.composite) p.fdma(b.m, s->fl[ax].d, s->id[ax].d, s->u1[ax].d, s->u2[ax].d, 0);
+  else if (b.cdn) p.pdma(b.m, s->pd[ax].d, s->pd_L[ax]);   // hholtz_adi.rs:64
   else p.scalevec(b.rows_spec, s->sd[ax].d, 1);
 }
 
@@ -1603,7 +1682,8 @@ static int nav_alloc(b2_space* sp, double** p) { return alloc_zero(sp, p); }
 
 int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double dt, double aspect, const char* bc,
                        int periodic, const double* lam, const double* fwd, const double* bwd, b2_navier** out) {
-  if (!bc || std::string(bc) != "rbc") return fail(B2_ERR_UNSUPPORTED, "only bc=\"rbc\" is built (\"hc\": SURVEY 8f item 2)");
+  if (!bc || (std::string(bc) != "rbc" && std::string(bc) != "hc")) return fail(B2_ERR_ARG, "Boundary condition type not recognized (\"rbc\" or \"hc\", navier.rs:238-252)");
+  const bool hc = std::string(bc) == "hc";
   b2_navier* nv = new b2_navier();
   nv->ctx = ctx; nv->nx = nx; nv->ny = ny; nv->periodic = periodic;
   nv->ra = ra; nv->pr = pr; nv->dt = dt; nv->scale[0] = aspect; nv->scale[1] = 1.0;
@@ -1615,7 +1695,7 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
   const int kx_ortho = periodic ? B2_FOURIER_R2C : B2_CHEBYSHEV;
   const int kx_pseu = periodic ? B2_FOURIER_R2C : B2_CHEB_NEUMANN;
   RET(b2_space2_create(ctx, kx_vel, nx, B2_CHEB_DIRICHLET, ny, &nv->sp_vel));     // navier.rs:235-236 / 356-357
-  RET(b2_space2_create(ctx, kx_temp, nx, B2_CHEB_DIRICHLET, ny, &nv->sp_temp));   // :240 / :361
+  RET(b2_space2_create(ctx, kx_temp, nx, hc ? B2_CHEB_DIRICHLET_NEUMANN : B2_CHEB_DIRICHLET, ny, &nv->sp_temp));   // :240,246-247 / :361,367
   RET(b2_space2_create(ctx, kx_ortho, nx, B2_CHEBYSHEV, ny, &nv->sp_ortho));      // :254,256 / :375,377
   RET(b2_space2_create(ctx, kx_pseu, nx, B2_CHEB_NEUMANN, ny, &nv->sp_pseu));     // :255 / :376
   RET(b2_field_create(nv->sp_vel, &nv->velx)); RET(b2_field_create(nv->sp_vel, &nv->vely));
@@ -1636,9 +1716,20 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
     RET(b2_space_coords(so, 1, y.data()));
     const double x1 = y[0], x2 = y[ny - 1], y1 = 0.5, y2 = -0.5;
     const double m = (y2 - y1) / (x2 - x1), n = (y1 * x2 - y2 * x1) / (x2 - x1);
-    for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) v[(size_t)i * ny + j] = m * y[j] + n;
     int row0 = 0, cnt = nx;
-    RET(b2_field_local_rows(nv->tempbc, B2_SHAPE_PHYSICAL, &row0, &cnt));   // every row is the same profile
+    RET(b2_field_local_rows(nv->tempbc, B2_SHAPE_PHYSICAL, &row0, &cnt));
+    if (!hc) {   // every row is the same profile
+      for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) v[(size_t)i * ny + j] = m * y[j] + n;
+    } else {     // bc_hc / bc_hc_periodic (boundary_conditions.rs:103-135 / :165-195): -0.5 cos(2 pi (x - x0) / L) at the bottom,
+                 // T = T' = 0 at the top: a parabola in y with its vertex at the top wall; L = x[last] - x[0] in both variants
+      std::vector<double> x(nx);
+      RET(b2_space_coords(so, 0, x.data()));
+      const double len = x[nx - 1] - x[0], pi = 3.14159265358979323846;
+      for (int i = 0; i < cnt; i++) {
+        const double fx = -0.5 * std::cos(2.0 * pi * (x[row0 + i] - x[0]) / len), a = fx / ((x1 - x2) * (x1 - x2));
+        for (int j = 0; j < ny; j++) v[(size_t)i * ny + j] = a * (y[j] - x2) * (y[j] - x2);
+      }
+    }
     RET(b2_field_set_v_host(nv->tempbc, v.data(), (size_t)cnt * ny * sizeof(double)));
     RET(b2_forward(nv->tempbc));
     RET(b2_backward(nv->tempbc));

@@ -52,6 +52,10 @@ enum LaneOpCode {
   OP_SCALE = 13,   // W *= a
   OP_PREBAND = 14, // an OP_BAND folded into the OP_FDMA that follows it (set by the launcher, fast geometry only): no-op here
   OP_BANDC = 15,   // an OP_BAND in chunk-streaming form (set by the launcher, fast geometry only): see band_chunk
+  OP_STEN3 = 16,   // ChebDirichletNeumann stencil (odd offsets): i1 = 0: y_j = x_j + a_{j-1} x_{j-1} + b_{j-2} x_{j-2} (to_ortho, S);
+                   //   i1 = 1: y_k = x_k + a_k x_{k+1} + b_k x_{k+2} (S^T);  i0 = len_out, p0 = a, p1 = b (natural order)
+  OP_PDMA = 17,    // PdmaPlus2 solve (7 diagonals -2..+4, src/solver/pdma_plus2.rs:123-157): i0 = n, i1 = pitch L of the packed LU
+                   //   p0 = [l2 shifted | ka | 1/mu | al | be | ga | de], each L doubles
 };
 enum { LD_ACC = 1, LD_PLAIN = 2, LD_MUL = 4, LD_STENCIL = 8,   // LD_STENCIL: value = src[j] + p1[j] * src[j-2]
        LD_TMA = 16,          // set by the launcher: the slab streams through the warps' staging slots (load_warps)
@@ -1062,6 +1066,74 @@ __device__ __noinline__ void op_rfft(const LaneProg& P, const LaneOp& op, double
   }
 }
 
+// ChebDirichletNeumann stencil (bc = "hc"): the three-term stencil couples neighbouring elements, so the pair structure of
+// the other banded operators does not apply; element-strided, register-staged (not on any BASELINE configuration's path).
+template <int CP, int LN>
+__device__ __noinline__ void op_sten3(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  const int TPL = P.TPL, LP = P.LP;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  const double* __restrict__ ca = (const double*)op.p0; const double* __restrict__ cb = (const double*)op.p1;
+  const int len_out = op.i0, mode = op.i1;
+  double* w = W + 4 * l;
+  double y[2 * CP];
+#pragma unroll
+  for (int i = 0; i < 2 * CP; i++) {
+    const int e = q + i * TPL;
+    double v = 0.0;
+    if (e < LP && e < len_out) {
+      v = w[Lay<LN>::eix(e)];
+      if (mode == 0) {
+        if (e >= 1) v = fma(ldg(ca + e - 1), w[Lay<LN>::eix(e - 1)], v);
+        if (e >= 2) v = fma(ldg(cb + e - 2), w[Lay<LN>::eix(e - 2)], v);
+      } else {
+        if (e + 1 < LP) v = fma(ldg(ca + e), w[Lay<LN>::eix(e + 1)], v);
+        if (e + 2 < LP) v = fma(ldg(cb + e), w[Lay<LN>::eix(e + 2)], v);
+      }
+    }
+    y[i] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2 * CP; i++) {
+    const int e = q + i * TPL;
+    if (e < LP) w[Lay<LN>::eix(e)] = y[i];
+  }
+  __syncthreads();
+}
+
+// PdmaPlus2::solve_lane (src/solver/pdma_plus2.rs:123-157): forward elimination (second order) and back substitution
+// (fourth order) over the elements of a lane; one thread per lane ("one thread per system") -- bc = "hc" only.
+template <int LN>
+__device__ __noinline__ void op_pdma(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  const int n = op.i0, L = op.i1;
+  if ((int)threadIdx.x < LN) {
+    double* w = W + 4 * threadIdx.x;
+    const double* __restrict__ l2 = (const double*)op.p0; const double* __restrict__ ka = l2 + L; const double* __restrict__ imu = ka + L;
+    const double* __restrict__ al = imu + L; const double* __restrict__ be = al + L; const double* __restrict__ ga = be + L; const double* __restrict__ de = ga + L;
+    double z1 = 0.0, z2 = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < n; i++) {
+      double t = fma(-z2, ldg(l2 + i), w[Lay<LN>::eix(i)]);
+      t = fma(-z1, ldg(ka + i), t);
+      const double z = t * ldg(imu + i);
+      w[Lay<LN>::eix(i)] = z;
+      z2 = z1; z1 = z;
+    }
+    double x1 = 0.0, x2 = 0.0, x3 = 0.0, x4 = 0.0;
+#pragma unroll 4
+    for (int i = n - 1; i >= 0; i--) {
+      double t = fma(-x4, ldg(de + i), w[Lay<LN>::eix(i)]);
+      t = fma(-x3, ldg(ga + i), t);
+      t = fma(-x2, ldg(be + i), t);
+      const double x = fma(-x1, ldg(al + i), t);
+      w[Lay<LN>::eix(i)] = x;
+      x4 = x3; x3 = x2; x2 = x1; x1 = x;
+    }
+    for (int i = n; i < P.LP; i++) w[Lay<LN>::eix(i)] = 0.0;
+  }
+  __syncthreads();
+}
+
 template <int LN>
 __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op, double* __restrict__ W, int g, int lb) {
   const int TPL = P.TPL, LP = P.LP;
@@ -1178,6 +1250,8 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
       case OP_BANDC:
         if constexpr (TPLC > 0) band_chunk<E, LN, TPLC>(P, op, W);
         break;
+      case OP_STEN3: op_sten3<E + 1, LN>(P, op, W); break;
+      case OP_PDMA: op_pdma<LN>(P, op, W); break;
       default: op_pointwise<LN>(P, op, W, g, lb); break;
     }
     if (P.prof && threadIdx.x == 0) {

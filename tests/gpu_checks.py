@@ -7,7 +7,7 @@ import rustpde_mpi_b200 as b2
 from oracle import rustpde_oracle as o
 
 TOL = 1e-10
-KIND_NAME = {0: "ch", 1: "cd", 2: "cn", 4: "r2c"}
+KIND_NAME = {0: "ch", 1: "cd", 2: "cn", 3: "cdn", 4: "r2c"}
 
 
 def relerr(a, ref):
@@ -127,10 +127,10 @@ def check_hholtz_tensor(k0, n0, k1, n1, c=(0.37, 1.3), seed=9):
     return relerr(hg.solve(rhs).get(), ho.solve(rhs))
 
 
-def make_navier_pair(nx, ny, ra, pr, dt, aspect, periodic, init="modes"):
+def make_navier_pair(nx, ny, ra, pr, dt, aspect, periodic, init="modes", bc="rbc"):
     eig = None if periodic else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0 / aspect ** 2)
-    no = o.Navier2D(nx, ny, ra, pr, dt, aspect, "rbc", periodic=periodic, pois_eig=eig)
-    ng = b2.Navier2D(nx, ny, ra, pr, dt, aspect, "rbc", periodic=periodic)
+    no = o.Navier2D(nx, ny, ra, pr, dt, aspect, bc, periodic=periodic, pois_eig=eig)
+    ng = b2.Navier2D(nx, ny, ra, pr, dt, aspect, bc, periodic=periodic)
     for nav in (no, ng):
         if init == "modes":
             nav.set_velocity(0.2, 1.0, 1.0)
@@ -149,8 +149,8 @@ def navier_errors(no, ng):
     return out
 
 
-def check_navier(nx, ny, steps, periodic=False, ra=1e5, dt=0.01, init="modes"):
-    no, ng = make_navier_pair(nx, ny, ra, 1.0, dt, 1.0, periodic, init)
+def check_navier(nx, ny, steps, periodic=False, ra=1e5, dt=0.01, init="modes", bc="rbc"):
+    no, ng = make_navier_pair(nx, ny, ra, 1.0, dt, 1.0, periodic, init, bc)
     for _ in range(steps):
         no.update()
     ng.update(steps)

@@ -63,6 +63,15 @@ elif case == "variants":
     f.vhat = a
     out = np.empty((15, 15)); f.vhat_into(out)
     assert np.array_equal(out, a)
+elif case == "hc":
+    # bc = "hc": ChebDirichletNeumann temperature base (three-term stencil OP_STEN3, PdmaPlus2 solves OP_PDMA)
+    for sp in [(2, 65, 3, 65), (4, 64, 3, 65)]:
+        for fn in (g.check_roundtrip_layout, g.check_to_ortho, g.check_from_ortho, g.check_backward, g.check_forward, g.check_hholtz):
+            e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
+    errs = g.check_navier(65, 65, 2, False, bc="hc")
+    assert max(errs.values()) < g.TOL, errs
+    errs = g.check_navier(64, 65, 2, True, bc="hc")
+    assert max(errs.values()) < g.TOL, errs
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
@@ -74,7 +83,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]

@@ -102,3 +102,21 @@ def test_navier_periodic_random_256x129():
 def test_diagnostics_nu_nuvol_re(periodic):
     """callback() diagnostics: transforms / projections / derivatives on the GPU, weighted means on the host."""
     assert g.check_diagnostics(64 if periodic else 65, 65, 3, periodic) < 1e-10
+
+
+# ---- bc = "hc" (SURVEY 8a row M, 8f item 2): ChebDirichletNeumann temperature base, PdmaPlus2 Helmholtz solves ----
+HC_SPACES = [(2, 65, 3, 65), (2, 129, 3, 257), (4, 128, 3, 129), (1, 65, 3, 1025)]
+
+
+@pytest.mark.parametrize("sp", HC_SPACES, ids=["-".join(f"{g.KIND_NAME[s[i]]}{s[i+1]}" for i in (0, 2)) for s in HC_SPACES])
+@pytest.mark.parametrize("op", ["forward", "backward", "to_ortho", "from_ortho", "hholtz"])
+def test_hc_field_ops(sp, op):
+    """cdn axis: three-term stencil (odd offsets), pentadiagonal from_ortho, PdmaPlus2 (pdma_plus2.rs:45-157) in HholtzAdi."""
+    assert getattr(g, "check_" + op)(*sp) < g.TOL
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_navier_hc_steps(periodic):
+    """Navier2D::new_confined / new_periodic with bc = "hc" (navier.rs:245-252, 366-372; bc_hc boundary field)."""
+    errs = g.check_navier(128 if periodic else 129, 129, 5, periodic, bc="hc")
+    assert max(errs.values()) < g.TOL, errs
