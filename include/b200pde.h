@@ -135,6 +135,7 @@ int b2_navier_field(b2_navier* nav, int which, b2_field** out);
 int b2_navier_update(b2_navier* nav, int nsteps);            /* Integrate::update, navier.rs:438-466 */
 int b2_navier_div_norm(b2_navier* nav, double* out);         /* navier_eq.rs:32-49 (exit() NaN guard); the global norm on every rank */
 int b2_navier_get_time(const b2_navier* nav, double* t);
+int b2_navier_set_time(b2_navier* nav, double t);            /* restart: `self.time = read_scalar(.., "time")`, navier_io.rs:30 */
 int b2_navier_set_mode(b2_navier* nav, int mode);            /* bit0: fused schedule (default on); bit1: no CUDA-graph replay */
 /* schedule facts for bench.py: out[8] = {parity-block GEMMs, P0, P1, m0, ce, co, parallel branches, launches per step} */
 int b2_navier_info(const b2_navier* nv, long long* out8);

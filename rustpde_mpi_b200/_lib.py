@@ -70,6 +70,7 @@ SYMBOLS = {
     "b2_navier_update": (_I, [_P, _I]),
     "b2_navier_div_norm": (_I, [_P, _DP]),
     "b2_navier_get_time": (_I, [_P, _DP]),
+    "b2_navier_set_time": (_I, [_P, _D]),
     "b2_navier_set_mode": (_I, [_P, _I]),
     "b2_navier_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "b2_navier_info": (_I, [_P, C.POINTER(C.c_longlong)]),

@@ -687,6 +687,59 @@ class Navier2D:
         keys = ("parity_blocks", "P0", "P1", "m0", "ce", "co", "branches", "launches_per_step")
         return dict(zip(keys, (int(x) for x in v)))
 
+    # snapshot / restart (src/navier_stokes/navier_io.rs:21-62; MPI: gathered to / scattered from rank 0, src/field_mpi/io.rs)
+    def write(self, filename):
+        """``Navier2D::write``: backward() the four state fields, then ``ux, uy, temp, pres, tempbc`` groups and the scalars.
+        With several ranks the arrays are gathered and rank 0 writes (src/navier_stokes_mpi/navier_io.rs)."""
+        from . import snapshot as sn
+
+        data = {}
+        fields = list(sn.FIELD_GROUPS) + [("tempbc", "tempbc")]
+        for attr, group in fields:
+            f = getattr(self, attr)
+            if attr != "tempbc":
+                f.backward()
+            v = self.ctx.all_gather_rows(f.v) if self.nranks > 1 else f.v
+            vhat = self.ctx.all_gather_rows(f.vhat) if self.nranks > 1 else f.vhat
+            data.update(sn.field_datasets(group, f.x[0], f.x[1], v, vhat))
+        data["time"] = self.get_time()
+        nu = np.sqrt(self.pr / (self.ra / 8.0)); ka = np.sqrt(1.0 / ((self.ra / 8.0) * self.pr))   # functions.rs:12-21, height 2
+        data.update({"ra": self.ra, "pr": self.pr, "nu": nu, "ka": ka})
+        if self.ctx.rank == 0:
+            sn.save_datasets(filename, data)
+        if self.nranks > 1:
+            self.ctx.barrier()
+
+    def read(self, filename):
+        """``Navier2D::read``: ``vhat`` of ux, uy, temp, pres (interpolated spectrally when the snapshot has another
+        resolution, src/field/io.rs:151-176), ``backward()``, and ``time``."""
+        from . import snapshot as sn
+
+        data = sn.load_datasets(filename)
+        for attr, group in sn.FIELD_GROUPS:
+            f = getattr(self, attr)
+            shape, cx = f.space.shape(SPECTRAL)
+            vh = sn.read_vhat(data, group, shape, cx, f.space.bases[0][0] == FOURIER_R2C)
+            f.vhat = vh[f.local_slice(SPECTRAL)]
+            f.backward()
+        self.set_time(float(data["time"]))
+
+    def write_unwrap(self, filename):
+        try:
+            self.write(filename)
+        except Exception as e:  # noqa: BLE001 - navier_io.rs:57-62 prints and carries on
+            print(f"Error while writing file {filename!r}. Error: {e}")
+
+    def read_unwrap(self, filename):
+        try:
+            self.read(filename)
+            print(f"Reading file {filename!r} was successfull.")
+        except Exception as e:  # noqa: BLE001
+            print(f"Error while reading file {filename!r}. Error: {e}")
+
+    def set_time(self, t):
+        check(lib().b2_navier_set_time(self._h, float(t)))
+
     def state(self):
         """This rank's slabs of the four spectral state arrays."""
         return {k: getattr(self, k).vhat for k in ("temp", "velx", "vely", "pres")}

@@ -2173,6 +2173,7 @@ int b2_navier_div_norm(b2_navier* nv, double* out) {
   return B2_OK;
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
+int b2_navier_set_time(b2_navier* nv, double t) { nv->time = t; return B2_OK; }
 int b2_navier_set_mode(b2_navier* nv, int mode) {
   // bit 0: fused schedule; bit 1: disable CUDA-graph replay; bit 2: disable parallel branches
   nv->fused = mode & 1; nv->use_graph = !(mode & 2); nv->branches = !(mode & 4); nv->warm_steps = 0;

@@ -72,6 +72,34 @@ elif case == "hc":
     assert max(errs.values()) < g.TOL, errs
     errs = g.check_navier(64, 65, 2, True, bc="hc")
     assert max(errs.values()) < g.TOL, errs
+elif case == "snapshot":
+    # write / read (navier_io.rs:21-62) through the C ABI: same grid = identical state, other grid = interpolate_2d + backward
+    import tempfile, os
+    from rustpde_mpi_b200 import snapshot as sn
+    d = tempfile.mkdtemp()
+    for periodic, (nx, ny), (nx2, ny2) in ((False, (65, 65), (129, 65)), (True, (64, 65), (128, 65))):
+        a = b2.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+        a.update(2)
+        fn = os.path.join(d, f"snap{int(periodic)}.npz")
+        a.write(fn)
+        keys = set(sn.load_datasets(fn))
+        grp = lambda g: {f"{g}/{k}" for k in (("x", "dx", "y", "dy", "v") + (("vhat_re", "vhat_im") if periodic else ("vhat",)))}
+        assert keys == set().union(*(grp(g) for g in ("ux", "uy", "temp", "pres", "tempbc"))) | {"time", "ra", "pr", "nu", "ka"}, keys
+        b = b2.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+        b.read(fn)
+        assert abs(b.get_time() - a.get_time()) < 1e-15
+        for k, v in a.state().items():
+            assert np.array_equal(b.state()[k], v), k
+        assert np.abs(b.temp.v - a.temp.v).max() < 1e-12
+        c = b2.Navier2D(nx2, ny2, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+        c.read(fn)
+        for k, v in a.state().items():
+            want = sn.interpolate_2d(v, c.state()[k].shape, periodic)
+            assert np.array_equal(c.state()[k], want), k
+    # oracle restatement of interpolate_2d (src/field/io.rs:151-176)
+    old = np.arange(12.0).reshape(3, 4)
+    new = sn.interpolate_2d(old, (5, 3), True)
+    assert new.shape == (5, 3) and np.array_equal(new[:3, :3], old[:, :3] * (4 / 2)) and not new[3:].any()
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
@@ -83,7 +111,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
