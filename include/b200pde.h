@@ -33,7 +33,7 @@ enum b2_base_kind {
   B2_CHEBYSHEV = 0,
   B2_CHEB_DIRICHLET = 1,
   B2_CHEB_NEUMANN = 2,
-  B2_CHEB_DIRICHLET_NEUMANN = 3, /* bc="hc": not built yet */
+  B2_CHEB_DIRICHLET_NEUMANN = 3, /* bc="hc": three-term stencil, PdmaPlus2 solves (src/solver/pdma_plus2.rs) */
   B2_FOURIER_R2C = 4,
   B2_FOURIER_C2C = 5 /* not on the Navier2D path */
 };
@@ -127,7 +127,7 @@ int b2_host_poisson_matrices(int kind0, int n0, double c0, double* a0, double* c
 
 /* ---- Navier2D (src/navier_stokes/navier.rs:215-466; MPI twin src/navier_stokes_mpi/navier.rs) ---- */
 int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double dt, double aspect,
-                       const char* bc /* "rbc" */, int periodic, const double* lam, const double* fwd,
+                       const char* bc /* "rbc" or "hc" */, int periodic, const double* lam, const double* fwd,
                        const double* bwd, b2_navier** out);
 int b2_navier_destroy(b2_navier* nav);
 /* which: 0 temp, 1 velx, 2 vely, 3 pres, 4 pseu, 5 tempbc */

@@ -15,7 +15,7 @@
 // skew between tile-row slots.  A_b is packed on the host in fragment order ([m tile][k stage][k4 step][8-row
 // fragment][lane]), one 8 KB bulk copy per block and stage.  Arithmetic: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05
 // has no FP64 path), 16 warps x (32 x 32) outputs, accumulators in registers, a 4-stage full/empty mbarrier pipeline
-// without CTA barriers (one thread refills a buffer as soon as all warps have released it).
+// without CTA barriers (bounded skew of two stages between the warps; one thread refills released buffers).
 // The epilogue writes 16-byte pieces (full 32-byte sectors per quad pair) straight into the tiled destination --
 // with several GPUs into the slab of the rank that owns the output rows (the pencil exchange rides on the epilogue).
 #pragma once
@@ -115,16 +115,15 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
 #pragma unroll
     for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+  // No CTA barrier in the main loop, but a bounded skew: a warp starts stage ks only when every warp has finished stage
+  // ks - 2.  (The warp scheduler prefers the highest warp id; without the bound the favoured warps run ahead until they
+  // starve on data that is only requested once the slowest warp releases a buffer -- every round then pays the copy
+  // latency.  With it, the refill of a buffer is always requested two stages before anybody needs it.)
   for (int ks = 0; ks < nks; ks++) {
     const int s = ks % G_NSTAGE;
-    if (tid == 0) {
-      // refill every buffer that all warps have released (no CTA barrier in this loop: the warps drift apart by up to
-      // a stage, which keeps the DMMA pipe fed across stage boundaries); stage ks itself must be on its way before
-      // anybody waits for it
-      while (issued < nks && (issued <= ks || mbar_test(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1)))) {
-        if (issued >= G_NSTAGE) mbar_wait(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1));
-        issue(issued); issued++;
-      }
+    if (ks >= 2) mbar_wait(&empty[(ks - 2) % G_NSTAGE], (unsigned)(((ks - 2) / G_NSTAGE) & 1));
+    if (tid == 0) {   // refill every buffer that all warps have released
+      while (issued < nks && mbar_test(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1))) { issue(issued); issued++; }
     }
     mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
     const double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;

@@ -81,3 +81,37 @@ def test_no_device_fails_loudly():
         pass
     with pytest.raises(rustpde_mpi_b200.B2Error):
         rustpde_mpi_b200.Context(0)
+
+
+def test_rust_sys_bindings_cover_the_header():
+    """rust/b200pde-sys/src/lib.rs is generated from the header (tools/gen_rust_sys.py; no Rust toolchain in this image): every
+    symbol is declared, with the header's argument count, and the committed file is what the generator produces."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    path = os.path.join(ROOT, "rust", "b200pde-sys", "src", "lib.rs")
+    text = open(path).read()
+    decl = dict(re.findall(r"pub fn (b2_[a-z0-9_]+)\((.*?)\) ->", text))
+    assert sorted(decl) == header_symbols()
+    for ret, name, args in gen.prototypes():
+        n_c = 0 if args.strip() == "void" else len(args.split(","))
+        n_r = 0 if not decl[name].strip() else len(decl[name].split(","))
+        assert n_c == n_r, name
+    before = text
+    gen.main()
+    assert open(path).read() == before, "rust/b200pde-sys/src/lib.rs is stale: run tools/gen_rust_sys.py"
+
+
+def test_cpp_driver_compiles_against_the_header():
+    """examples/cpp_driver/navier_rbc.cpp: plain C++ over the C ABI (no CUDA headers); it must compile and link here."""
+    import subprocess
+    import tempfile
+
+    build.build()
+    out = os.path.join(tempfile.mkdtemp(), "navier_rbc")
+    libdir = os.path.join(ROOT, "rustpde_mpi_b200")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cpp_driver", "navier_rbc.cpp"),
+                    "-o", out, "-L", libdir, "-lb200pde", "-ldl", f"-Wl,-rpath,{libdir}"], check=True)
+    assert os.path.exists(out)
