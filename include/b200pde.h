@@ -84,6 +84,13 @@ int b2_array_sumsq_local(const b2_array* a, double* out);
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes);
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes);
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x); /* y += alpha x (same shape kind) */
+/* diagnostics on the device (callback(): src/navier_stokes/functions.rs:146-233, src/field/average.rs:26-59, src/field_mpi/average.rs:15-61) */
+int b2_field_array(b2_field* f, int which /* 0 = v, 1 = vhat */, b2_array** out /* borrowed */);
+int b2_array_copy(b2_array* dst, const b2_array* src);                                            /* same padded shape */
+int b2_array_combine(b2_array* dst, const b2_array* a, const b2_array* b, int op, double alpha);   /* 0: alpha a b; 1: alpha sqrt(a^2+b^2); 2: dst + alpha a b */
+/* dx-weighted sums over this rank's rows of a real array: mode 0: out[0] = sum_ij w0[i] w1[j] a[i][j]; mode 1: out[j] = sum_i w0[i] a[i][j]
+ * (w0: one weight per LOCAL row, w1 / out: one per column; the caller adds the ranks' partial sums -- all_gather_sum) */
+int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const double* w1, int mode, double* out);
 int b2_array_norm2(const b2_array* a, double* out);              /* sqrt(sum |a|^2) of the GLOBAL array (collective over the ranks), functions.rs:24-35 */
 
 /* ---- Field2 (src/field.rs:59-129) ---- */

@@ -44,6 +44,10 @@ SYMBOLS = {
     "b2_array_get_host": (_I, [_P, _P, _SZ]),
     "b2_array_axpy": (_I, [_P, _D, _P]),
     "b2_array_norm2": (_I, [_P, _DP]),
+    "b2_field_array": (_I, [_P, _I, _PP]),
+    "b2_array_copy": (_I, [_P, _P]),
+    "b2_array_combine": (_I, [_P, _P, _P, _I, _D]),
+    "b2_array_weighted_sum": (_I, [_P, _DP, _DP, _I, _DP]),
     "b2_field_create": (_I, [_P, _PP]),
     "b2_field_destroy": (_I, [_P]),
     "b2_field_set_v_host": (_I, [_P, _P, _SZ]),

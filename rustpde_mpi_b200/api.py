@@ -80,11 +80,12 @@ class Context:
         import torch
         import torch.distributed as dist
 
-        t = torch.tensor([float(x)], dtype=torch.float64)
+        scalar = np.ndim(x) == 0
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), dtype=torch.float64)
         if dist.get_backend() == "nccl":
             t = t.cuda(self.device)
         dist.all_reduce(t)
-        return float(t.item())
+        return float(t.item()) if scalar else t.cpu().numpy()
 
     def all_gather_rows(self, a):
         """Concatenate the ranks' row slabs (gather(local) == global)."""
@@ -538,7 +539,7 @@ class Navier2D:
     def close(self):
         """Free every device array, solver and space of this solver."""
         if getattr(self, "_h", None):
-            for k in ("_field", "_temp_twin", "_diag_a", "_diag_b"):
+            for k in ("_field", "_field2", "_temp_twin", "_diag_a", "_diag_b"):
                 if getattr(self, k, None) is not None:
                     setattr(self, k, None)
             _release(lib().b2_navier_destroy, self._h)
@@ -604,62 +605,81 @@ class Navier2D:
         """navier.rs:482-489: break when |div| is NaN."""
         return bool(np.isnan(self.div_norm()))
 
-    # diagnostics (SURVEY 8f item 1): the transforms / projections / derivatives run on the GPU through the C ABI,
-    # the dx-weighted means of src/field/average.rs are taken on the host from the downloaded physical field
-    # (callback-only work, once per save interval; single rank).
+    # diagnostics (SURVEY 8f item 1; src/navier_stokes/functions.rs:146-233): everything runs on the device through the C ABI --
+    # transforms, projections, derivatives, the pointwise products and the dx-weighted means of src/field/average.rs
+    # (b2_array_weighted_sum over this rank's rows); with several ranks the partial sums are added across the ranks like
+    # `all_gather_sum` in src/field_mpi/average.rs:15-61.  Only scalars (and one row profile for Nu) reach the host.
+    def _borrow(self, f, which):
+        h = C.c_void_p()
+        check(lib().b2_field_array(f._h, which, C.byref(h)))
+        return DeviceArray(f.space, PHYSICAL if which == 0 else SPECTRAL, handle=h, owner=False)
+
     def _diag_field(self):
-        if self.nranks != 1:
-            raise B2Error("diagnostics are single-rank in this round (gather the state and use rank 0)")
         if getattr(self, "_field", None) is None:
             bx = fourier_r2c(self.nx) if self.periodic else chebyshev(self.nx)
             self._field = Field2(Space2(bx, chebyshev(self.ny), ctx=self.ctx))
+            self._field2 = Field2(Space2(bx, chebyshev(self.ny), ctx=self.ctx))
             # the solver's own fields are borrowed handles without a standalone space: projections go through a twin
             self._temp_twin = Field2(Space2(*self.temp.space.bases, ctx=self.ctx))
+            self._diag_a = DeviceArray(self._temp_twin.space, ORTHO)
+            self._diag_b = DeviceArray(self._field.space, ORTHO)
             height = self.scale[1] * 2.0   # functions.rs:12-21
             self.nu = float(np.sqrt(self.pr / (self.ra / height ** 3.0)))
             self.ka = float(np.sqrt(1.0 / ((self.ra / height ** 3.0) * self.pr)))
+            f = self._field
+            lo = f.local_slice(PHYSICAL)
+            self._w0 = np.ascontiguousarray((f.dx[0] / abs(f.x[0][-1] - f.x[0][0]))[lo])   # src/field/average.rs:26-35: dx / length
+            self._w1 = np.ascontiguousarray(f.dx[1] / abs(f.x[1][-1] - f.x[1][0]))
         return self._field
 
-    @staticmethod
-    def _average_axis(f, v, axis):   # src/field/average.rs:26-35
-        w = f.dx[axis] / abs(f.x[axis][-1] - f.x[axis][0])
-        return np.tensordot(w, v, axes=(0, axis))
+    def _wsum(self, arr, mode):
+        """this rank's part of average(v) (mode 0) or average_axis(v, 0) (mode 1), then summed over the ranks"""
+        out = np.zeros(len(self._w1) if mode == 1 else 1)
+        check(lib().b2_array_weighted_sum(arr._h, _dp(self._w0), _dp(self._w1), mode, _dp(out)))
+        out = self.ctx.all_reduce_sum(out)
+        return out if mode == 1 else float(out[0])
 
-    @classmethod
-    def _average(cls, f, v):         # src/field/average.rs:53-59
-        return float(np.sum(cls._average_axis(f, v, 0) * f.dx[1] / abs(f.x[1][-1] - f.x[1][0])))
-
-    def _temp_ortho(self):
-        self._temp_twin.vhat = self.temp.vhat
-        return self._temp_twin.to_ortho().get() + self.tempbc.vhat   # tempbc lives in the orthonormal space already
+    def _temp_ortho_into(self, f):
+        """f.vhat = to_ortho(temp) + to_ortho(tempbc)  (tempbc lives in the orthonormal space already)"""
+        check(lib().b2_array_copy(self._borrow(self._temp_twin, 1)._h, self._borrow(self.temp, 1)._h))
+        self._temp_twin.to_ortho(out=self._diag_a)
+        fv = self._borrow(f, 1)
+        check(lib().b2_array_copy(fv._h, self._diag_a._h))
+        fv.axpy(1.0, self._borrow(self.tempbc, 1))
 
     def eval_nu(self):
         """Nusselt number from the heat flux at the plates (functions.rs:146-168)."""
         f = self._diag_field()
-        f.vhat = self._temp_ortho()
-        f.vhat = f.gradient([0, 1], None).get() * (-2.0 / self.scale[1])
+        self._temp_ortho_into(f)
+        f.gradient([0, 1], [1.0, -self.scale[1] / 2.0], out=self._diag_b)   # d/dy * (-2 / scale_y)
+        check(lib().b2_array_copy(self._borrow(f, 1)._h, self._diag_b._h))
         f.backward()
-        x_avg = self._average_axis(f, f.v, 0)
+        x_avg = self._wsum(self._borrow(f, 0), 1)
         return float((x_avg[-1] + x_avg[0]) / 2.0)
 
     def eval_nuvol(self):
         """Volumetric Nusselt number (functions.rs:175-207)."""
         f = self._diag_field()
-        f.vhat = self._temp_ortho()
-        f.backward()
-        tphys = f.v
+        g = self._field2
+        self._temp_ortho_into(g)
+        check(lib().b2_array_copy(self._borrow(f, 1)._h, self._borrow(g, 1)._h))
+        g.backward()                                                           # T in physical space
         self.vely.backward()
-        vely_temp = tphys * self.vely.v
-        f.vhat = f.gradient([0, 1], None).get() / (-self.scale[1])
+        f.gradient([0, 1], [1.0, -self.scale[1]], out=self._diag_b)            # -dT/dy / scale_y
+        check(lib().b2_array_copy(self._borrow(f, 1)._h, self._diag_b._h))
         f.backward()
-        return self._average(f, (f.v + vely_temp / self.ka) * 2.0 * self.scale[1])
+        fv = self._borrow(f, 0)
+        check(lib().b2_array_combine(fv._h, self._borrow(g, 0)._h, self._borrow(self.vely, 0)._h, 2, 1.0 / self.ka))   # + uy T / ka
+        return self._wsum(fv, 0) * 2.0 * self.scale[1]
 
     def eval_re(self):
         """Reynolds number from the kinetic energy (functions.rs:215-233)."""
         f = self._diag_field()
         self.velx.backward()
         self.vely.backward()
-        return self._average(f, np.sqrt(self.velx.v ** 2 + self.vely.v ** 2) * (2.0 * self.scale[1] / self.nu))
+        fv = self._borrow(f, 0)
+        check(lib().b2_array_combine(fv._h, self._borrow(self.velx, 0)._h, self._borrow(self.vely, 0)._h, 1, 2.0 * self.scale[1] / self.nu))
+        return self._wsum(fv, 0)
 
     def callback(self, info_name=None):
         """The I/O part of ``callback_from_filename`` (src/navier_stokes/navier_io.rs:122-147): print time, |div|, Nu,

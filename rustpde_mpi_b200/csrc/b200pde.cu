@@ -504,6 +504,29 @@ __global__ void k_sumsq(size_t n, const double* __restrict__ x, double* out) {
   }
 }
 
+// dst = alpha * a * b (op 0), alpha * sqrt(a^2 + b^2) (op 1), dst + alpha * a * b (op 2): pointwise on arrays of one layout
+__global__ void k_combine(size_t n, double* __restrict__ dst, const double* __restrict__ a, const double* __restrict__ b, int op, double alpha) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double x = a[i], y = b[i];
+    dst[i] = op == 0 ? alpha * x * y : (op == 1 ? alpha * sqrt(x * x + y * y) : dst[i] + alpha * x * y);
+  }
+}
+// dx-weighted sums of a tiled real array slab (src/field/average.rs:26-59): thread per column j,
+//   out[j] = sum_i w0[i] a[i][j]  (mode 1)   or   out[0] += w1[j] * that  (mode 0)
+__global__ void k_weighted_sum(const double* __restrict__ a, int rows, int cols, int tiles, const double* __restrict__ w0,
+                               const double* __restrict__ w1, int mode, double* out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (j < cols)
+    for (int i = 0; i < rows; i++) s += w0[i] * a[tiled_index(i, j, tiles)];
+  if (mode == 1) { if (j < cols) out[j] = s; return; }
+  s *= (j < cols) ? w1[j] : 0.0;
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 static int ew_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 8); }
 
 // ------------------------------------------------------------------------------------------------
@@ -1547,11 +1570,54 @@ int b2_array_local_rows(const b2_array* a, int* row_start, int* row_count) {
 int b2_array_set_host(b2_array* a, const void* buf, size_t bytes) { return array_copy(a, const_cast<void*>(buf), bytes, 1); }
 int b2_array_get_host(const b2_array* a, void* buf, size_t bytes) { return array_copy(a, buf, bytes, 0); }
 int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
-  if (y->sp->elems() != x->sp->elems() || y->shape_kind != x->shape_kind) return fail(B2_ERR_SHAPE, "axpy: different spaces / shape kinds");
+  int yr, yc, xr, xc;
+  RET(shape_of(y->sp, y->shape_kind, &yr, &yc)); RET(shape_of(x->sp, x->shape_kind, &xr, &xc));
+  if (y->sp->elems() != x->sp->elems() || yr != xr || yc != xc || shape_complex(y->sp, y->shape_kind) != shape_complex(x->sp, x->shape_kind))
+    return fail(B2_ERR_SHAPE, "axpy: different shapes");
   const size_t n = y->sp->elems();
   B2_LAUNCH(k_axpby, ew_grid(n), 256, 0, y->sp->ctx->stream, n, y->d, alpha, x->d, 1.0);
   CK(cudaGetLastError());
   y->sp->ctx->launches++;
+  return B2_OK;
+}
+int b2_field_array(b2_field* f, int which, b2_array** out) {
+  if (which < 0 || which > 1) return fail(B2_ERR_ARG, "which: 0 = v, 1 = vhat");
+  *out = which == 0 ? f->v : f->vhat;   // borrowed: owned by the field
+  return B2_OK;
+}
+int b2_array_copy(b2_array* dst, const b2_array* src) {
+  if (dst->sp->elems() != src->sp->elems() || dst->sp->P[0] != src->sp->P[0] || dst->sp->P[1] != src->sp->P[1]) return fail(B2_ERR_SHAPE, "copy: different padded shapes");
+  CK(cudaMemcpyAsync(dst->d, src->d, dst->sp->elems() * sizeof(double), cudaMemcpyDeviceToDevice, dst->sp->ctx->stream));
+  return B2_OK;
+}
+int b2_array_combine(b2_array* dst, const b2_array* a, const b2_array* b, int op, double alpha) {
+  if (op < 0 || op > 2) return fail(B2_ERR_ARG, "combine op");
+  const size_t n = dst->sp->elems();
+  if (a->sp->elems() != n || b->sp->elems() != n || a->sp->P[1] != dst->sp->P[1] || b->sp->P[1] != dst->sp->P[1]) return fail(B2_ERR_SHAPE, "combine: different padded shapes");
+  B2_LAUNCH(k_combine, ew_grid(n), 256, 0, dst->sp->ctx->stream, n, dst->d, a->d, b->d, op, alpha);
+  CK(cudaGetLastError());
+  dst->sp->ctx->launches++;
+  return B2_OK;
+}
+int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const double* w1, int mode, double* out) {
+  b2_space* sp = a->sp;
+  if (shape_complex(sp, a->shape_kind)) return fail(B2_ERR_UNSUPPORTED, "weighted sums are defined on real (physical) arrays");
+  int rows, cols, row0, cnt;
+  RET(shape_of(sp, a->shape_kind, &rows, &cols));
+  local_rows(sp, rows, &row0, &cnt);
+  const int nout = mode == 1 ? cols : 1;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)(cnt + cols + nout + 1) * sizeof(double)));
+  double* dw0 = d; double* dw1 = d + cnt; double* dout = dw1 + cols;
+  if (cnt) CK(cudaMemcpyAsync(dw0, w0_local, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
+  CK(cudaMemcpyAsync(dw1, w1, (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
+  CK(cudaMemsetAsync(dout, 0, (size_t)nout * sizeof(double), sp->ctx->stream));
+  B2_LAUNCH(k_weighted_sum, (cols + 127) / 128, 128, 0, sp->ctx->stream, a->d, cnt, cols, sp->P[1] / 4, dw0, dw1, mode, dout);
+  CK(cudaGetLastError());
+  sp->ctx->launches++;
+  CK(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
+  CK(cudaStreamSynchronize(sp->ctx->stream));
+  CK(cudaFree(d));
   return B2_OK;
 }
 static int norm2_dev(b2_space* sp, const double* d, double* out, bool global) {

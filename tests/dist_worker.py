@@ -50,6 +50,10 @@ def main():
         err = float(np.linalg.norm((got[k] - v).ravel()) / np.linalg.norm(v.ravel()))
         worst = max(worst, err)
     assert abs(dn - ref.div_norm()) <= 1e-8 * max(1.0, ref.div_norm()), (dn, ref.div_norm())
+    # callback() diagnostics on the slabs (src/field_mpi/average.rs:15-61: partial dx-weighted sums + all_gather_sum)
+    for name in ("eval_nu", "eval_nuvol", "eval_re"):
+        a, b = getattr(nav, name)(), getattr(ref, name)()
+        assert abs(a - b) <= 1e-10 * abs(b), (name, a, b)
     print(f"rank {rank}/{world}: nx={nx} ny={ny} steps={steps} periodic={periodic} mode={mode} worst_rel_err={worst:.3e}", flush=True)
     assert worst < 1e-10, worst
     dist.barrier()
