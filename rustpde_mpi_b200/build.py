@@ -22,7 +22,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC, "-lcublas"]
+           "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

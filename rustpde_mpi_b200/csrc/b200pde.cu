@@ -9,9 +9,6 @@
 #include "gemm_f64.cuh"
 #include "../../include/b200pde.h"
 
-#ifndef B2_EMU
-#include <cublas_v2.h>
-#endif
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -32,11 +29,6 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess)                                                                         \
       return fail(B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
   } while (0)
-#define CKB(call)                                                                                  \
-  do {                                                                                             \
-    cublasStatus_t s_ = (call);                                                                    \
-    if (s_ != CUBLAS_STATUS_SUCCESS) return fail(B2_ERR_CUDA, std::string(#call) + ": cublas error " + std::to_string((int)s_)); \
-  } while (0)
 #define RET(call)                    \
   do {                               \
     int r_ = (call);                 \
@@ -55,10 +47,8 @@ struct b2_ctx {
   cudaStream_t cur = nullptr;         // stream the next pass is launched on (origin or a side stream)
   cudaEvent_t evp[16] = {nullptr};    // fork / join events
   int evn = 0;
-  cublasHandle_t blas = nullptr;
   long long launches = 0;  // lane-kernel + helper launches (counted, for bench.py's gpu_launches)
   double* stage = nullptr; size_t stage_bytes = 0;   // host<->device staging (plain layout)
-  void* blas_ws = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // b2_ctx_timer_*
   bool profile = false;                              // time the GEMM launches separately
   std::vector<cudaEvent_t> gemm_events;
@@ -447,15 +437,12 @@ struct b2_solver {
   // poisson
   bool dense = false;
   int m0 = 0;
-  DVecD fwd, bwd;           // dense (m0 x m0) row-major
   DVecD pfl, pid, pu1, pu2; // per-lane LU in scan layout
-  // parity blocks (single-GPU fused step): the eigenvectors couple indices of equal parity only, so with the modes
-  // grouped by parity class both GEMMs split into two half-size GEMMs (half the flops)
+  // parity blocks: the eigenvectors couple indices of equal parity only, so with the modes grouped by parity class both
+  // GEMMs split into two half-size GEMMs (half the flops)
   bool blocks = false;
   int ce = 0, co = 0;       // even / odd indices (= modes of the even / odd class)
-  DVecD fe, fo, be, bo;     // fwd_e (ce x ce), fwd_o (co x co), bwd_e, bwd_o, row-major
   DVecD qfl, qid, qu1, qu2; // per-lane LU for the parity-grouped mode order
-  double* plain[2] = {nullptr, nullptr};
   // own FP64 GEMM on the tiled arrays (gemm_f64.cuh): forward (x -> eigenmodes) and backward products
   GemmPlan gf, gb;
   bool own_gemm = false;
@@ -1064,14 +1051,19 @@ static int gemm_plan_create(b2_space* sp, GemmPlan* g, const double* Ae, int Me,
 }
 static int gemm_run(b2_ctx* ctx, const GemmPlan& g, const double* B, double* C) {
   static bool attr_set[64] = {false};
+  static const int dbg = getenv("B2_GEMM_DBG") ? atoi(getenv("B2_GEMM_DBG")) : 0;   // measurement only (tools/sweep.py): see gemm_pb_kernel
   if (!attr_set[ctx->device & 63]) {
-    CK(cudaFuncSetAttribute(gemm_pb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
   GemmParams p = g.p;
   p.B = B; p.C = C;
   if (ctx->nranks > 1) p.c_off = reinterpret_cast<const char*>(C) - static_cast<const char*>(ctx->peer_base[ctx->rank]);
-  B2_LAUNCH(gemm_pb_kernel, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  if (dbg == 1) B2_LAUNCH(gemm_pb_kernel<1>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 2) B2_LAUNCH(gemm_pb_kernel<2>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else B2_LAUNCH(gemm_pb_kernel<0>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
   CK(cudaGetLastError());
   ctx->launches++;
   return ctx->nranks > 1 ? ctx_barrier(ctx) : B2_OK;   // the epilogue wrote into the peers' slabs
@@ -1100,9 +1092,6 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     s->dense = true; s->m0 = b0.m;
     lam.assign(lam_in, lam_in + b0.m);
     lanes = b0.m;
-    std::vector<double> f(fwd, fwd + (size_t)b0.m * b0.m), q(bwd, bwd + (size_t)b0.m * b0.m);
-    RET(s->fwd.upload(f)); RET(s->bwd.upload(q));
-    RET(alloc_zero(sp, &s->plain[0])); RET(alloc_zero(sp, &s->plain[1]));
   } else if (!b0.cheb) {
     // Fourier axis 0: lam = diag(laplacian) = -k^2 c0 (fdma_tensor.rs:118-121), singularity shift poisson.rs:84-86
     lanes = 2 * b0.m;
@@ -1157,23 +1146,19 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     }
     for (int k = 0; k < 2 && ok; k++) for (int r = 0; r < m0; r++) if (cls[r] == k) perm.push_back(r);
     int ne = 0; for (int r = 0; r < m0; r++) ne += (cls[r] == 0);
-    const bool own = getenv("B2_CUBLAS") == nullptr;   // B2_CUBLAS=1: library DGEMM on row-major copies (A/B measurements only)
-    if (ok && ne == ce && (own ? (ce % 4 == 0) : (nr == 1 || (ce % 2 == 0 && sp->cfg[0].LN == 4 && sp->cfg[1].LN == 4)))) {   // the odd block starts on a tile row (own GEMM) / at an even column of the x-pencil operands (library path)
+    if (ok && ne == ce && ce % 4 == 0) {   // the odd block starts on a tile row of the grouped array (gemm_f64.cuh)
       std::vector<double> fe((size_t)ce * ce), fo((size_t)co * co), be((size_t)ce * ce), bo((size_t)co * co), lam2(lam.size());
       for (int r = 0; r < ce; r++) for (int k = 0; k < ce; k++) { fe[(size_t)r * ce + k] = fwd[(size_t)perm[r] * m0 + 2 * k]; be[(size_t)k * ce + r] = bwd[(size_t)(2 * k) * m0 + perm[r]]; }
       for (int r = 0; r < co; r++) for (int k = 0; k < co; k++) { fo[(size_t)r * co + k] = fwd[(size_t)perm[ce + r] * m0 + 2 * k + 1]; bo[(size_t)k * co + r] = bwd[(size_t)(2 * k + 1) * m0 + perm[ce + r]]; }
       for (int r = 0; r < m0; r++) lam2[r] = lam[perm[r]];
-      RET(s->fe.upload(fe)); RET(s->fo.upload(fo)); RET(s->be.upload(be)); RET(s->bo.upload(bo));
       RET(build_lanes(lam2, &s->qfl, &s->qid, &s->qu1, &s->qu2));
       s->blocks = true; s->ce = ce; s->co = co;
-      if (own) {   // own GEMM straight on the tiled arrays
-        RET(gemm_plan_create(sp, &s->gf, fe.data(), ce, ce, fo.data(), co, co, true, false));
-        RET(gemm_plan_create(sp, &s->gb, be.data(), ce, ce, bo.data(), co, co, false, true));
-        s->own_gemm = true;
-      }
+      RET(gemm_plan_create(sp, &s->gf, fe.data(), ce, ce, fo.data(), co, co, true, false));   // forward: natural x rows -> modes grouped by class
+      RET(gemm_plan_create(sp, &s->gb, be.data(), ce, ce, bo.data(), co, co, false, true));   // backward: the reverse
+      s->own_gemm = true;
     }
   }
-  if (s->dense && !s->own_gemm && getenv("B2_CUBLAS") == nullptr) {   // dense decomposition: full products, natural mode order
+  if (s->dense && !s->own_gemm) {   // a decomposition without the parity structure: full products, natural mode order
     RET(gemm_plan_create(sp, &s->gf, fwd, s->m0, s->m0, nullptr, 0, 0, false, false));
     RET(gemm_plan_create(sp, &s->gb, bwd, s->m0, s->m0, nullptr, 0, 0, false, false));
     s->own_gemm = true; s->blocks = false;
@@ -1224,42 +1209,13 @@ static int poisson_solve(b2_solver* s, const double* in, double* out, bool zero0
   b2_ctx* ctx = sp->ctx;
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
   const int P0 = sp->P[0], P1 = sp->P[1];
-  if (s->dense && s->own_gemm) {
+  if (s->dense) {
     // matvec along y and x (two transposing passes: back in the y-lane orientation, rows = x index), then the core
     Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1); y.store(sp->tmp[0], l, ST_TRANS);
     RET(run_pass(sp, 0, y));
     Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0); x.store(sp->tmp[1], l, ST_TRANS);
     RET(run_pass(sp, 1, x));
     return poisson_core(s, sp, sp->tmp[1], false, sp->tmp[0], sp->tmp[2], out, zero00);
-  }
-  if (s->dense) {
-    // matvec along y, transpose
-    Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1); y.store(sp->tmp[0], l, ST_TRANS);
-    RET(run_pass(sp, 0, y));
-    // matvec along x, keep x-lanes, write row-major for the GEMM
-    Prog x; x.load(sp->tmp[0], b0.rows_ortho); l = x.matvec(b0); x.store(s->plain[0], l, ST_PLAIN);
-    RET(run_pass(sp, 1, x));
-    // out[j, :] = fwd . rhs[j, :]  (dense FP64 GEMM, src/solver/poisson.rs:213-219)
-    const double one = 1.0, zero = 0.0;
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1 / ctx->nranks, s->m0, &one, s->fwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
-    RET(gemm_mark(ctx));
-    ctx->launches++;
-    Prog x2; x2.load(s->plain[1], s->m0, 1.0, LD_PLAIN); x2.store(sp->tmp[0], s->m0, ST_TRANS);
-    RET(run_pass(sp, 1, x2));
-    // per-row banded solves with (lap1 + lam_i mass1)
-    Prog y2; y2.load(sp->tmp[0], b1.m); y2.fdma(b1.m, s->pfl.d, s->pid.d, s->pu1.d, s->pu2.d, FD_PERLANE); y2.store(sp->tmp[1], b1.m, ST_TRANS);
-    RET(run_pass(sp, 0, y2));
-    Prog x3; x3.load(sp->tmp[1], s->m0); x3.store(s->plain[0], s->m0, ST_PLAIN);
-    RET(run_pass(sp, 1, x3));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, s->m0, P1 / ctx->nranks, s->m0, &one, s->bwd.d, s->m0, s->plain[0], P0, &zero, s->plain[1], P0));
-    RET(gemm_mark(ctx));
-    ctx->launches++;
-    Prog x4; x4.load(s->plain[1], s->m0, 1.0, LD_PLAIN);
-    if (zero00) x4.zeroelem(0, 0);
-    x4.store(out, s->m0, ST_TRANS);
-    return run_pass(sp, 1, x4);
   }
   Prog y; y.load(in, b1.rows_ortho); int l = y.matvec(b1);
   y.fdma(b1.m, s->pfl.d, s->pid.d, s->pu1.d, s->pu2.d, FD_PERLANE);
@@ -1333,12 +1289,6 @@ int b2_ctx_create(int device, int rank, int nranks, size_t heap_bytes, b2_ctx** 
   c->cur = c->stream;
   for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
   for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&c->evp[i], cudaEventDisableTiming));
-  CKB(cublasCreate(&c->blas));
-  CKB(cublasSetStream(c->blas, c->stream));
-#ifndef B2_EMU
-  CK(cudaMalloc(&c->blas_ws, (size_t)64 << 20));   // fixed workspace so that the GEMMs can live inside a CUDA graph
-  CKB(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)64 << 20));
-#endif
   if (nranks > 1) {
     if (heap_bytes < (1u << 20)) return fail(B2_ERR_ARG, "nranks > 1 needs a symmetric heap (heap_bytes)");
     c->heap_bytes = heap_bytes;
@@ -1355,14 +1305,12 @@ int b2_ctx_destroy(b2_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& st : c->side) if (st) cudaStreamSynchronize(st);
-  if (c->blas) cublasDestroy(c->blas);
   for (auto e : c->gemm_events) cudaEventDestroy(e);
   for (auto& e : c->evp) if (e) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (auto& st : c->side) if (st) cudaStreamDestroy(st);
   if (c->stream) cudaStreamDestroy(c->stream);
-  if (c->blas_ws) cudaFree(c->blas_ws);
   if (c->stage) cudaFree(c->stage);
   if (c->d_prof) cudaFree(c->d_prof);
   if (c->d_peers) cudaFree(c->d_peers);
@@ -1703,10 +1651,10 @@ int b2_hholtz_create(const b2_field* f, double c0, double c1, const double* lam,
 }
 int b2_solver_destroy(b2_solver* s) {
   if (!s) return B2_OK;
-  for (int ax = 0; ax < 2; ax++) { s->fl[ax].release(); s->id[ax].release(); s->u1[ax].release(); s->u2[ax].release(); s->sd[ax].release(); }
-  s->fwd.release(); s->bwd.release(); s->pfl.release(); s->pid.release(); s->pu1.release(); s->pu2.release();
-  s->fe.release(); s->fo.release(); s->be.release(); s->bo.release(); s->qfl.release(); s->qid.release(); s->qu1.release(); s->qu2.release();
-  for (auto& p : s->plain) ctx_free(s->sp->ctx, p);
+  for (int ax = 0; ax < 2; ax++) { s->fl[ax].release(); s->id[ax].release(); s->u1[ax].release(); s->u2[ax].release(); s->sd[ax].release(); s->pd[ax].release(); }
+  s->pfl.release(); s->pid.release(); s->pu1.release(); s->pu2.release();
+  s->qfl.release(); s->qid.release(); s->qu1.release(); s->qu2.release();
+  for (GemmPlan* g : {&s->gf, &s->gb}) { g->A[0].release(); g->A[1].release(); }
   delete s;
   return B2_OK;
 }
@@ -2071,106 +2019,23 @@ static int nav_update_fused(b2_navier* nv) {
   }
   // ---- Poisson (src/solver/poisson.rs:195-236) ----
   b2_solver* ps = nv->pois;
-  const double* pseu_src; int pseu_flags, pseu_i1 = 0;
-  if (ps->dense && ps->own_gemm) {
+  if (ps->dense) {
     // own FP64 GEMMs on the tiled arrays (gemm_f64.cuh): no row-major copies, every load / store of the lane passes
     // around them is a zero-copy slab copy; with several GPUs the exchanges ride on those stores and on the GEMM epilogue
     RET(poisson_core(ps, so, nv->R0, true, nv->G0, nv->G1, nv->pseu->vhat->d, true));
-    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
-  } else if (ps->dense && ctx->nranks > 1 && ps->blocks) {
-    // slabs + parity blocks: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y,
-    // row-major, x contiguous); the x index is stored parity-split (ST_PSPLITC / LD_PSPLITC), the modes parity-grouped
-    const double one = 1.0, zero = 0.0;
-    const int P1loc = P1 / ctx->nranks, m0 = ps->m0, ce = ps->ce, co = ps->co;
-    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_TRANS | ST_PLAIN | ST_PSPLITC, 1.0, m0);
-    RET(run_pass(so, 0, y));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ce, P1loc, ce, &one, ps->fe.d, ce, nv->G0, P0, &zero, nv->G1, P0));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, co, P1loc, co, &one, ps->fo.d, co, nv->G0 + ce, P0, &zero, nv->G1 + ce, P0));
-    RET(gemm_mark(ctx));
-    ctx->launches += 2;
-    Prog x; x.load(nv->G1, m0, 1.0, LD_PLAIN); x.store(nv->U1, m0, ST_TRANS);
-    RET(run_pass(so, 1, x));
-    Prog y2; y2.load(nv->U1, byp.m); y2.fdma(byp.m, ps->qfl.d, ps->qid.d, ps->qu1.d, ps->qu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_TRANS | ST_PLAIN);
-    RET(run_pass(so, 0, y2));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ce, P1loc, ce, &one, ps->be.d, ce, nv->G0, P0, &zero, nv->G1, P0));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, co, P1loc, co, &one, ps->bo.d, co, nv->G0 + ce, P0, &zero, nv->G1 + ce, P0));
-    RET(gemm_mark(ctx));
-    ctx->launches += 2;
-    Prog x2; x2.load(nv->G1, m0, 1.0, LD_PLAIN | LD_PSPLITC, m0); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, m0, ST_TRANS);
-    RET(run_pass(so, 1, x2));
-    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
-  } else if (ps->dense && ctx->nranks > 1) {
-    // slabs: the eigen-transform contracts over x, so the GEMMs run on x-pencils (rows = local y, row-major)
-    const double one = 1.0, zero = 0.0;
-    const int P1loc = P1 / ctx->nranks;
-    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_TRANS | ST_PLAIN);
-    RET(run_pass(so, 0, y));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->fwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
-    RET(gemm_mark(ctx));
-    ctx->launches++;
-    Prog x; x.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x.store(nv->U1, ps->m0, ST_TRANS);
-    RET(run_pass(so, 1, x));
-    Prog y2; y2.load(nv->U1, byp.m); y2.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_TRANS | ST_PLAIN);
-    RET(run_pass(so, 0, y2));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_T, CUBLAS_OP_N, ps->m0, P1loc, ps->m0, &one, ps->bwd.d, ps->m0, nv->G0, P0, &zero, nv->G1, P0));
-    RET(gemm_mark(ctx));
-    ctx->launches++;
-    Prog x2; x2.load(nv->G1, ps->m0, 1.0, LD_PLAIN); x2.zeroelem(0, 0); x2.store(nv->pseu->vhat->d, ps->m0, ST_TRANS);
-    RET(run_pass(so, 1, x2));
-    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
-  } else if (ps->dense && ps->blocks && ctx->nranks == 1) {
-    // parity-grouped: rows of the GEMM operands are stored even indices first, then odd (ST_PSPLIT / LD_PSPLIT);
-    // G1_e = fwd_e G0_e, G1_o = fwd_o G0_o  (row-major views; half the flops of the full product)
-    const double one = 1.0, zero = 0.0;
-    const int m0 = ps->m0, ce = ps->ce, co = ps->co;
-    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN | ST_PSPLIT, 1.0, m0);
-    RET(run_pass(so, 0, y));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ce, ce, &one, nv->G0, P1, ps->fe.d, ce, &zero, nv->G1, P1));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, co, co, &one, nv->G0 + (size_t)ce * P1, P1, ps->fo.d, co, &zero, nv->G1 + (size_t)ce * P1, P1));
-    RET(gemm_mark(ctx)); ctx->launches += 2;
-    Prog y2; y2.load(nv->G1, byp.m, 1.0, LD_PLAIN); y2.fdma(byp.m, ps->qfl.d, ps->qid.d, ps->qu1.d, ps->qu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_PLAIN);
-    RET(run_pass(so, 0, y2));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ce, ce, &one, nv->G0, P1, ps->be.d, ce, &zero, nv->G1, P1));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, co, co, &one, nv->G0 + (size_t)ce * P1, P1, ps->bo.d, co, &zero, nv->G1 + (size_t)ce * P1, P1));
-    RET(gemm_mark(ctx)); ctx->launches += 2;
-    pseu_src = nv->G1; pseu_flags = LD_PLAIN | LD_PSPLIT; pseu_i1 = m0;
-  } else if (ps->dense) {
-    const double one = 1.0, zero = 0.0;
-    Prog y; y.load(nv->R0, byo.rows_ortho); int l = y.matvec(byp); y.store(nv->G0, l, ST_PLAIN);
-    RET(run_pass(so, 0, y));
-    RET(gemm_mark(ctx));   // G1[i', j] = sum_i fwd[i', i] G0[i, j]   (row-major views)
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ps->m0, ps->m0, &one, nv->G0, P1, ps->fwd.d, ps->m0, &zero, nv->G1, P1));
-    RET(gemm_mark(ctx)); ctx->launches++;
-    Prog y2; y2.load(nv->G1, byp.m, 1.0, LD_PLAIN); y2.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE); y2.store(nv->G0, byp.m, ST_PLAIN);
-    RET(run_pass(so, 0, y2));
-    RET(gemm_mark(ctx));
-    CKB(cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, P1, ps->m0, ps->m0, &one, nv->G0, P1, ps->bwd.d, ps->m0, &zero, nv->G1, P1));
-    RET(gemm_mark(ctx)); ctx->launches++;
-    pseu_src = nv->G1; pseu_flags = LD_PLAIN;
   } else {
     Prog y; y.load(nv->R0, byo.rows_ortho); y.matvec(byp);
     y.fdma(byp.m, ps->pfl.d, ps->pid.d, ps->pu1.d, ps->pu2.d, FD_PERLANE);
     y.zeroelem(0, 0); y.zeroelem(1, 0);
     y.store(nv->pseu->vhat->d, byp.m, 0);
     RET(run_pass(so, 0, y));
-    pseu_src = nv->pseu->vhat->d; pseu_flags = 0;
   }
   // ---- E: velocity correction and pressure update part 2 (navier_eq.rs:117-143) ----
   {
     const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
     Prog y;
     for (int k = 0; k < 3; k++) {
-      y.load(pseu_src, byp.m, 1.0, pseu_flags, pseu_i1);
-      if (pseu_flags & LD_PLAIN) {   // single-GPU dense path: pseu still sits in the GEMM's row-major buffer
-        y.zeroelem(0, 0);
-        if (k == 0) y.store(nv->pseu->vhat->d, byp.m, 0);
-      }
+      y.load(nv->pseu->vhat->d, byp.m);
       y.to_ortho(byp);
       if (k == 1) y.deriv_axis(byo, 1, sy);
       int l = byo.rows_ortho;

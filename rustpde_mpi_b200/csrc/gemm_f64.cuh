@@ -59,6 +59,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #endif
 }
 
+// DBG (measurement only, results invalid): 1 = no copies and no waits (arithmetic + shared-memory reads alone), 2 = copies and waits
+// without the DMMAs (data movement alone)
+template <int DBG>
 __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ GemmParams P) {
   B2_DYN_SMEM(char, gsm);
   uint64_t* full = reinterpret_cast<uint64_t*>(gsm);       // stage s has landed (bulk copies, transaction count)
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
       bulk_load_1d(st + 2 * G_KK * G_SLOT_PITCH + bb * G_ACHUNK, P.A[bb] + ((size_t)mt * nks + ks) * G_ACHUNK, G_ACHUNK * 8u, &full[s]);
   };
   int issued = 0;
-  if (tid == 0) for (; issued < G_NSTAGE && issued < nks; issued++) issue(issued);
+  if (tid == 0 && DBG != 1) for (; issued < G_NSTAGE && issued < nks; issued++) issue(issued);
 
   // fragment addresses inside a stage (doubles)
   const int k = lane & 3, n8 = lane >> 2;
@@ -121,13 +124,13 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
   // latency.  With it, the refill of a buffer is always requested two stages before anybody needs it.)
   for (int ks = 0; ks < nks; ks++) {
     const int s = ks % G_NSTAGE;
-    if (ks >= 2) mbar_wait(&empty[(ks - 2) % G_NSTAGE], (unsigned)(((ks - 2) / G_NSTAGE) & 1));
-    if (tid == 0) {   // refill every buffer that all warps have released
+    if (ks >= 2 && DBG != 1) mbar_wait(&empty[(ks - 2) % G_NSTAGE], (unsigned)(((ks - 2) / G_NSTAGE) & 1));
+    if (tid == 0 && DBG != 1) {   // refill every buffer that all warps have released
       while (issued < nks && mbar_test(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1))) { issue(issued); issued++; }
     }
-    mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
+    if (DBG != 1) mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
     const double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
-    if (mf_n > 0 && nf_n > 0) {
+    if (mf_n > 0 && nf_n > 0 && DBG != 2) {
 #pragma unroll
       for (int kk = 0; kk < G_KK; kk++) {
         double a[4], bf[4];
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    if (lane == 0 && DBG != 1) mbar_arrive(&empty[s]);
   }
   // epilogue: thread holds C[8 i + lane / 4][8 j + 2 (lane % 4) + {0, 1}] of its 32 x 32 block
 #pragma unroll

@@ -237,30 +237,5 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 
-// ---- cuBLAS subset ----
-typedef void* cublasHandle_t;
-typedef int cublasStatus_t;
-enum { CUBLAS_STATUS_SUCCESS = 0 };
-enum cublasOperation_t { CUBLAS_OP_N, CUBLAS_OP_T };
-static inline cublasStatus_t cublasCreate(cublasHandle_t* h) { *h = nullptr; return 0; }
-static inline cublasStatus_t cublasDestroy(cublasHandle_t) { return 0; }
-static inline cublasStatus_t cublasSetStream(cublasHandle_t, cudaStream_t) { return 0; }
-// column-major C(m x n) = alpha op(A) op(B) + beta C   (only the op combinations the host code uses)
-static inline cublasStatus_t cublasDgemm(cublasHandle_t, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k,
-                                         const double* alpha, const double* A, int lda, const double* B, int ldb,
-                                         const double* beta, double* C, int ldc) {
-  for (int j = 0; j < n; j++)
-    for (int i = 0; i < m; i++) {
-      double s = 0;
-      for (int p = 0; p < k; p++) {
-        double a = (ta == CUBLAS_OP_N) ? A[(size_t)p * lda + i] : A[(size_t)i * lda + p];
-        double b = (tb == CUBLAS_OP_N) ? B[(size_t)j * ldb + p] : B[(size_t)p * ldb + j];
-        s += a * b;
-      }
-      C[(size_t)j * ldc + i] = *alpha * s + (*beta == 0.0 ? 0.0 : *beta * C[(size_t)j * ldc + i]);
-    }
-  return 0;
-}
-
 #define B2_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::block().dyn.data()) + 127) & ~uintptr_t(127))
 #define B2_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
