@@ -436,7 +436,9 @@ def poisson_eig(kind0, n0, c0, parity_split=None):
             return z["lam"], z["fwd"], z["bwd"]
         lam, fwd, bwd = _poisson_eig(kind0, n0, c0, parity_split)
         os.makedirs(d, exist_ok=True)
-        np.savez(f, lam=lam, fwd=fwd, bwd=bwd)
+        tmp = f"{f}.{os.getpid()}.tmp.npz"   # several ranks may fill the cache at once: write aside, then rename
+        np.savez(tmp, lam=lam, fwd=fwd, bwd=bwd)
+        os.replace(tmp, f)
         return lam, fwd, bwd
     return _poisson_eig(kind0, n0, c0, parity_split)
 

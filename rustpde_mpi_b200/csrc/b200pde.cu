@@ -624,7 +624,6 @@ static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 }
 
 static bool g_use_tma = getenv("B2_NOTMA") == nullptr;     // B2_NOTMA=1: every load/store on the per-thread LDG/STG path (A/B measurements)
-static bool g_use_direct = getenv("B2_NODIRECT") == nullptr; // B2_NODIRECT=1: plain loads/stores go through the ring / staging as well
 static bool g_use_ring = getenv("B2_LDTHREADS") == nullptr;  // combining loads (accumulate / multiply / stencil / scaled) stream through the warps' own
                                                              // copy pipelines (load_warps); B2_LDTHREADS=1: per-thread 16-byte loads instead
 
@@ -639,11 +638,9 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   p.prof = ctx->d_prof; p.LN = c.LN;
   p.NT = c.NT; p.CHW = c.CHW; p.nsc = c.nsc; p.wslot_bytes = c.wslot_bytes; p.CHD = c.CHD; p.nchd = c.nchd;
   p.w_off = c.w_off; p.st_off = c.st_off;
-  p.bulk1d = (c.LN == 4 && getenv("B2_NOBULK1D") == nullptr) ? 1 : 0;
+  p.bulk1d = c.LN == 4 ? 1 : 0;   // a whole lane group is one contiguous slab: 1-D bulk copies, no tensor map
   bool exchange = false;
   int npst = 0;
-  static const bool peer_tma = getenv("B2_PEER_THREADS") == nullptr;        // B2_PEER_THREADS=1: per-thread peer stores (round-1 path)
-  static const bool peer_acc_tma = getenv("B2_PEER_ACC_THREADS") == nullptr; // accumulating peer stores as bulk reductions over NVLink
   if (ctx->nranks > 1) {   // a transposing store is the pencil transpose: tiles go straight into the owner's slab
     for (int i = 0; i < p.nops; i++)
       if (p.ops[i].code == OP_STORE && (p.ops[i].i2 & ST_TRANS)) { p.ops[i].i2 |= ST_PEER; p.ops[i].p1 = ctx->d_peers; exchange = true; }
@@ -651,13 +648,11 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   } else {
     for (int i = 0; i < p.nops; i++) if (p.ops[i].code == OP_STORE) p.ops[i].i2 &= ~ST_COLSPLIT;   // one GPU: a plain same-orientation store
   }
-  // A tiled load followed by the composite -> orthonormal stencil (to_ortho: y_j = x_j + s_j x_{j-2}) becomes ONE load that
-  // applies the stencil on the fly (LD_STENCIL, per-thread 16-byte loads; the second operand x_{j-2} comes from the same
-  // lines): measured on C4 a direct load costs 9.5k cycles per lane group, a combining load 10.6k and the banded pass
-  // 7.1k, so the pair drops from 16.6k to ~10.6k.  B2_NOLDSTEN=1 keeps the two ops.
-  static const bool ld_sten = getenv("B2_NOLDSTEN") == nullptr;
-  static const bool bandc = getenv("B2_NOBANDC") == nullptr;   // chunk-streaming band ops (band_chunk) on transform-sized lanes
-  for (int i = 0; ld_sten && !(c.fast && bandc) && i + 1 < p.nops; i++) {
+  // Generic geometry: a tiled load followed by the composite -> orthonormal stencil (to_ortho: y_j = x_j + s_j x_{j-2}) becomes
+  // ONE load that applies the stencil on the fly (LD_STENCIL).  Transform-sized lanes keep the zero-copy load and run the
+  // stencil as a chunk-streaming band op instead (measured on C4: stencil-on-load through the staging slots 20-22k cycles
+  // per lane group, zero-copy load + band_chunk 5.7k + 9.8k; profiles/r02/sweep_*.log).
+  for (int i = 0; !c.fast && i + 1 < p.nops; i++) {
     LaneOp& lo = p.ops[i]; LaneOp& bo = p.ops[i + 1];
     if (lo.code != OP_LOAD || (lo.i2 & (LD_PLAIN | LD_STENCIL | LD_ACC | LD_MUL)) || bo.code != OP_BAND) continue;
     const int h0 = (int)(signed char)(bo.i1 & 0xff), h1 = (int)(signed char)((bo.i1 >> 8) & 0xff), h2 = (int)(signed char)((bo.i1 >> 16) & 0xff);
@@ -668,8 +663,8 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   // Fold a banded mat-vec into the LU solve that consumes it (forward offsets only, same output length; shared
   // coefficient vectors): the solve forms its right-hand side on the fly (lane_fast.cuh, fdma_fast_body<PREBAND>).
   // Measured: +1.5 % on C2 (E = 8), -2 % on C4 (E = 16, where the extra coefficient streams cost more than the saved
-  // pass), so it is applied to the short-lane instances only (B2_FUSE=1 forces it on, B2_NOFUSE=1 off).
-  if (c.fast && getenv("B2_NOFUSE") == nullptr && (c.E <= 8 || getenv("B2_FUSE") != nullptr)) {
+  // pass), so it is applied to the short-lane instances only.
+  if (c.fast && c.E <= 8) {
     for (int i = 0; i + 1 < p.nops; i++) {
       LaneOp& bo = p.ops[i]; LaneOp& fo = p.ops[i + 1];
       if (bo.code != OP_BAND || fo.code != OP_FDMA || (fo.i2 & FD_PERLANE) || bo.i0 != fo.i0) continue;
@@ -688,7 +683,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   }
   // Remaining banded mat-vecs on transform-sized lanes run in chunk-streaming form (band_chunk: one read and one write
   // traversal of the lane group): pair offsets {0, +1, +2} or {0, -1}, vector coefficients through their scan-layout copies.
-  if (c.fast && bandc) {
+  if (c.fast) {
     for (int i = 0; i < p.nops; i++) {
       LaneOp& bo = p.ops[i];
       if (bo.code != OP_BAND) continue;
@@ -719,7 +714,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
     LaneOp& op = p.ops[i];
     B2TMapDesc d; memset(&d, 0, sizeof(d));
     if (op.code == OP_LOAD && !(op.i2 & LD_PLAIN)) {
-      const bool direct = g_use_direct && !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
+      const bool direct = !(op.i2 & (LD_ACC | LD_MUL | LD_STENCIL)) && op.a == 1.0;
       for (int k = 0; k < i; k++)   // re-reading an array this program stored: the bulk stores have to be complete first
         if (p.ops[k].code == OP_STORE && p.ops[k].p0 == op.p0) op.i2 |= LD_AFTER_STORE;
       if (!direct && !g_use_ring) continue;   // per-thread path (B2_LDTHREADS=1)
@@ -730,7 +725,8 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
       op.i2 |= direct ? LD_DIRECT : LD_TMA;
     } else if (op.code == OP_STORE && (op.i2 & ST_PEER) && !(op.i2 & ST_PLAIN)) {
       // one transposed view per owner: rows = the tiles of the destination that live in that rank's slab
-      if (!peer_tma || ((op.i2 & ST_ACC) && !peer_acc_tma) || npst >= B2_MAXPST) continue;   // per-thread peer stores
+      static const bool peer_threads = getenv("B2_PEER_THREADS") != nullptr;   // debugging: per-thread peer stores instead of tensor stores
+      if (npst >= B2_MAXPST || peer_threads) continue;   // (more peer views than the program has room for: per-thread peer stores)
       const int gpr = c.in_tiles / ctx->nranks;
       for (int o = 0; o < ctx->nranks; o++) {
         B2TMapDesc dd; memset(&dd, 0, sizeof(dd));
@@ -768,7 +764,7 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
         }
         op.i2 |= ST_TMA;
       } else {
-        const bool direct = g_use_direct && !(op.i2 & ST_ACC) && op.a == 1.0;
+        const bool direct = !(op.i2 & ST_ACC) && op.a == 1.0;
         if (op.i2 & ST_COLSPLIT) {   // zero-copy runs per owner (contiguous slabs only), else per-thread peer stores
           if (direct && p.bulk1d) op.i2 |= ST_DIRECT;
           continue;
@@ -786,13 +782,24 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
   ctx->launches++;
   const int r = launch_pass(ctx, c, p);
   if (r != B2_OK) return r;
+  static const bool dbg_sync = getenv("B2_DEBUG_SYNC") != nullptr;   // debugging: name the pass a device fault belongs to
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (dbg_sync) cudaStreamIsCapturing(ctx->cur, &cap);
+  if (dbg_sync && cap == cudaStreamCaptureStatusNone) {
+    cudaError_t e = cudaStreamSynchronize(ctx->cur);
+    if (e != cudaSuccess) {
+      std::string ops;
+      for (int i = 0; i < p.nops; i++) ops += std::to_string(p.ops[i].code) + ":" + std::to_string(p.ops[i].i2) + " ";
+      return fail(B2_ERR_CUDA, std::string("pass failed (") + cudaGetErrorString(e) + "), orient " + std::to_string(orient) + ", ops code:flags = " + ops);
+    }
+  }
   return exchange ? ctx_barrier(ctx) : B2_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // context / space / arrays
 // ------------------------------------------------------------------------------------------------
-static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
+static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c, int nranks) {
   c->in_tiles = Pl / 4; c->out_tiles = Pc / 4; c->groups = Pc / 4; c->LP = Pl;
   const int N = lane_base.N;
   // E = FFT points per thread; a thread also owns CP = E+1 element pairs of the lane for the banded ops,
@@ -850,6 +857,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c) {
   int chw = (int)(room / ((size_t)nwarps * 2) / tile_bytes) - 1;   // one halo tile in front of every slot
   if (const char* e = getenv("B2_CHW")) { int v = atoi(e); if (v >= 2) chw = std::min(chw, v); }
   chw = std::max(2, std::min(chw, std::min(64, c->in_tiles)));
+  if (nranks > 1) chw = std::max(2, std::min(chw, c->in_tiles / nranks));   // a sub-chunk's tensor-store box never exceeds one owner's rows of the transposed view
   if (c->LN == 2 && (chw % 2 == 0)) chw--;                 // (CHW + 1) tiles of 64 bytes: a multiple of 128
   c->CHW = chw;
   c->nsc = (c->in_tiles + chw - 1) / chw;
@@ -1130,7 +1138,7 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     return B2_OK;
   };
   RET(build_lanes(lam, &s->pfl, &s->pid, &s->pu1, &s->pu2));
-  if (s->dense && getenv("B2_NOBLOCKS") == nullptr) {
+  if (s->dense) {
     // parity classes of the modes: row r of fwd (= mode r) touches even columns only, or odd columns only
     const int m0 = s->m0, ce = (m0 + 1) / 2, co = m0 / 2;
     std::vector<int> cls(m0, 0), perm;
@@ -1421,8 +1429,8 @@ int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space
   if (r != B2_OK) { delete sp; return r; }
   // padded so that the 4-row lane groups split evenly over the ranks (slab decomposition)
   for (int ax = 0; ax < 2; ax++) sp->P[ax] = roundup(std::max(sp->b[ax].rows_phys, sp->b[ax].rows_ortho), 4 * ctx->nranks);
-  r = make_cfg(sp->b[1], sp->P[1], sp->P[0], &sp->cfg[0]);
-  if (r == B2_OK) r = make_cfg(sp->b[0], sp->P[0], sp->P[1], &sp->cfg[1]);
+  r = make_cfg(sp->b[1], sp->P[1], sp->P[0], &sp->cfg[0], ctx->nranks);
+  if (r == B2_OK) r = make_cfg(sp->b[0], sp->P[0], sp->P[1], &sp->cfg[1], ctx->nranks);
   if (r == B2_OK) r = sp->b[1].init(sp->cfg[0].C, sp->cfg[0].TPL);   // cfg[0]: lanes along axis 1
   if (r == B2_OK) r = sp->b[0].init(sp->cfg[1].C, sp->cfg[1].TPL);
   if (r != B2_OK) { delete sp; return r; }
@@ -1908,7 +1916,7 @@ static int nav_update_fused(b2_navier* nv) {
   // Independent passes run as parallel branches (three streams = three branches of the captured graph): a pass
   // has ~P/4 CTAs, which fills the GPU only for the largest grids.  With several GPUs every stream has its own
   // barrier flags and epoch (ctx_barrier), so the branches stay independent across the exchange barriers too.
-  const bool par = nv->branches && (ctx->nranks == 1 || getenv("B2_NOBRANCH_MULTI") == nullptr);   // every stream has its own barrier flags
+  const bool par = nv->branches;   // (every stream has its own barrier flags)
   auto on = [&](int k) { ctx->cur = par ? nav_stream(ctx, k) : ctx->stream; };
   auto after = [&](int k, int j) -> int { return par ? nav_after(ctx, k, j) : B2_OK; };
   RET(after(1, 0)); RET(after(2, 0));   // fork
@@ -2118,7 +2126,7 @@ int b2_navier_info(const b2_navier* nv, long long* out) {
   const b2_solver* ps = nv->pois;
   out[0] = ps && ps->blocks; out[1] = nv->sp_ortho->P[0]; out[2] = nv->sp_ortho->P[1];
   out[3] = ps ? ps->m0 : 0; out[4] = ps ? ps->ce : 0; out[5] = ps ? ps->co : 0;
-  out[6] = nv->branches && (nv->ctx->nranks == 1 || getenv("B2_NOBRANCH_MULTI") == nullptr); out[7] = nv->launches_per_step;
+  out[6] = nv->branches; out[7] = nv->launches_per_step;
   return B2_OK;
 }
 int b2_navier_launch_count(const b2_navier* nv, long long* k) { *k = nv->launches_per_step; return B2_OK; }

@@ -48,12 +48,7 @@ struct GemmParams {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
 #ifdef B2_EMU
-  // A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4], C[row = lane / 4][col = 2 (lane % 4) + {0, 1}]
-  const int lane = threadIdx.x & 31, row = lane >> 2, col = 2 * (lane & 3);
-  for (int k = 0; k < 4; k++) {
-    const double av = emu::shfl(a, row * 4 + k), b0 = emu::shfl(b, col * 4 + k), b1 = emu::shfl(b, (col + 1) * 4 + k);
-    c0 = fma(av, b0, c0); c1 = fma(av, b1, c1);
-  }
+  emu::dmma884(c0, c1, a, b);
 #else
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 #endif

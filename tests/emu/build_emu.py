@@ -15,9 +15,11 @@ DEPS = sorted(glob.glob(os.path.join(ROOT, "rustpde_mpi_b200", "csrc", "*"))) + 
 def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
+    tmp = f"{OUT}.{os.getpid()}.tmp"   # several ranks of a multi-process test may build at once: build aside, then rename
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-DB2_EMU", "-I", HERE, "-pthread", "-shared", "-fPIC",
-           "-Wno-unused-function", "-o", OUT, SRC]
+           "-Wno-unused-function", "-o", tmp, SRC]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, OUT)
     return OUT
 
 

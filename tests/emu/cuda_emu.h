@@ -41,20 +41,30 @@ using std::max;
 namespace emu {
 struct Dim3 { int x = 1, y = 1, z = 1; };
 
+// Sense-reversing barrier on atomics: the waiters spin briefly and then yield (a mutex / condition-variable barrier wakes
+// all waiters into one lock: with 32-512 OS threads per block on a few cores that dominated the run time of the suite)
 class Barrier {
  public:
-  void reset(int n) { n_ = n; count_ = 0; gen_ = 0; }
+  void reset(int n) { n_ = n; count_.store(0); gen_.store(0); }
   void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    const uint64_t g = gen_;
-    if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
-    else cv_.wait(lk, [&] { return gen_ != g; });
+    const unsigned g = gen_.load(std::memory_order_acquire);
+    if (count_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+      count_.store(0, std::memory_order_relaxed);
+      gen_.store(g + 1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == g) {
+        if (++spins > 32) std::this_thread::yield();
+      }
+    }
   }
  private:
-  std::mutex m_; std::condition_variable cv_; int n_ = 1, count_ = 0; uint64_t gen_ = 0;
+  int n_ = 1;
+  std::atomic<int> count_{0};
+  std::atomic<unsigned> gen_{0};
 };
 
-struct Warp { double buf[32]; Barrier bar; };
+struct Warp { double buf[32]; double buf2[32]; Barrier bar; };
 
 struct Block {
   Barrier bar;
@@ -128,6 +138,21 @@ template <class F> inline void launch(int grid, int blockdim, size_t smem, F&& b
   }
 }
 
+// mma.sync.m8n8k4.f64 for the emulated GEMM: A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4],
+// C[row = lane / 4][col = 2 (lane % 4) + {0, 1}]; one exchange through the warp's buffers per instruction
+inline void dmma884(double& c0, double& c1, double a, double b) {
+  Warp& w = block().warps[t_threadIdx.x / 32];
+  const int lane = t_threadIdx.x % 32, row = lane >> 2, col = 2 * (lane & 3);
+  w.buf[lane] = a; w.buf2[lane] = b;
+  w.bar.wait();
+  for (int k = 0; k < 4; k++) {
+    const double av = w.buf[row * 4 + k];
+    c0 = std::fma(av, w.buf2[col * 4 + k], c0);
+    c1 = std::fma(av, w.buf2[(col + 1) * 4 + k], c1);
+  }
+  w.bar.wait();
+}
+
 inline double shfl(double v, int src_lane) {
   Warp& w = block().warps[t_threadIdx.x / 32];
   const int lane = t_threadIdx.x % 32;
@@ -187,6 +212,8 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0 };
+static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) { *s = cudaStreamCaptureStatusNone; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }

@@ -21,8 +21,8 @@ def run(world, args, port):
 
 
 @pytest.mark.parametrize("world,nx,ny,steps,periodic,mode,port", [
-    (2, 65, 65, 2, 0, 1, 29611),   # confined, fused schedule
-    (2, 64, 65, 2, 1, 1, 29612),   # periodic, fused
+    (2, 65, 65, 1, 0, 1, 29611),   # confined, fused schedule
+    (2, 64, 65, 1, 1, 1, 29612),   # periodic, fused
     (2, 65, 65, 1, 0, 0, 29613),   # confined, one pass pair per reference call
     (3, 65, 65, 1, 0, 1, 29614),   # uneven split: 17 lane groups padded to 18 over 3 ranks
 ])

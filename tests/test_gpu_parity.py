@@ -120,3 +120,31 @@ def test_navier_hc_steps(periodic):
     """Navier2D::new_confined / new_periodic with bc = "hc" (navier.rs:245-252, 366-372; bc_hc boundary field)."""
     errs = g.check_navier(128 if periodic else 129, 129, 5, periodic, bc="hc")
     assert max(errs.values()) < g.TOL, errs
+
+
+@pytest.mark.parametrize("periodic,shape,shape2", [(False, (65, 65), (129, 65)), (True, (64, 65), (128, 129))])
+def test_snapshot_write_read_and_interpolation(periodic, shape, shape2, tmp_path):
+    """navier_io.rs:21-62 + field/io.rs:75-84,151-176: same grid = identical state, other grid = interpolate_2d + backward."""
+    import rustpde_mpi_b200 as b2
+    from rustpde_mpi_b200 import snapshot as sn
+
+    a = b2.Navier2D(*shape, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+    a.update(3)
+    fn = str(tmp_path / "snap.npz")
+    a.write(fn)
+    b = b2.Navier2D(*shape, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+    b.read(fn)
+    assert abs(b.get_time() - a.get_time()) < 1e-15
+    for k, v in a.state().items():
+        assert np.array_equal(b.state()[k], v), k
+    a.update(2); b.update(2)                       # a restarted run continues bit-identically
+    for k, v in a.state().items():
+        assert np.array_equal(b.state()[k], v), k
+    c = b2.Navier2D(*shape2, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=periodic)
+    c.read(fn)
+    data = sn.load_datasets(fn)
+    for attr, group in sn.FIELD_GROUPS:
+        f = getattr(c, attr)
+        sh, cx = f.space.shape(b2.SPECTRAL)
+        want = sn.read_vhat(data, group, sh, cx, periodic)
+        assert np.array_equal(f.vhat, want), attr
