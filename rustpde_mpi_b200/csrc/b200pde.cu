@@ -871,6 +871,9 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c, int nran
 static int alloc_zero(b2_space* sp, double** out) {
   RET(ctx_alloc(sp->ctx, sp->elems() * sizeof(double), out));
   CK(cudaMemsetAsync(*out, 0, sp->elems() * sizeof(double), sp->ctx->stream));
+  // several GPUs: a peer may store into this array as soon as ITS allocation returns -- not before every rank has cleared its copy
+  // (allocation is collective on the symmetric heap: every rank allocates the same arrays in the same order)
+  if (sp->ctx->nranks > 1 && sp->ctx->attached) RET(ctx_barrier(sp->ctx));
   return B2_OK;
 }
 
