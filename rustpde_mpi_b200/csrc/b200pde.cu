@@ -1064,17 +1064,21 @@ static int gemm_run(b2_ctx* ctx, const GemmPlan& g, const double* B, double* C) 
   static bool attr_set[64] = {false};
   static const int dbg = getenv("B2_GEMM_DBG") ? atoi(getenv("B2_GEMM_DBG")) : 0;   // measurement only (tools/sweep.py): see gemm_pb_kernel
   if (!attr_set[ctx->device & 63]) {
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
   GemmParams p = g.p;
   p.B = B; p.C = C;
   if (ctx->nranks > 1) p.c_off = reinterpret_cast<const char*>(C) - static_cast<const char*>(ctx->peer_base[ctx->rank]);
-  if (dbg == 1) B2_LAUNCH(gemm_pb_kernel<1>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else if (dbg == 2) B2_LAUNCH(gemm_pb_kernel<2>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else B2_LAUNCH(gemm_pb_kernel<0>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  if (dbg == 1) B2_LAUNCH((gemm_pb_kernel<1, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 2) B2_LAUNCH((gemm_pb_kernel<2, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 3) B2_LAUNCH((gemm_pb_kernel<0, true>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 4) B2_LAUNCH((gemm_pb_kernel<1, true>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else B2_LAUNCH((gemm_pb_kernel<0, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
   CK(cudaGetLastError());
   ctx->launches++;
   return ctx->nranks > 1 ? ctx_barrier(ctx) : B2_OK;   // the epilogue wrote into the peers' slabs
