@@ -36,6 +36,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 static inline int roundup(int a, int b) { return (a + b - 1) / b * b; }
+#ifdef B2_EMU
+#define B2_SPIN_PAUSE() std::this_thread::yield()   // emulated ranks are OS processes sharing a few cores
+#else
+#define B2_SPIN_PAUSE()
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // structures
@@ -106,7 +111,7 @@ __global__ void k_barrier(unsigned long long* const* peers_, int rank, int nrank
   if ((int)threadIdx.x < nranks) {
     *reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + rank) = e;
     __threadfence_system();
-    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) {}
+    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) { B2_SPIN_PAUSE(); }
   }
   __syncthreads();
   if (threadIdx.x == 0) mine[B2_MAXPEERS] = e;
@@ -130,7 +135,7 @@ __global__ void k_allreduce(unsigned long long* const* peers_, int rank, int nra
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + rank) = e;
     __threadfence_system();
-    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) {}
+    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) { B2_SPIN_PAUSE(); }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -857,6 +862,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c, int nran
   int chw = (int)(room / ((size_t)nwarps * 2) / tile_bytes) - 1;   // one halo tile in front of every slot
   if (const char* e = getenv("B2_CHW")) { int v = atoi(e); if (v >= 2) chw = std::min(chw, v); }
   chw = std::max(2, std::min(chw, std::min(64, c->in_tiles)));
+  if (wbytes > 100 * 1024) chw = std::min(chw, 12);   // long lanes: 12-tile sub-chunks pipeline better than the largest that fit (C4: lane time 8.50 -> 8.27 ms)
   if (nranks > 1) chw = std::max(2, std::min(chw, c->in_tiles / nranks));   // a sub-chunk's tensor-store box never exceeds one owner's rows of the transposed view
   if (c->LN == 2 && (chw % 2 == 0)) chw--;                 // (CHW + 1) tiles of 64 bytes: a multiple of 128
   c->CHW = chw;
@@ -1064,21 +1070,17 @@ static int gemm_run(b2_ctx* ctx, const GemmPlan& g, const double* B, double* C) 
   static bool attr_set[64] = {false};
   static const int dbg = getenv("B2_GEMM_DBG") ? atoi(getenv("B2_GEMM_DBG")) : 0;   // measurement only (tools/sweep.py): see gemm_pb_kernel
   if (!attr_set[ctx->device & 63]) {
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_pb_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_pb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
     attr_set[ctx->device & 63] = true;
   }
   GemmParams p = g.p;
   p.B = B; p.C = C;
   if (ctx->nranks > 1) p.c_off = reinterpret_cast<const char*>(C) - static_cast<const char*>(ctx->peer_base[ctx->rank]);
-  if (dbg == 1) B2_LAUNCH((gemm_pb_kernel<1, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else if (dbg == 2) B2_LAUNCH((gemm_pb_kernel<2, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else if (dbg == 3) B2_LAUNCH((gemm_pb_kernel<0, true>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else if (dbg == 4) B2_LAUNCH((gemm_pb_kernel<1, true>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else B2_LAUNCH((gemm_pb_kernel<0, false>), g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  if (dbg == 1) B2_LAUNCH(gemm_pb_kernel<1>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 2) B2_LAUNCH(gemm_pb_kernel<2>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else B2_LAUNCH(gemm_pb_kernel<0>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
   CK(cudaGetLastError());
   ctx->launches++;
   return ctx->nranks > 1 ? ctx_barrier(ctx) : B2_OK;   // the epilogue wrote into the peers' slabs

@@ -55,9 +55,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // DBG (measurement only, results invalid): 1 = no copies and no waits (arithmetic + shared-memory reads alone), 2 = copies and waits
-// without the DMMAs (data movement alone).  DB: fragments double-buffered in registers inside a stage (the loads of k4 step kk + 1 are
-// issued before the DMMAs of step kk)
-template <int DBG, bool DB>
+// without the DMMAs (data movement alone).  (Measured: double-buffering the fragments in registers changes neither the arithmetic-only
+// nor the full time -- the four warps of a scheduler hide the fragment loads of each other.)
+template <int DBG>
 __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ GemmParams P) {
   B2_DYN_SMEM(char, gsm);
   uint64_t* full = reinterpret_cast<uint64_t*>(gsm);       // stage s has landed (bulk copies, transaction count)
@@ -127,27 +127,13 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
     if (DBG != 1) mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
     const double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
     if (mf_n > 0 && nf_n > 0 && DBG != 2) {
-      double fa[2][4], fb[2][4];
-      if (DB) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) fa[0][i] = st[aoff + i * 32];
-#pragma unroll
-        for (int j = 0; j < 4; j++) fb[0][j] = st[boff[0] + j * 32];
-      }
 #pragma unroll
       for (int kk = 0; kk < G_KK; kk++) {
-        double* a = fa[kk & 1]; double* bf = fb[kk & 1];
-        if (!DB) {
+        double a[4], bf[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) a[i] = st[aoff + (kk * 8 + i) * 32];
+        for (int i = 0; i < 4; i++) a[i] = st[aoff + (kk * 8 + i) * 32];
 #pragma unroll
-          for (int j = 0; j < 4; j++) bf[j] = st[boff[kk] + j * 32];
-        } else if (kk + 1 < G_KK) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) fa[(kk + 1) & 1][i] = st[aoff + ((kk + 1) * 8 + i) * 32];
-#pragma unroll
-          for (int j = 0; j < 4; j++) fb[(kk + 1) & 1][j] = st[boff[(kk + 1) % G_KK] + j * 32];
-        }
+        for (int j = 0; j < 4; j++) bf[j] = st[boff[kk] + j * 32];
         if (mf_n == 4 && nf_n == 4) {
 #pragma unroll
           for (int i = 0; i < 4; i++)
