@@ -21,11 +21,13 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
+    tmp = f"{OUT}.{os.getpid()}.tmp"   # build aside and rename: a reader (another rank, a snapshot) never sees a half-written library
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
+           "-shared", "-Xcompiler", "-fPIC", "-o", tmp, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -1269,7 +1269,7 @@ struct b2_navier {
   double *that = nullptr, *tbc_ortho = nullptr, *tbc_diff = nullptr, *rhs = nullptr, *g1 = nullptr, *g2 = nullptr, *conv = nullptr, *div = nullptr, *ux = nullptr, *uy = nullptr;
   double* d_scalar = nullptr;
   // fused schedule: intermediates (suffix T = stored in the transposed orientation)
-  double *Pf[3] = {nullptr}, *Qf[3] = {nullptr}, *V1[3] = {nullptr}, *Cx[3] = {nullptr}, *Zf[3] = {nullptr};
+  double *Pf[3] = {nullptr}, *Qf[3] = {nullptr}, *V1[3] = {nullptr}, *Cx[3] = {nullptr}, *Zf[3] = {nullptr}, *Of[3] = {nullptr};
   double *VTv = nullptr, *uxT = nullptr, *uyT = nullptr, *cv[3] = {nullptr}, *PH = nullptr, *PHy = nullptr, *F1 = nullptr, *F2 = nullptr, *R0 = nullptr;
   double *G0 = nullptr, *G1 = nullptr, *U1 = nullptr, *U2 = nullptr, *U3 = nullptr;
   double *GxT = nullptr, *GyT = nullptr, *KbT = nullptr, *KTT = nullptr;   // constants of the step
@@ -1774,7 +1774,7 @@ int b2_navier2d_create(b2_ctx* ctx, int nx, int ny, double ra, double pr, double
     double** fw[] = {&nv->VTv, &nv->uxT, &nv->uyT, &nv->cv[0], &nv->cv[1], &nv->cv[2], &nv->PH, &nv->PHy, &nv->F1, &nv->F2, &nv->R0, &nv->G0, &nv->G1,
                      &nv->U1, &nv->U2, &nv->U3, &nv->GxT, &nv->GyT, &nv->KbT, &nv->KTT};
     for (auto w : fw) RET(nav_alloc(so, w));
-    for (int i = 0; i < 3; i++) { RET(nav_alloc(so, &nv->Pf[i])); RET(nav_alloc(so, &nv->Qf[i])); RET(nav_alloc(so, &nv->V1[i])); RET(nav_alloc(so, &nv->Cx[i])); RET(nav_alloc(so, &nv->Zf[i])); }
+    for (int i = 0; i < 3; i++) { RET(nav_alloc(so, &nv->Pf[i])); RET(nav_alloc(so, &nv->Qf[i])); RET(nav_alloc(so, &nv->V1[i])); RET(nav_alloc(so, &nv->Cx[i])); RET(nav_alloc(so, &nv->Zf[i])); RET(nav_alloc(so, &nv->Of[i])); }
     const Base1& bxo = so->b[0]; const Base1& byo = so->b[1];
     // GxT / GyT = backward(d/dx tempbc), backward(d/dy tempbc): physical values, kept in x-lane orientation
     for (int d = 0; d < 2; d++) {
@@ -1803,7 +1803,7 @@ int b2_navier_destroy(b2_navier* nv) {
   double* fw[] = {nv->VTv, nv->uxT, nv->uyT, nv->cv[0], nv->cv[1], nv->cv[2], nv->PH, nv->PHy, nv->F1, nv->F2, nv->R0, nv->G0, nv->G1, nv->U1, nv->U2, nv->U3,
                   nv->GxT, nv->GyT, nv->KbT, nv->KTT};
   for (auto w : fw) ctx_free(nv->ctx, w);
-  for (int i = 0; i < 3; i++) { ctx_free(nv->ctx, nv->Pf[i]); ctx_free(nv->ctx, nv->Qf[i]); ctx_free(nv->ctx, nv->V1[i]); ctx_free(nv->ctx, nv->Cx[i]); ctx_free(nv->ctx, nv->Zf[i]); }
+  for (int i = 0; i < 3; i++) { ctx_free(nv->ctx, nv->Pf[i]); ctx_free(nv->ctx, nv->Qf[i]); ctx_free(nv->ctx, nv->V1[i]); ctx_free(nv->ctx, nv->Cx[i]); ctx_free(nv->ctx, nv->Zf[i]); ctx_free(nv->ctx, nv->Of[i]); }
   b2_field* fs[] = {nv->temp, nv->velx, nv->vely, nv->pres, nv->pseu, nv->tempbc};
   for (auto f : fs) b2_field_destroy(f);
 #ifndef B2_EMU
@@ -1944,10 +1944,13 @@ static int nav_update_fused(b2_navier* nv) {
     const Base1& by = f->sp->b[1];
     const double* src = f->vhat->d;
     Prog y;
-    y.load(src, by.rows_spec); y.to_ortho(by); int l = y.backward_ortho(by); y.store(nv->Pf[i], l, ST_TRANS);
-    y.load(src, by.rows_spec); y.to_ortho(by); y.deriv_axis(by, 1, sy); l = y.backward_ortho(by); y.store(nv->Qf[i], l, ST_TRANS);
-    y.load(src, by.rows_spec); y.to_ortho(by); emit_hh_axis(y, nv->hh[i], 1); y.store(nv->V1[i], by.m, ST_TRANS);
-    if (i == 2) { y.load(src, by.rows_spec); y.to_ortho(by); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->VTv, by.m, ST_TRANS); }
+    // the orthonormal image of the lanes is needed three (four) times: project once, keep a copy (a zero-copy slab store and
+    // zero-copy reloads) instead of repeating the stencil pass after every reload of the composite coefficients
+    y.load(src, by.rows_spec); int lo = y.to_ortho(by); y.store(nv->Of[i], lo, 0);
+    int l = y.backward_ortho(by); y.store(nv->Pf[i], l, ST_TRANS);
+    y.load(nv->Of[i], lo); y.deriv_axis(by, 1, sy); l = y.backward_ortho(by); y.store(nv->Qf[i], l, ST_TRANS);
+    y.load(nv->Of[i], lo); emit_hh_axis(y, nv->hh[i], 1); y.store(nv->V1[i], by.m, ST_TRANS);
+    if (i == 2) { y.load(nv->Of[i], lo); emit_hh_axis(y, nv->hh[1], 1); y.store(nv->VTv, by.m, ST_TRANS); }
     RET(run_pass(so, 0, y));
   }
   // ---- A-x: convection velocities ux, uy (physical, x-lane orientation) ----
@@ -2052,8 +2055,8 @@ static int nav_update_fused(b2_navier* nv) {
     const Base1& byv = nv->sp_vel->b[1]; const Base1& bxv = nv->sp_vel->b[0];
     Prog y;
     for (int k = 0; k < 3; k++) {
-      y.load(nv->pseu->vhat->d, byp.m);
-      y.to_ortho(byp);
+      if (k == 0) { y.load(nv->pseu->vhat->d, byp.m); const int lo = y.to_ortho(byp); y.store(nv->G0, lo, 0); }   // (G0 is free again: one projection, two zero-copy reloads)
+      else y.load(nv->G0, byo.rows_ortho);
       if (k == 1) y.deriv_axis(byo, 1, sy);
       int l = byo.rows_ortho;
       if (k < 2) l = y.from_ortho(byv);

@@ -636,15 +636,38 @@ __device__ __noinline__ void store_warps(const LaneProg& P, const LaneOp& op, co
     }
     fence_proxy_async();
     __syncwarp();
+    // Several GPUs: a sub-chunk whose box lies completely inside ONE owner's view of the transposed array leaves as one tensor
+    // store into that owner's slab.  A box that straddles two owners or overhangs the end of the view is NOT handed to the copy
+    // engine (partly out-of-bounds tensor stores on peer memory faulted on hardware): the warp writes those few tiles itself.
+    bool peer_irregular = false;
+    if ((flags & ST_TRANS) && (flags & ST_PEER)) {
+      const int gpr = P.groups_per_rank, o0 = J0 / gpr;
+      peer_irregular = (J0 + CHW > (o0 + 1) * gpr) || (J0 + CHW > in_tiles);
+      if (peer_irregular) {
+        char* const* peers = reinterpret_cast<char* const*>(op.p1);
+        const size_t off = static_cast<const char*>(op.p0) - peers[P.rank];
+        for (int pc = ln; pc < npc; pc += 32) {
+          const int tt = pc >> LSH, J = J0 + tt;
+          if (J >= in_tiles) break;
+          const int o = J / gpr;
+          // destination tile (J - o gpr, g) of owner o: [jl][lane]; slot piece pc & (2^LSH - 1) = (jl, lane pair)
+          double* d = reinterpret_cast<double*>(peers[o] + off) + ((size_t)(J - o * gpr) * P.out_tiles + g) * 16
+                      + ((pc & ((1 << LSH) - 1)) / HL) * 4 + lb + 2 * (pc & (HL - 1));
+          const double2 v = st[pc];
+          if (flags & ST_ACC) { atomicAdd(d, v.x); atomicAdd(d + 1, v.y); }
+          else *reinterpret_cast<double2*>(d) = v;
+        }
+      }
+    }
     if (ln == 0) {
       // whole lane groups (LN == 4): a destination tile is 128 contiguous bytes, and the view says so ([16][tile column][tile
-      // row]: one 128-byte row per tile -- the copy engine works row by row, and 32-byte rows made this store 4x slower)
-      if ((flags & ST_TRANS) && (flags & ST_PEER)) {
-        const int gpr = P.groups_per_rank, Jl = min(J0 + CHW, in_tiles) - 1;
-        for (int o = J0 / gpr; o <= Jl / gpr; o++) {
-          if (LN == 4) { if (flags & ST_ACC) tma_reduce_add_3d(tm + o, 0, g, J0 - o * gpr, st); else tma_store_3d(tm + o, 0, g, J0 - o * gpr, st); }
-          else if (flags & ST_ACC) tma_reduce_add_4d(tm + o, lb, 0, g, J0 - o * gpr, st); else tma_store_4d(tm + o, lb, 0, g, J0 - o * gpr, st);
-        }
+      // row]: one 128-byte row per tile)
+      if (peer_irregular) {
+        // (an empty group keeps the slot accounting of bulk_wait_read uniform)
+      } else if ((flags & ST_TRANS) && (flags & ST_PEER)) {
+        const int gpr = P.groups_per_rank, o = J0 / gpr;
+        if (LN == 4) { if (flags & ST_ACC) tma_reduce_add_3d(tm + o, 0, g, J0 - o * gpr, st); else tma_store_3d(tm + o, 0, g, J0 - o * gpr, st); }
+        else if (flags & ST_ACC) tma_reduce_add_4d(tm + o, lb, 0, g, J0 - o * gpr, st); else tma_store_4d(tm + o, lb, 0, g, J0 - o * gpr, st);
       } else if (flags & ST_TRANS) {
         if (LN == 4) { if (flags & ST_ACC) tma_reduce_add_3d(tm, 0, g, J0, st); else tma_store_3d(tm, 0, g, J0, st); }
         else if (flags & ST_ACC) tma_reduce_add_4d(tm, lb, 0, g, J0, st); else tma_store_4d(tm, lb, 0, g, J0, st);

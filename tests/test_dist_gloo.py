@@ -11,8 +11,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(world, args, port):
-    env = dict(os.environ, B2_TEST_EMU="1", OMP_NUM_THREADS="1")
+def run(world, args, port, extra_env=None):
+    env = dict(os.environ, B2_TEST_EMU="1", OMP_NUM_THREADS="1", **(extra_env or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")] + [str(a) for a in args]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
@@ -28,3 +28,9 @@ def run(world, args, port):
 ])
 def test_slab_decomposition_matches_serial_oracle(world, nx, ny, steps, periodic, mode, port):
     run(world, (nx, ny, steps, periodic, mode), port)
+
+
+def test_sub_chunks_that_straddle_two_owners():
+    """5-tile sub-chunks against 6 tiles per rank: boxes that straddle two owners' slabs or overhang the view take the warp's
+    own peer stores instead of a tensor store (lane_kernel.cuh, store_warps)."""
+    run(3, (65, 65, 1, 0, 1), 29615, {"B2_CHW": "5"})
