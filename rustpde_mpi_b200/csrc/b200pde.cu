@@ -1077,10 +1077,12 @@ static int gemm_run(b2_ctx* ctx, const GemmPlan& g, const double* B, double* C) 
   }
   GemmParams p = g.p;
   p.B = B; p.C = C;
+  static const int gate = getenv("B2_GEMM_GATE") ? std::max(1, std::min(G_NSTAGE - 1, atoi(getenv("B2_GEMM_GATE")))) : 2;   // measurement knob
+  p.gate = gate;
   if (ctx->nranks > 1) p.c_off = reinterpret_cast<const char*>(C) - static_cast<const char*>(ctx->peer_base[ctx->rank]);
-  if (dbg == 1) B2_LAUNCH(gemm_pb_kernel<1>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else if (dbg == 2) B2_LAUNCH(gemm_pb_kernel<2>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
-  else B2_LAUNCH(gemm_pb_kernel<0>, g.grid, 512, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  if (dbg == 1) B2_LAUNCH(gemm_pb_kernel<1>, g.grid, G_THREADS, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else if (dbg == 2) B2_LAUNCH(gemm_pb_kernel<2>, g.grid, G_THREADS, (size_t)G_SMEM_BYTES, ctx->cur, p);
+  else B2_LAUNCH(gemm_pb_kernel<0>, g.grid, G_THREADS, (size_t)G_SMEM_BYTES, ctx->cur, p);
   CK(cudaGetLastError());
   ctx->launches++;
   return ctx->nranks > 1 ? ctx_barrier(ctx) : B2_OK;   // the epilogue wrote into the peers' slabs

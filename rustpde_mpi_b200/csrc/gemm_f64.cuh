@@ -14,14 +14,15 @@
 // wants: thread (k = lane % 4, n = lane / 4) reads element [row(k)][n % 4] of tile n / 4, conflict-free with a 32-byte
 // skew between tile-row slots.  A_b is packed on the host in fragment order ([m tile][k stage][k4 step][8-row
 // fragment][lane]), one 8 KB bulk copy per block and stage.  Arithmetic: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05
-// has no FP64 path), 16 warps x (32 x 32) outputs, accumulators in registers, a 4-stage full/empty mbarrier pipeline
-// without CTA barriers (bounded skew of two stages between the warps; one thread refills released buffers).
+// has no FP64 path), 16 compute warps x (32 x 32) outputs, accumulators in registers, a 4-stage full/empty mbarrier pipeline
+// without CTA barriers, fed by a seventeenth warp that only issues the bulk copies.
 // The epilogue writes 16-byte pieces (full 32-byte sectors per quad pair) straight into the tiled destination --
 // with several GPUs into the slab of the rank that owns the output rows (the pencil exchange rides on the epilogue).
 #pragma once
 #include "async_ops.cuh"
 
 #define G_NSTAGE 4
+#define G_THREADS 544                                    // 16 compute warps + one copy warp
 #define G_KK 4                                           // k4 steps per stage: a stage holds 16 k per block
 #define G_SLOT_PITCH (32 * 16 + 4)                       // doubles per tile-row slot of B: 32 tiles + 32 bytes of skew
 #define G_ACHUNK (G_KK * 8 * 32)                         // packed A per block and stage: 64 rows x 16 k
@@ -44,6 +45,7 @@ struct GemmParams {
   int offB[2], strB;        // natural B row of (b, k) = offB[b] + k * strB   (strB = 2: offB = {0, 1})
   int offC[2], strC;        // natural C row of (b, m)
   int rows_per_rank;        // C rows owned by one rank (multiple of 4); >= all rows on one GPU
+  int gate;                 // a warp starts stage ks only when every warp has finished stage ks - gate (1 .. G_NSTAGE - 1)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -58,7 +60,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // without the DMMAs (data movement alone).  (Measured: double-buffering the fragments in registers changes neither the arithmetic-only
 // nor the full time -- the four warps of a scheduler hide the fragment loads of each other.)
 template <int DBG>
-__global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ GemmParams P) {
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_pb_kernel(const __grid_constant__ GemmParams P) {
   B2_DYN_SMEM(char, gsm);
   uint64_t* full = reinterpret_cast<uint64_t*>(gsm);       // stage s has landed (bulk copies, transaction count)
   uint64_t* empty = full + G_NSTAGE;                       // all 16 warps have finished reading stage s
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
     mbar_fence_init();
   }
   __syncthreads();
-  auto issue = [&](int ks) {   // thread 0: stage ks -> buffer ks % G_NSTAGE
+  auto issue = [&](int ks) {   // copy warp: stage ks -> buffer ks % G_NSTAGE
     const int s = ks % G_NSTAGE;
     double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
     const uint32_t rowbytes = (uint32_t)ntc * 128u;
@@ -88,8 +90,17 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
     for (int bb = 0; bb < 2; bb++)
       bulk_load_1d(st + 2 * G_KK * G_SLOT_PITCH + bb * G_ACHUNK, P.A[bb] + ((size_t)mt * nks + ks) * G_ACHUNK, G_ACHUNK * 8u, &full[s]);
   };
-  int issued = 0;
-  if (tid == 0 && DBG != 1) for (; issued < G_NSTAGE && issued < nks; issued++) issue(issued);
+  // Warp 16 only moves data: it refills a buffer as soon as all 16 compute warps have released it.  (With the copies issued by
+  // a compute thread, that thread's warp fell behind by the issue work of every stage, and -- the skew between the warps being
+  // bounded -- all the others waited for it: 4.4 ms of arithmetic took 5.0 ms.)
+  if (warp == 16) {
+    if (lane == 0 && DBG != 1)
+      for (int ks = 0; ks < nks; ks++) {
+        if (ks >= G_NSTAGE) mbar_wait(&empty[ks % G_NSTAGE], (unsigned)(((ks / G_NSTAGE) - 1) & 1));
+        issue(ks);
+      }
+    return;
+  }
 
   // fragment addresses inside a stage (doubles)
   const int k = lane & 3, n8 = lane >> 2;
@@ -120,10 +131,7 @@ __global__ void __launch_bounds__(512) gemm_pb_kernel(const __grid_constant__ Ge
   // latency.  With it, the refill of a buffer is always requested two stages before anybody needs it.)
   for (int ks = 0; ks < nks; ks++) {
     const int s = ks % G_NSTAGE;
-    if (ks >= 2 && DBG != 1) mbar_wait(&empty[(ks - 2) % G_NSTAGE], (unsigned)(((ks - 2) / G_NSTAGE) & 1));
-    if (tid == 0 && DBG != 1) {   // refill every buffer that all warps have released
-      while (issued < nks && mbar_test(&empty[issued % G_NSTAGE], (unsigned)(((issued / G_NSTAGE) - 1) & 1))) { issue(issued); issued++; }
-    }
+    if (ks >= P.gate && DBG != 1) mbar_wait(&empty[(ks - P.gate) % G_NSTAGE], (unsigned)(((ks - P.gate) / G_NSTAGE) & 1));
     if (DBG != 1) mbar_wait(&full[s], (unsigned)((ks / G_NSTAGE) & 1));
     const double* st = stage0 + (size_t)s * G_STAGE_DOUBLES;
     if (mf_n > 0 && nf_n > 0 && DBG != 2) {
