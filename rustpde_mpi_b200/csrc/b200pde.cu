@@ -37,7 +37,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 static inline int roundup(int a, int b) { return (a + b - 1) / b * b; }
 #ifdef B2_EMU
-#define B2_SPIN_PAUSE() std::this_thread::yield()   // emulated ranks are OS processes sharing a few cores
+#define B2_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(20))   // emulated ranks are OS processes sharing a few cores
 #else
 #define B2_SPIN_PAUSE()
 #endif

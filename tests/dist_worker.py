@@ -56,6 +56,39 @@ def main():
         assert abs(a - b) <= 1e-10 * abs(b), (name, a, b)
     print(f"rank {rank}/{world}: nx={nx} ny={ny} steps={steps} periodic={periodic} mode={mode} worst_rel_err={worst:.3e}", flush=True)
     assert worst < 1e-10, worst
+    if len(sys.argv) > 6 and sys.argv[6] == "extras":
+        # HholtzMpi / PoissonMpi (src/solver_mpi/{hholtz,poisson}.rs): the field solvers on slabs, input and output as local rows
+        for name, kinds in (("Hholtz", (1, 1)), ("Poisson", (2, 2))):
+            k0 = 4 if periodic else kinds[0]
+            fo = o.Field2(o.Space2(o.Base(k0, nx), o.Base(kinds[1], ny)))
+            fg = b2.Field2(b2.Space2((k0, nx), (kinds[1], ny), ctx=ctx))
+            c = [0.37, 1.3] if name == "Hholtz" else [1.0, 1.0]
+            e = None
+            if not periodic:
+                e = b2.hholtz_eig(k0, nx, c[0]) if name == "Hholtz" else b2.poisson_eig(k0, nx, c[0])
+            so_, sg = getattr(o, name)(fo, c, eig=e), getattr(b2, name)(fg, c)
+            sh = fo.space.to_ortho(fo.vhat).shape
+            rng = np.random.default_rng(11)
+            rhs = rng.standard_normal(sh) + (1j * rng.standard_normal(sh) if periodic else 0)
+            inp = b2.DeviceArray(fg.space, b2.ORTHO)
+            r0, cnt = inp.local_rows()
+            inp.set(rhs[r0:r0 + cnt])
+            x = ctx.all_gather_rows(sg.solve(inp).get())
+            xo = so_.solve(rhs)
+            if name == "Poisson":
+                x[0, 0] = 0; xo[0, 0] = 0
+            err = float(np.abs(x - xo).max() / np.abs(xo).max())
+            assert err < 1e-10, (name, err)
+        # snapshot / restart on slabs (src/field_mpi/io.rs): gathered write on rank 0, every rank reads its rows back
+        import tempfile
+        fn = os.path.join(tempfile.gettempdir(), f"b2_snap_{os.environ.get('MASTER_PORT', '0')}.npz")
+        nav.write(fn)
+        nav2 = b2.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=bool(periodic), ctx=ctx)
+        nav2.read(fn)
+        for k, v in nav.state().items():
+            assert np.array_equal(nav2.state()[k], v), k
+        assert abs(nav2.get_time() - nav.get_time()) < 1e-15
+        print(f"rank {rank}/{world}: extras ok (HholtzMpi, PoissonMpi, snapshot)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

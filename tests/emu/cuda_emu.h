@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -54,7 +55,8 @@ class Barrier {
     } else {
       int spins = 0;
       while (gen_.load(std::memory_order_acquire) == g) {
-        if (++spins > 32) std::this_thread::yield();
+        if (++spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(50));   // a long wait (another rank's process): get off the cores
+        else if (spins > 32) std::this_thread::yield();
       }
     }
   }

@@ -34,3 +34,8 @@ def test_sub_chunks_that_straddle_two_owners():
     """5-tile sub-chunks against 6 tiles per rank: boxes that straddle two owners' slabs or overhang the view take the warp's
     own peer stores instead of a tensor store (lane_kernel.cuh, store_warps)."""
     run(3, (65, 65, 1, 0, 1), 29615, {"B2_CHW": "5"})
+
+
+def test_field_solvers_and_snapshot_on_slabs():
+    """HholtzMpi / PoissonMpi standalone solves and the snapshot write / read path with 2 ranks."""
+    run(2, (65, 65, 1, 0, 1, "extras"), 29616)
