@@ -29,6 +29,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # torchrun pins OMP_NUM_THREADS=1; the (untimed) host LAPACK setup of the Poisson solver is minutes at one thread: give every
+    # rank its share of the host cores before numpy / OpenBLAS load
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["WORLD_SIZE"])))
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")   # CPU arm: idle OpenMP threads must not spin against OpenBLAS's own pool
 
 CONFIGS = {
@@ -247,7 +251,7 @@ def main():
 
     parity = None if args.no_parity else parity_small(b2, ctx, dist)   # same ranks, same context, before the timing
     t_setup = time.perf_counter()
-    eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
+    eig = None if per else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)   # host LAPACK setup (not timed)
     nav = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=per, ctx=ctx, pois_eig=eig)
     nav.init_random(0.1)
     nav.set_mode(args.mode)
