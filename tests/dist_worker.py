@@ -30,8 +30,9 @@ def main():
     if not use_emu:
         torch.cuda.set_device(device)
     nx, ny, steps, periodic, mode = (int(v) for v in sys.argv[1:6])
+    bc = "hc" if "hc" in sys.argv[6:] else "rbc"
     ctx = b2.Context.distributed(device, heap_bytes=(200 * (nx + 16) * (ny + 16) * 8) // world + (8 << 20))
-    nav = b2.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=bool(periodic), ctx=ctx)
+    nav = b2.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, bc, periodic=bool(periodic), ctx=ctx)
     nav.set_mode(mode)
     nav.set_velocity(0.2, 1.0, 1.0)
     nav.set_temperature(0.2, 1.0, 1.0)
@@ -39,7 +40,7 @@ def main():
     got = nav.gather_state()
     dn = nav.div_norm()
     eig = None if periodic else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
-    ref = o.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=bool(periodic), pois_eig=eig)
+    ref = o.Navier2D(nx, ny, 1e5, 1.0, 0.01, 1.0, bc, periodic=bool(periodic), pois_eig=eig)
     ref.set_velocity(0.2, 1.0, 1.0)
     ref.set_temperature(0.2, 1.0, 1.0)
     for _ in range(steps):
@@ -56,7 +57,7 @@ def main():
         assert abs(a - b) <= 1e-10 * abs(b), (name, a, b)
     print(f"rank {rank}/{world}: nx={nx} ny={ny} steps={steps} periodic={periodic} mode={mode} worst_rel_err={worst:.3e}", flush=True)
     assert worst < 1e-10, worst
-    if len(sys.argv) > 6 and sys.argv[6] == "extras":
+    if "extras" in sys.argv[6:]:
         # HholtzMpi / PoissonMpi (src/solver_mpi/{hholtz,poisson}.rs): the field solvers on slabs, input and output as local rows
         for name, kinds in (("Hholtz", (1, 1)), ("Poisson", (2, 2))):
             k0 = 4 if periodic else kinds[0]

@@ -36,6 +36,11 @@ def test_sub_chunks_that_straddle_two_owners():
     run(3, (65, 65, 1, 0, 1), 29615, {"B2_CHW": "5"})
 
 
+def test_hc_boundary_conditions_on_slabs():
+    """bc = "hc" with 2 ranks: the x-dependent boundary field is built per slab, OP_STEN3 / OP_PDMA run on local lanes."""
+    run(2, (65, 65, 1, 0, 1, "hc"), 29617)
+
+
 def test_field_solvers_and_snapshot_on_slabs():
     """HholtzMpi / PoissonMpi standalone solves and the snapshot write / read path with 2 ranks."""
     run(2, (65, 65, 1, 0, 1, "extras"), 29616)
