@@ -233,6 +233,7 @@ struct Base1 {
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
   DVecD d_sten2, d_sten2s, d_s2, d_tfl, d_tid, d_tu1, d_bd, d_bu1, d_bu2, d_tw, d_tw2, d_isin;
   std::vector<double> ca, cb;                         // cdn stencil: ortho_k = c_k + ca[k-1] c_{k-1} + cb[k-2] c_{k-2}
+  DVecD d_dfwd, d_dbwd; bool dense_tr = false;       // transform sizes the FFT core does not handle: dense matrices (OP_DENSE)
   DVecD d_ca, d_cb, d_pent; int pent_L = 0;            // cdn: stencil vectors, packed PdmaPlus2 LU of S^T S (from_ortho)
   DVecD d_s2_sc, d_bd_sc, d_bu1_sc, d_bu2_sc, d_sten2s_sc;   // scan-layout copies for band ops folded into an LU solve (see run_pass)
 
@@ -294,7 +295,7 @@ struct Base1 {
   void release() {
     const void* keys[] = {d_bd.d, d_bu1.d, d_bu2.d, d_s2.d, d_sten2s.d};
     for (auto k : keys) if (k) scan_of().erase(k);
-    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc, &d_sten2s_sc, &d_ca, &d_cb, &d_pent};
+    DVecD* all[] = {&d_sten2, &d_sten2s, &d_s2, &d_tfl, &d_tid, &d_tu1, &d_bd, &d_bu1, &d_bu2, &d_tw, &d_tw2, &d_isin, &d_s2_sc, &d_bd_sc, &d_bu1_sc, &d_bu2_sc, &d_sten2s_sc, &d_ca, &d_cb, &d_pent, &d_dfwd, &d_dbwd};
     for (auto* v : all) v->release();
   }
 };
@@ -392,6 +393,31 @@ int Base1::init(int C, int TPL) {
     for (int j = 0; j <= M; j++) { tw2[2 * j] = (double)cosl(2 * PI * j / N); tw2[2 * j + 1] = (double)(-sinl(2 * PI * j / N)); }
     for (int k = 1; k < M; k++) isin[k] = (double)(1.0L / (4.0L * sinl(PI * k / N)));
     RET(d_tw.upload(tw)); RET(d_tw2.upload(tw2)); RET(d_isin.upload(isin));
+  } else if (n <= 2049) {
+    // any other size: the transforms as dense matrices, applied per lane by OP_DENSE -- O(n^2) per lane, meant
+    // for small grids such as the reference's criterion sizes (128, 264, 265, 512)
+    const long double PI = 3.14159265358979323846264338327950288L;
+    if (cheb) {   // c = F v: c_k = f_k (-1)^k / (n-1) sum_j g_j v_j cos(pi j k / (n-1));  v = B c: v_j = sum_k (-1)^k c_k cos(pi j k / (n-1))
+      std::vector<double> F((size_t)n * n), B((size_t)n * n);
+      for (int k = 0; k < n; k++)
+        for (int j = 0; j < n; j++) {
+          const long double c = cosl(PI * (long double)((long long)j * k % (2 * (n - 1))) / (n - 1));
+          const long double fk = (k == 0 || k == n - 1) ? 0.5L : 1.0L, gj = (j == 0 || j == n - 1) ? 1.0L : 2.0L, sg = (k & 1) ? -1.0L : 1.0L;
+          F[(size_t)k * n + j] = (double)(fk * sg * gj * c / (n - 1));
+          B[(size_t)j * n + k] = (double)(sg * c);
+        }
+      RET(d_dfwd.upload(F)); RET(d_dbwd.upload(B));
+    } else {      // r2c (unnormalised) / c2r (1/n): rows 2k, 2k+1 = Re, Im of mode k
+      std::vector<double> F((size_t)2 * m * n), B((size_t)n * 2 * m);
+      for (int k = 0; k < m; k++)
+        for (int j = 0; j < n; j++) {
+          const long double a = 2 * PI * (long double)((long long)j * k % n) / n, wk = (k == 0 || 2 * k == n) ? 1.0L : 2.0L;
+          F[(size_t)(2 * k) * n + j] = (double)cosl(a); F[(size_t)(2 * k + 1) * n + j] = (double)(-sinl(a));
+          B[(size_t)j * 2 * m + 2 * k] = (double)(wk * cosl(a) / n); B[(size_t)j * 2 * m + 2 * k + 1] = (double)(-wk * sinl(a) / n);
+        }
+      RET(d_dfwd.upload(F)); RET(d_dbwd.upload(B));
+    }
+    dense_tr = true;
   }
   return B2_OK;
 }
@@ -546,8 +572,13 @@ struct Prog {
   void fdma(int len, const double* fl, const double* id, const double* u1, const double* u2, int flags) {
     LaneOp* o = add(OP_FDMA); o->i0 = len; o->i2 = flags; o->p0 = fl; o->p1 = id; o->p2 = u1; o->p3 = u2;
   }
-  void dct(const Base1& b, int mode) { LaneOp* o = add(OP_DCT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; o->p2 = b.d_isin.d; }
-  void rfft(const Base1& b, int mode) { LaneOp* o = add(OP_RFFT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; }
+  void dense(int n_out, int n_in, const double* M) { LaneOp* o = add(OP_DENSE); o->i0 = n_out; o->i1 = n_in; o->p0 = M; }
+  void dct(const Base1& b, int mode) {
+    if (b.dense_tr) { dense(b.n, b.n, mode == 0 ? b.d_dfwd.d : b.d_dbwd.d); return; }
+    LaneOp* o = add(OP_DCT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; o->p2 = b.d_isin.d; }
+  void rfft(const Base1& b, int mode) {
+    if (b.dense_tr) { if (mode == 0) dense(2 * b.m, b.n, b.d_dfwd.d); else dense(b.n, 2 * b.m, b.d_dbwd.d); return; }
+    LaneOp* o = add(OP_RFFT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; }
   void fdiff(int modes, int d, double scale) { LaneOp* o = add(OP_FDIFF); o->i0 = modes; o->i1 = d; o->a = scale; }
   void scalevec(int len, const double* v, int shift) { LaneOp* o = add(OP_SCALEVEC); o->i0 = len; o->i1 = shift; o->p0 = v; }
   void zerotail(int from) { LaneOp* o = add(OP_ZEROTAIL); o->i0 = from; }
@@ -899,7 +930,7 @@ static bool shape_complex(const b2_space* sp, int shape_kind) { return !sp->b[0]
 // ------------------------------------------------------------------------------------------------
 static int op_forward(b2_space* sp, const double* v, double* vhat) {
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
-  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transforms need n-1 (Chebyshev) / n (Fourier) = 2^k >= 64");
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transform size: n-1 (Chebyshev) / n (Fourier) = 2^k >= 64 runs the FFT core, other sizes up to 2049 a dense matrix; larger non-power-of-two sizes are not supported");
   Prog y; y.load(v, b1.rows_phys); y.forward_ortho(b1); int l = y.from_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
   RET(run_pass(sp, 0, y));
   Prog x; x.load(sp->tmp[0], b0.rows_phys); x.forward_ortho(b0); l = x.from_ortho(b0); x.store(vhat, l, ST_TRANS);
@@ -907,7 +938,7 @@ static int op_forward(b2_space* sp, const double* v, double* vhat) {
 }
 static int op_backward(b2_space* sp, const double* vhat, double* v) {
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
-  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transforms need n-1 (Chebyshev) / n (Fourier) = 2^k >= 64");
+  if (!sp->transforms_ok) return fail(B2_ERR_UNSUPPORTED, "transform size: n-1 (Chebyshev) / n (Fourier) = 2^k >= 64 runs the FFT core, other sizes up to 2049 a dense matrix; larger non-power-of-two sizes are not supported");
   Prog y; y.load(vhat, b1.rows_spec); y.to_ortho(b1); int l = y.backward_ortho(b1); y.store(sp->tmp[0], l, ST_TRANS);
   RET(run_pass(sp, 0, y));
   Prog x; x.load(sp->tmp[0], b0.rows_spec); x.to_ortho(b0); l = x.backward_ortho(b0); x.store(v, l, ST_TRANS);
@@ -1445,7 +1476,7 @@ int b2_space2_create(b2_ctx* ctx, int kind0, int n0, int kind1, int n1, b2_space
   if (r == B2_OK) r = sp->b[1].init(sp->cfg[0].C, sp->cfg[0].TPL);   // cfg[0]: lanes along axis 1
   if (r == B2_OK) r = sp->b[0].init(sp->cfg[1].C, sp->cfg[1].TPL);
   if (r != B2_OK) { delete sp; return r; }
-  sp->transforms_ok = sp->b[0].d_tw.d && sp->b[1].d_tw.d;
+  sp->transforms_ok = (sp->b[0].d_tw.d || sp->b[0].dense_tr) && (sp->b[1].d_tw.d || sp->b[1].dense_tr);
   for (int i = 0; i < 3; i++) RET(alloc_zero(sp, &sp->tmp[i]));
   *out = sp;
   return B2_OK;

@@ -54,6 +54,8 @@ enum LaneOpCode {
   OP_BANDC = 15,   // an OP_BAND in chunk-streaming form (set by the launcher, fast geometry only): see band_chunk
   OP_STEN3 = 16,   // ChebDirichletNeumann stencil (odd offsets): i1 = 0: y_j = x_j + a_{j-1} x_{j-1} + b_{j-2} x_{j-2} (to_ortho, S);
                    //   i1 = 1: y_k = x_k + a_k x_{k+1} + b_k x_{k+2} (S^T);  i0 = len_out, p0 = a, p1 = b (natural order)
+  OP_DENSE = 18,   // dense mat-vec along the lane: y_k = sum_j M[k][j] x_j, i0 = n_out, i1 = n_in, p0 = M (row-major): the transforms
+                   //   of sizes the FFT core does not handle (n - 1 / n not a power of two): O(n^2) per lane, small grids only
   OP_PDMA = 17,    // PdmaPlus2 solve (7 diagonals -2..+4, src/solver/pdma_plus2.rs:123-157): i0 = n, i1 = pitch L of the packed LU
                    //   p0 = [l2 shifted | ka | 1/mu | al | be | ga | de], each L doubles
 };
@@ -1124,6 +1126,36 @@ __device__ __noinline__ void op_sten3(const LaneProg& P, const LaneOp& op, doubl
   __syncthreads();
 }
 
+// Transform of a lane as a dense mat-vec (DCT-I / r2c / c2r matrices built on the host): the fallback for transform sizes that are
+// not 2^k (+1) -- e.g. the reference's criterion sizes 128, 264, 265, 512 (benches/benchmark_navier.rs:6-7).  Thread q of a lane
+// accumulates the outputs k = q + i TPL in registers while every thread of the lane walks the same input element.
+template <int CP, int LN>
+__device__ __noinline__ void op_dense(const LaneProg& P, const LaneOp& op, double* __restrict__ W) {
+  const int TPL = P.TPL, LP = P.LP;
+  const int l = threadIdx.x & (LN - 1), q = threadIdx.x >> Lay<LN>::LOG;
+  const int n_out = op.i0, n_in = op.i1;
+  const double* __restrict__ M = (const double*)op.p0;
+  double* w = W + 4 * l;
+  double y[2 * CP];
+#pragma unroll
+  for (int i = 0; i < 2 * CP; i++) y[i] = 0.0;
+  for (int j = 0; j < n_in; j++) {
+    const double x = w[Lay<LN>::eix(j)];
+#pragma unroll
+    for (int i = 0; i < 2 * CP; i++) {
+      const int k = q + i * TPL;
+      if (k < n_out) y[i] = fma(ldg(M + (size_t)k * n_in + j), x, y[i]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2 * CP; i++) {
+    const int k = q + i * TPL;
+    if (k < LP) w[Lay<LN>::eix(k)] = (k < n_out) ? y[i] : 0.0;
+  }
+  __syncthreads();
+}
+
 // PdmaPlus2::solve_lane (src/solver/pdma_plus2.rs:123-157): forward elimination (second order) and back substitution
 // (fourth order) over the elements of a lane; one thread per lane ("one thread per system") -- bc = "hc" only.
 template <int LN>
@@ -1273,6 +1305,7 @@ __global__ void B2_LB lane_kernel(const __grid_constant__ LaneProg Pp) {
       case OP_BANDC:
         if constexpr (TPLC > 0) band_chunk<E, LN, TPLC>(P, op, W);
         break;
+      case OP_DENSE: op_dense<E + 1, LN>(P, op, W); break;
       case OP_STEN3: op_sten3<E + 1, LN>(P, op, W); break;
       case OP_PDMA: op_pdma<LN>(P, op, W); break;
       default: op_pointwise<LN>(P, op, W, g, lb); break;

@@ -100,6 +100,15 @@ elif case == "snapshot":
     old = np.arange(12.0).reshape(3, 4)
     new = sn.interpolate_2d(old, (5, 3), True)
     assert new.shape == (5, 3) and np.array_equal(new[:3, :3], old[:, :3] * (4 / 2)) and not new[3:].any()
+elif case == "anysize":
+    # transform sizes that are not 2^k (+1): dense-matrix transforms (OP_DENSE)
+    for sp in [(1, 30, 2, 23), (4, 24, 1, 19)]:
+        for fn in (g.check_backward, g.check_forward, g.check_hholtz):
+            e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
+    errs = g.check_navier(27, 22, 1)
+    assert max(errs.values()) < g.TOL, errs
+    errs = g.check_navier(24, 19, 1, True)
+    assert max(errs.values()) < g.TOL, errs
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
@@ -111,7 +120,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot", "anysize"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
