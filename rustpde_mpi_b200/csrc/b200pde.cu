@@ -647,7 +647,7 @@ static int launch_pass(b2_ctx* ctx, const PassCfg& c, const LaneProg& p) {
 #define B2_INST(e, ln, tpl) if (c.fast && c.E == e && c.LN == ln && c.TPL == tpl) return launch_ELT<e, ln, tpl>(ctx, c, p);
   B2_INST(16, 4, 128) B2_INST(16, 4, 64) B2_INST(16, 4, 32) B2_INST(16, 4, 16) B2_INST(16, 4, 8)
   B2_INST(16, 2, 256) B2_INST(16, 2, 128)
-  B2_INST(8, 4, 64) B2_INST(8, 4, 32) B2_INST(8, 4, 16) B2_INST(8, 4, 8) B2_INST(4, 4, 8)
+  B2_INST(8, 4, 64) B2_INST(8, 4, 32) B2_INST(8, 4, 16) B2_INST(8, 4, 8) B2_INST(4, 4, 8) B2_INST(4, 4, 16) B2_INST(4, 4, 32)
 #undef B2_INST
   if (c.LN == 4) {
     if (c.E == 16) return launch_ELT<16, 4, 0>(ctx, c, p);
@@ -835,6 +835,15 @@ static int run_pass(b2_space* sp, int orient, Prog& pr) {
 // ------------------------------------------------------------------------------------------------
 // context / space / arrays
 // ------------------------------------------------------------------------------------------------
+// the (E, LN, TPL) combinations that have a compile-time-geometry kernel instance (launch_pass): only those may run the
+// launcher's fast-geometry rewrites (OP_BANDC, OP_PREBAND) -- the generic instances do not implement them
+static bool has_fast_instance(int E, int LN, int TPL) {
+  if (LN == 2) return E == 16 && (TPL == 256 || TPL == 128);
+  if (E == 16) return TPL == 128 || TPL == 64 || TPL == 32 || TPL == 16 || TPL == 8;
+  if (E == 8) return TPL == 64 || TPL == 32 || TPL == 16 || TPL == 8;
+  if (E == 4) return TPL == 8 || TPL == 16 || TPL == 32;
+  return false;
+}
 static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c, int nranks) {
   c->in_tiles = Pl / 4; c->out_tiles = Pc / 4; c->groups = Pc / 4; c->LP = Pl;
   const int N = lane_base.N;
@@ -873,7 +882,7 @@ static int make_cfg(const Base1& lane_base, int Pl, int Pc, PassCfg* c, int nran
   }
   c->C = c->E + 1;
   c->NT = c->LN * c->TPL;
-  c->fast = is_pow2(N) && N >= 64 && N == 2 * c->E * c->TPL && Pl >= N + 4 && getenv("B2_NOFAST") == nullptr;
+  c->fast = is_pow2(N) && N >= 64 && N == 2 * c->E * c->TPL && Pl >= N + 4 && has_fast_instance(c->E, c->LN, c->TPL) && getenv("B2_NOFAST") == nullptr;
   if (c->NT % 32) return fail(B2_ERR_UNSUPPORTED, "compute threads must fill whole warps");
   // shared memory: [mbarriers][program copy][scratch][W][per warp: 2 staging slots of CHW + 1 tiles]
   const int tile_bytes = c->LN * 32;

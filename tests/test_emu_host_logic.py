@@ -109,6 +109,14 @@ elif case == "anysize":
     assert max(errs.values()) < g.TOL, errs
     errs = g.check_navier(24, 19, 1, True)
     assert max(errs.values()) < g.TOL, errs
+elif case == "e4":
+    # 4 FFT points per thread on a 128-point lane (E = 4, TPL = 16): the layout an 8-rank run of 129 x 129 picks because of
+    # its padding (pitch 160); forced here on one rank with B2_E=4.  Regression: this layout once had no compile-time-geometry
+    # kernel instance and silently skipped the chunk-streaming band ops.
+    for sp in [(1, 129, 2, 129)]:
+        for fn in (g.check_backward, g.check_forward, g.check_to_ortho, g.check_hholtz):
+            e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
+        e = g.check_gradient(*sp, (1, 0)); assert e < g.TOL, ("gradient", sp, e)
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
@@ -133,4 +141,10 @@ def test_emulated_path_variants(env):
     """The tuning switches select alternative implementations of the same operators; each must give the same step."""
     r = subprocess.run([sys.executable, "-c", SCRIPT, "variants"], capture_output=True, text=True, timeout=900, cwd=ROOT,
                        env=dict(os.environ, **env))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_emulated_four_points_per_thread_layout():
+    r = subprocess.run([sys.executable, "-c", SCRIPT, "e4"], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                       env=dict(os.environ, B2_E="4"))
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
