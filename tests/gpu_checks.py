@@ -157,6 +157,42 @@ def check_navier(nx, ny, steps, periodic=False, ra=1e5, dt=0.01, init="modes", b
     return navier_errors(no, ng)
 
 
+def check_navier_white_noise(nx, ny, steps, periodic=False, ra=1e5, dt=0.01):
+    """White-noise initial fields (U(-0.1, 0.1) in physical space, navier.rs:171-182).  The projection step cancels a large
+    divergent part of the intermediate velocity, so the step itself is conditioned well above rounding: returns the errors of the
+    CUDA path against the oracle AND the yardstick = the oracle against itself when the same input is changed in the last bit
+    (multiplied by 1 + 4e-16 N(0,1)); tests bound the error by max(TOL, 10 x yardstick) (same rule as test_gpu_parity_large)."""
+    def fields(perturb):
+        out = {}
+        for name, seed in (("temp", 1), ("velx", 2), ("vely", 3)):
+            f = np.random.default_rng(seed).uniform(-0.1, 0.1, size=(nx, ny))
+            if perturb:
+                f = f * (1.0 + 4e-16 * np.random.default_rng(100 + seed).standard_normal((nx, ny)))
+            out[name] = f
+        return out
+
+    def start(nav, perturb):
+        for name, f in fields(perturb).items():
+            fld = getattr(nav, name)
+            fld.v = f
+            fld.forward()
+
+    eig = None if periodic else b2.poisson_eig(b2.CHEB_NEUMANN, nx, 1.0)
+    refs = []
+    for perturb in (False, True):
+        no = o.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=periodic, pois_eig=eig)
+        start(no, perturb)
+        for _ in range(steps):
+            no.update()
+        refs.append(no)
+    ng = b2.Navier2D(nx, ny, ra, 1.0, dt, 1.0, "rbc", periodic=periodic)
+    start(ng, False)
+    ng.update(steps)
+    errs = navier_errors(refs[0], ng)
+    yard = navier_errors(refs[0], refs[1])
+    return errs, max(yard.values())
+
+
 def check_diagnostics(nx, ny, steps, periodic=False):
     """Nu, Nuvol, Re (src/navier_stokes/functions.rs:146-233) after a few steps: CUDA path vs oracle, relative."""
     no, ng = make_navier_pair(nx, ny, 1e5, 1.0, 0.01, 1.0, periodic, "modes")

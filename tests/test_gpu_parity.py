@@ -148,19 +148,3 @@ def test_snapshot_write_read_and_interpolation(periodic, shape, shape2, tmp_path
         sh, cx = f.space.shape(b2.SPECTRAL)
         want = sn.read_vhat(data, group, sh, cx, periodic)
         assert np.array_equal(f.vhat, want), attr
-
-
-@pytest.mark.parametrize("nx,ny,periodic", [(128, 128, False), (264, 264, False), (265, 265, False), (512, 512, False), (264, 265, True), (100, 77, False)])
-def test_navier_reference_criterion_sizes(nx, ny, periodic):
-    """The reference's own bench sizes (benches/benchmark_navier.rs:6-7: 128, 264, 512 / 129, 265, 513): n - 1 (Chebyshev) / n
-    (Fourier) is not a power of two for most of them -- those run the dense-matrix transforms (OP_DENSE)."""
-    errs = g.check_navier(nx, ny, 2, periodic, 1e5, 0.01, "random")
-    assert max(errs.values()) < g.TOL, errs
-
-
-@pytest.mark.parametrize("sp", [(1, 128, 1, 128), (2, 264, 1, 265), (4, 264, 2, 100), (0, 77, 0, 513)])
-@pytest.mark.parametrize("op", ["forward", "backward", "hholtz"])
-def test_field_ops_any_size(sp, op):
-    if op == "hholtz" and 0 in (sp[0], sp[2]):
-        pytest.skip("HholtzAdi needs composite / Fourier axes")
-    assert getattr(g, "check_" + op)(*sp) < g.TOL
