@@ -288,7 +288,7 @@ def main():
             nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
     clocks = sampler.stop()
     clocks["note"] = f"sampled every 100 ms from warm-up through the timed region ({(t_b - t_a) * 1e3:.0f} ms) and {n_more} continuation bursts of the same loop"
-    # GEMM share of the step (separate short pass: event pairs around the two cuBLAS calls, no graph replay)
+    # GEMM share of the step (separate short pass: event pairs around the two gemm_pb_kernel launches, no graph replay)
     n_prof = max(2, min(args.steps, 10))
     ctx.profile(True)
     nav.update(n_prof)

@@ -1588,16 +1588,19 @@ int b2_array_axpy(b2_array* y, double alpha, const b2_array* x) {
   return B2_OK;
 }
 int b2_field_array(b2_field* f, int which, b2_array** out) {
+  if (!f || !out) return fail(B2_ERR_ARG, "b2_field_array: null argument");
   if (which < 0 || which > 1) return fail(B2_ERR_ARG, "which: 0 = v, 1 = vhat");
   *out = which == 0 ? f->v : f->vhat;   // borrowed: owned by the field
   return B2_OK;
 }
 int b2_array_copy(b2_array* dst, const b2_array* src) {
+  if (!dst || !src) return fail(B2_ERR_ARG, "b2_array_copy: null array");
   if (dst->sp->elems() != src->sp->elems() || dst->sp->P[0] != src->sp->P[0] || dst->sp->P[1] != src->sp->P[1]) return fail(B2_ERR_SHAPE, "copy: different padded shapes");
   CK(cudaMemcpyAsync(dst->d, src->d, dst->sp->elems() * sizeof(double), cudaMemcpyDeviceToDevice, dst->sp->ctx->stream));
   return B2_OK;
 }
 int b2_array_combine(b2_array* dst, const b2_array* a, const b2_array* b, int op, double alpha) {
+  if (!dst || !a || !b) return fail(B2_ERR_ARG, "b2_array_combine: null array");
   if (op < 0 || op > 2) return fail(B2_ERR_ARG, "combine op");
   const size_t n = dst->sp->elems();
   if (a->sp->elems() != n || b->sp->elems() != n || a->sp->P[1] != dst->sp->P[1] || b->sp->P[1] != dst->sp->P[1]) return fail(B2_ERR_SHAPE, "combine: different padded shapes");
@@ -1606,16 +1609,22 @@ int b2_array_combine(b2_array* dst, const b2_array* a, const b2_array* b, int op
   dst->sp->ctx->launches++;
   return B2_OK;
 }
+// scratch device buffer of one call: released on every return path
+struct ScratchBuf {
+  double* p = nullptr;
+  ~ScratchBuf() { if (p) cudaFree(p); }
+};
 int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const double* w1, int mode, double* out) {
+  if (!a || !w0_local || !w1 || !out || (mode != 0 && mode != 1)) return fail(B2_ERR_ARG, "b2_array_weighted_sum: null argument or mode not 0 / 1");
   b2_space* sp = a->sp;
   if (shape_complex(sp, a->shape_kind)) return fail(B2_ERR_UNSUPPORTED, "weighted sums are defined on real (physical) arrays");
   int rows, cols, row0, cnt;
   RET(shape_of(sp, a->shape_kind, &rows, &cols));
   local_rows(sp, rows, &row0, &cnt);
   const int nout = mode == 1 ? cols : 1;
-  double* d = nullptr;
-  CK(cudaMalloc(&d, (size_t)(cnt + cols + nout + 1) * sizeof(double)));
-  double* dw0 = d; double* dw1 = d + cnt; double* dout = dw1 + cols;
+  ScratchBuf buf;
+  CK(cudaMalloc(&buf.p, (size_t)(cnt + cols + nout + 1) * sizeof(double)));
+  double* dw0 = buf.p; double* dw1 = buf.p + cnt; double* dout = dw1 + cols;
   if (cnt) CK(cudaMemcpyAsync(dw0, w0_local, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
   CK(cudaMemcpyAsync(dw1, w1, (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
   CK(cudaMemsetAsync(dout, 0, (size_t)nout * sizeof(double), sp->ctx->stream));
@@ -1624,12 +1633,12 @@ int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const doubl
   sp->ctx->launches++;
   CK(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
   CK(cudaStreamSynchronize(sp->ctx->stream));
-  CK(cudaFree(d));
   return B2_OK;
 }
 static int norm2_dev(b2_space* sp, const double* d, double* out, bool global) {
-  double* acc = nullptr;
-  CK(cudaMalloc(&acc, sizeof(double)));
+  ScratchBuf buf;
+  CK(cudaMalloc(&buf.p, sizeof(double)));
+  double* acc = buf.p;
   CK(cudaMemsetAsync(acc, 0, sizeof(double), sp->ctx->stream));
   const size_t n = sp->elems();
   B2_LAUNCH(k_sumsq, ew_grid(n), 256, 0, sp->ctx->stream, n, d, acc);
@@ -1642,7 +1651,6 @@ static int norm2_dev(b2_space* sp, const double* d, double* out, bool global) {
   double h = 0;
   CK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
   CK(cudaStreamSynchronize(sp->ctx->stream));
-  CK(cudaFree(acc));
   *out = h;
   return B2_OK;
 }
@@ -2166,7 +2174,11 @@ int b2_navier_div_norm(b2_navier* nv, double* out) {
   return B2_OK;
 }
 int b2_navier_get_time(const b2_navier* nv, double* t) { *t = nv->time; return B2_OK; }
-int b2_navier_set_time(b2_navier* nv, double t) { nv->time = t; return B2_OK; }
+int b2_navier_set_time(b2_navier* nv, double t) {
+  if (!nv) return fail(B2_ERR_ARG, "b2_navier_set_time: null handle");
+  nv->time = t;
+  return B2_OK;
+}
 int b2_navier_set_mode(b2_navier* nv, int mode) {
   // bit 0: fused schedule; bit 1: disable CUDA-graph replay; bit 2: disable parallel branches
   nv->fused = mode & 1; nv->use_graph = !(mode & 2); nv->branches = !(mode & 4); nv->warm_steps = 0;
