@@ -294,6 +294,74 @@ class Field2:
         r0, cnt = self.local_rows(kind)
         return slice(r0, r0 + cnt)
 
+    # ---- rank bookkeeping and host-side gather / scatter of the slabs (src/field_mpi.rs:309-321, 363-453) ----
+    # Host conveniences for set-up, output and tests: they move whole arrays through torch.distributed object collectives and are
+    # not part of the timestep (the pencil exchanges of the hot path are peer stores inside the kernels).
+    def nrank(self):
+        return self.space.ctx.rank
+
+    def nprocs(self):
+        return self.space.ctx.nranks
+
+    def get_coords_local(self, axis):
+        """Coordinates of this rank's part of the physical array along ``axis`` (src/field_mpi.rs:128-131): axis 0 is split."""
+        return self.x[axis][self.local_slice(PHYSICAL)] if axis == 0 else self.x[axis]
+
+    def _gather(self, local, root):
+        ctx = self.space.ctx
+        if ctx.nranks == 1:
+            return local
+        import torch.distributed as dist
+
+        if root is None:
+            return ctx.all_gather_rows(local)
+        parts = [None] * ctx.nranks if ctx.rank == root else None
+        dist.gather_object(local, parts, dst=root)
+        return np.concatenate([p for p in parts if p.shape[0] > 0], axis=0) if ctx.rank == root else None
+
+    def _scatter(self, glob, kind, root):
+        ctx = self.space.ctx
+        if ctx.nranks == 1:
+            return np.asarray(glob)
+        import torch.distributed as dist
+
+        bounds = [None] * ctx.nranks
+        dist.all_gather_object(bounds, self.local_rows(kind))
+        parts = None
+        if ctx.rank == root:
+            shape, _ = self.space.shape(kind)
+            glob = np.asarray(glob)
+            if glob.shape != tuple(shape):
+                raise B2Error(f"shape mismatch: got {glob.shape}, expected {tuple(shape)}")   # reference: panic
+            parts = [np.ascontiguousarray(glob[r0:r0 + cnt]) for r0, cnt in bounds]
+        out = [None]
+        dist.scatter_object_list(out, parts, src=root)
+        return out[0]
+
+    def gather_physical_root(self, root=0):
+        """The global physical array on ``root`` (None elsewhere), src/field_mpi.rs:391-399."""
+        return self._gather(self.v, root)
+
+    def gather_spectral_root(self, root=0):
+        """The global spectral array on ``root`` (None elsewhere), src/field_mpi.rs:371-380."""
+        return self._gather(self.vhat, root)
+
+    def all_gather_physical(self):
+        """The global physical array on every rank, src/field_mpi.rs:439-444."""
+        return self._gather(self.v, None)
+
+    def all_gather_spectral(self):
+        """The global spectral array on every rank, src/field_mpi.rs:447-453."""
+        return self._gather(self.vhat, None)
+
+    def scatter_physical_root(self, v_global=None, root=0):
+        """Distribute ``root``'s global physical array over the ranks' slabs of ``v``, src/field_mpi.rs:410-419."""
+        self.v = self._scatter(v_global, PHYSICAL, root)
+
+    def scatter_spectral_root(self, vhat_global=None, root=0):
+        """Distribute ``root``'s global spectral array over the ranks' slabs of ``vhat``, src/field_mpi.rs:430-436."""
+        self.vhat = self._scatter(vhat_global, SPECTRAL, root)
+
     # host views of the device-resident data (this rank's rows)
     @property
     def v(self):

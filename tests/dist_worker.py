@@ -80,6 +80,22 @@ def main():
                 x[0, 0] = 0; xo[0, 0] = 0
             err = float(np.abs(x - xo).max() / np.abs(xo).max())
             assert err < 1e-10, (name, err)
+        # gather / scatter of the slabs (src/field_mpi.rs:363-453): scatter from rank 0, transform on the slabs, gather back
+        fo = o.Field2(o.Space2(o.Base(4 if periodic else 1, nx), o.Base(2, ny)))
+        fg = b2.Field2(b2.Space2((4 if periodic else 1, nx), (2, ny), ctx=ctx))
+        vg = np.random.default_rng(5).standard_normal((nx, ny))
+        fg.scatter_physical_root(vg if rank == 0 else None, root=0)
+        assert fg.nrank() == rank and fg.nprocs() == world
+        assert np.array_equal(fg.all_gather_physical(), vg)
+        assert np.array_equal(fg.get_coords_local(0), fg.x[0][fg.local_slice(b2.PHYSICAL)])
+        fg.forward()
+        fo.v = vg; fo.forward()
+        got = fg.gather_spectral_root(root=world - 1)
+        assert (got is None) == (rank != world - 1)
+        if got is not None:
+            assert float(np.abs(got - fo.vhat).max() / np.abs(fo.vhat).max()) < 1e-10
+        fg.scatter_spectral_root(fo.vhat if rank == 0 else None, root=0)
+        assert np.array_equal(fg.all_gather_spectral(), fo.vhat)
         # snapshot / restart on slabs (src/field_mpi/io.rs): gathered write on rank 0, every rank reads its rows back
         import tempfile
         fn = os.path.join(tempfile.gettempdir(), f"b2_snap_{os.environ.get('MASTER_PORT', '0')}.npz")
@@ -89,7 +105,7 @@ def main():
         for k, v in nav.state().items():
             assert np.array_equal(nav2.state()[k], v), k
         assert abs(nav2.get_time() - nav.get_time()) < 1e-15
-        print(f"rank {rank}/{world}: extras ok (HholtzMpi, PoissonMpi, snapshot)", flush=True)
+        print(f"rank {rank}/{world}: extras ok (HholtzMpi, PoissonMpi, gather / scatter, snapshot)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
