@@ -25,6 +25,7 @@ def run(world, args, port, extra_env=None):
     (2, 64, 65, 1, 1, 1, 29612),   # periodic, fused
     (2, 65, 65, 1, 0, 0, 29613),   # confined, one pass pair per reference call
     (3, 65, 65, 1, 0, 1, 29614),   # uneven split: 17 lane groups padded to 18 over 3 ranks
+    (4, 65, 65, 1, 0, 1, 29618),   # pitch 80 = exactly the 2 x 5 x 8 elements the thread layout holds (the 8-rank 129-point case in small)
 ])
 def test_slab_decomposition_matches_serial_oracle(world, nx, ny, steps, periodic, mode, port):
     run(world, (nx, ny, steps, periodic, mode), port)
