@@ -68,19 +68,24 @@ struct b2_ctx {
   bool attached = false;
   long long barriers = 0;
   unsigned long long* d_prof = nullptr;   // per-op cycle counters (debug/profiling)
+  int* d_differs = nullptr;               // result word of k_same_value (collective allocator)
 };
 static const size_t B2_HEAP_RESERVED = 4096;  // flags[0..nranks) + epoch counter live at the start of the heap
 
 static int ctx_alloc(b2_ctx* c, size_t bytes, double** out) {
   if (c->nranks == 1) { CK(cudaMalloc(out, bytes)); return B2_OK; }
   const size_t need = (bytes + 255) / 256 * 256;
+  // exact-size reuse (arrays of a problem share one padded size); the LOWEST free block of that size, so that the choice depends
+  // on the set of free blocks only, not on the order in which a rank's host code happened to release them
+  size_t best = c->heap_free.size();
   for (size_t i = 0; i < c->heap_free.size(); i++)
-    if (c->heap_free[i].second == need) {   // exact-size reuse (arrays of a problem share one padded size)
-      *out = reinterpret_cast<double*>(c->heap + c->heap_free[i].first);
-      c->heap_free.erase(c->heap_free.begin() + i);
-      c->heap_live[*out] = need;
-      return B2_OK;
-    }
+    if (c->heap_free[i].second == need && (best == c->heap_free.size() || c->heap_free[i].first < c->heap_free[best].first)) best = i;
+  if (best < c->heap_free.size()) {
+    *out = reinterpret_cast<double*>(c->heap + c->heap_free[best].first);
+    c->heap_free.erase(c->heap_free.begin() + best);
+    c->heap_live[*out] = need;
+    return B2_OK;
+  }
   if (c->heap_used + need > c->heap_bytes) return fail(B2_ERR_ARG, "symmetric heap exhausted: pass a larger heap_bytes to b2_ctx_create");
   *out = reinterpret_cast<double*>(c->heap + c->heap_used);
   c->heap_used += need;
@@ -143,6 +148,35 @@ __global__ void k_allreduce(unsigned long long* const* peers_, int rank, int nra
     double s = 0;
     for (int r = 0; r < nranks; r++) s += v[r];
     *out = s;
+    mine[B2_MAXPEERS] = e;
+  }
+}
+// Barrier + agreement check on the stream: every rank publishes one word to every peer (flag exchange of barrier lane 3, value
+// buffers alternating with the epoch like k_allreduce) and reports whether any rank's word differs from its own.  Used by the
+// collective allocator: an array must have the same heap offset on every rank, or peer stores land in somebody else's array.
+__global__ void k_same_value(unsigned long long* const* peers_, int rank, int nranks, unsigned long long value, int* differs) {
+  __shared__ unsigned long long* peers[B2_MAXPEERS];
+  if ((int)threadIdx.x < nranks) peers[threadIdx.x] = peers_[threadIdx.x] + 16 * 3;
+  __syncthreads();
+  unsigned long long* mine = peers[rank];
+  __shared__ unsigned long long epoch;
+  if (threadIdx.x == 0) epoch = mine[B2_MAXPEERS] + 1;
+  __syncthreads();
+  const unsigned long long e = epoch;
+  const int buf = (int)(e & 1ull) * B2_MAXPEERS;
+  if ((int)threadIdx.x < nranks) {
+    *reinterpret_cast<volatile unsigned long long*>(peers_[threadIdx.x] + 320 + buf + rank) = value;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + rank) = e;
+    __threadfence_system();
+    while (*reinterpret_cast<volatile unsigned long long*>(mine + threadIdx.x) < e) { B2_SPIN_PAUSE(); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const volatile unsigned long long* v = peers_[rank] + 320 + buf;
+    int d = 0;
+    for (int r = 0; r < nranks; r++) d |= (v[r] != value);
+    *differs = d;
     mine[B2_MAXPEERS] = e;
   }
 }
@@ -919,7 +953,20 @@ static int alloc_zero(b2_space* sp, double** out) {
   CK(cudaMemsetAsync(*out, 0, sp->elems() * sizeof(double), sp->ctx->stream));
   // several GPUs: a peer may store into this array as soon as ITS allocation returns -- not before every rank has cleared its copy
   // (allocation is collective on the symmetric heap: every rank allocates the same arrays in the same order)
-  if (sp->ctx->nranks > 1 && sp->ctx->attached) RET(ctx_barrier(sp->ctx));
+  // The same exchange checks that the heaps are still symmetric (host code that releases arrays at different moments on different
+  // ranks -- e.g. garbage collection -- would otherwise corrupt other arrays silently).
+  b2_ctx* c = sp->ctx;
+  if (c->nranks > 1 && c->attached) {
+    if (!c->d_differs) CK(cudaMalloc(&c->d_differs, sizeof(int)));
+    const unsigned long long off = (unsigned long long)(reinterpret_cast<char*>(*out) - c->heap);
+    B2_LAUNCH(k_same_value, 1, 32, 0, c->stream, reinterpret_cast<unsigned long long* const*>(c->d_peers), c->rank, c->nranks, off, c->d_differs);
+    CK(cudaGetLastError());
+    c->barriers++;
+    int differs = 0;
+    CK(cudaMemcpyAsync(&differs, c->d_differs, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (differs) return fail(B2_ERR_ARG, "symmetric heap diverged: the ranks did not create / release their arrays in the same order (offset " + std::to_string(off) + " on rank " + std::to_string(c->rank) + ")");
+  }
   return B2_OK;
 }
 
@@ -1372,6 +1419,7 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stage) cudaFree(c->stage);
   if (c->d_prof) cudaFree(c->d_prof);
+  if (c->d_differs) cudaFree(c->d_differs);
   if (c->d_peers) cudaFree(c->d_peers);
 #ifndef B2_EMU
   for (int r = 0; r < c->nranks; r++) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
