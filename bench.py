@@ -21,6 +21,7 @@ parity_check: 2 steps of a 257 x 129 problem on the same ranks against the numpy
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -280,12 +281,15 @@ def main():
     value = 1e3 / ms_per_step
     # keep the same loop running until nvidia-smi (100 ms period) has seen >= 1.5 s of it
     n_more = 0
-    n_target = 0 if dist is not None else 10 ** 9   # multi-rank: every rank must issue the same number of steps
-    while n_more < n_target and time.time() - t_a < 1.5:
-        nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
-    if dist is not None:
-        for _ in range(4):
-            nav.update(max(1, args.steps // 4)); ctx.sync(); n_more += 1
+    burst = max(1, args.steps // 4)
+    if dist is None:
+        while time.time() - t_a < 1.5:
+            nav.update(burst); ctx.sync(); n_more += 1
+    else:
+        # multi-rank: every rank must issue the same number of steps, so the count comes from the all-reduced step time
+        # (identical on every rank), not from the local wall clock: ~2 s of the loop, nvidia-smi needs a few 100 ms to start
+        for _ in range(min(2000, max(4, int(math.ceil(2000.0 / (burst * ms_per_step)))))):
+            nav.update(burst); ctx.sync(); n_more += 1
     clocks = sampler.stop()
     clocks["note"] = f"sampled every 100 ms from warm-up through the timed region ({(t_b - t_a) * 1e3:.0f} ms) and {n_more} continuation bursts of the same loop"
     # GEMM share of the step (separate short pass: event pairs around the two gemm_pb_kernel launches, no graph replay)
