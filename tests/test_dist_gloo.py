@@ -45,3 +45,11 @@ def test_hc_boundary_conditions_on_slabs():
 def test_field_solvers_and_snapshot_on_slabs():
     """HholtzMpi / PoissonMpi standalone solves and the snapshot write / read path with 2 ranks."""
     run(2, (65, 65, 1, 0, 1, "extras"), 29616)
+
+
+@pytest.mark.skipif(os.environ.get("B2_SLOW_TESTS") != "1", reason="6-12 min per case on a CPU host: run with B2_SLOW_TESTS=1")
+@pytest.mark.parametrize("nx,ny,steps,periodic,mode,port", [
+    (129, 129, 1, 0, 1, 29621), (257, 129, 2, 0, 1, 29622), (128, 129, 1, 1, 1, 29623), (129, 129, 1, 0, 0, 29624)])
+def test_eight_ranks(nx, ny, steps, periodic, mode, port):
+    """The configurations of tests/test_gpu_multi.py on 8 emulated ranks (pitch 160 / 288: the layouts an 8-GPU run selects)."""
+    run(8, (nx, ny, steps, periodic, mode), port)
