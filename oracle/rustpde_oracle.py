@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 import scipy.linalg as sla
-from scipy.fft import dct, irfft, rfft
+from scipy.fft import dct, fft, ifft, irfft, rfft
 
 # BaseKind enum order, src/field.rs:173-177 (funspace ``BaseKind``)
 CHEBYSHEV, CHEB_DIRICHLET, CHEB_NEUMANN, CHEB_DIRICHLET_NEUMANN, FOURIER_R2C, FOURIER_C2C = range(6)
@@ -51,8 +51,10 @@ class Base:
             self.m = n - 2
         elif kind == FOURIER_R2C:
             self.m = n // 2 + 1
+        elif kind == FOURIER_C2C:
+            self.m = n   # bases.rs:15: complex in, complex out, n modes in FFT order (not on the Navier2D path; funspace semantics unpinned)
         else:
-            raise ValueError("FourierC2c is not on the Navier2D path")
+            raise ValueError("bad base kind")
         self.is_cheb = kind in _CHEB
 
     # -- grid -------------------------------------------------------------
@@ -64,6 +66,8 @@ class Base:
         return 2.0 * np.pi * np.arange(n) / n
 
     def wavenumbers(self):
+        if self.kind == FOURIER_C2C:
+            return np.fft.fftfreq(self.n, 1.0 / self.n)   # 0 .. n/2-1, -n/2 .. -1
         return np.arange(self.m, dtype=np.float64)
 
     # -- stencil -----------------------------------------------
@@ -153,6 +157,8 @@ class Base:
             c = self._cheb_fwd(np.asarray(v))
             if self.kind in _COMPOSITE:
                 c = self.from_ortho(c, 0)
+        elif self.kind == FOURIER_C2C:
+            c = fft(np.asarray(v, dtype=np.complex128), axis=0)
         else:
             c = rfft(v, axis=0)
         return np.moveaxis(c, 0, axis)
@@ -162,6 +168,8 @@ class Base:
         c = _mv(c, axis)
         if self.is_cheb:
             v = self._cheb_bwd(self.to_ortho(c, 0))
+        elif self.kind == FOURIER_C2C:
+            v = ifft(c, axis=0)
         else:
             v = irfft(c, n=self.n, axis=0)
         return np.moveaxis(v, 0, axis)
@@ -192,7 +200,7 @@ class Base:
         return self.stencil()
 
     def laplace(self):
-        if self.kind == FOURIER_R2C:
+        if self.kind in (FOURIER_R2C, FOURIER_C2C):
             return np.diag(-self.wavenumbers() ** 2)
         raise NotImplementedError("laplace() is only read for Fourier axes (src/field.rs:213)")
 
@@ -232,6 +240,10 @@ def fourier_r2c(n):
     return Base(FOURIER_R2C, n)
 
 
+def fourier_c2c(n):
+    return Base(FOURIER_C2C, n)
+
+
 class Space2:
     """funspace ``Space2`` as used through src/field.rs:81-129."""
 
@@ -248,10 +260,10 @@ class Space2:
         return (self.bases[0].m, self.bases[1].m)
 
     def spectral_dtype(self):
-        return np.complex128 if self.bases[0].kind == FOURIER_R2C else np.float64
+        return np.complex128 if self.bases[0].kind in (FOURIER_R2C, FOURIER_C2C) else np.float64
 
     def ndarray_physical(self):
-        return np.zeros(self.shape_physical())
+        return np.zeros(self.shape_physical(), dtype=np.complex128 if self.bases[0].kind == FOURIER_C2C else np.float64)
 
     def ndarray_spectral(self):
         return np.zeros(self.shape_spectral(), dtype=self.spectral_dtype())
@@ -305,7 +317,7 @@ class Field2:
         self.v = space.ndarray_physical()
         self.vhat = space.ndarray_spectral()
         self.x = space.coords()
-        self.dx = [self._get_dx(x, space.bases[i].kind == FOURIER_R2C) for i, x in enumerate(self.x)]
+        self.dx = [self._get_dx(x, space.bases[i].kind in (FOURIER_R2C, FOURIER_C2C)) for i, x in enumerate(self.x)]
 
     @staticmethod
     def _get_dx(x, periodic):
@@ -355,7 +367,7 @@ class Field2:
     def ingredients_for_poisson(self, axis):
         """src/field.rs:229-249."""
         a, bm, pre = self.ingredients_for_hholtz(axis)
-        return a, bm, pre, self.space.bases[axis].kind == FOURIER_R2C
+        return a, bm, pre, self.space.bases[axis].kind in (FOURIER_R2C, FOURIER_C2C)   # src/field.rs:244
 
 
 # ---------------------------------------------------------------------------

@@ -36,6 +36,11 @@ def fourier_r2c(n):
     return (FOURIER_R2C, n)
 
 
+def fourier_c2c(n):
+    """bases.rs:15: complex physical values, n modes in FFT order.  Not on the Navier2D path: dense-matrix transform, n <= 1024."""
+    return (FOURIER_C2C, n)
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -262,7 +267,7 @@ class Field2:
         else:
             self._h = handle
         self.x = space.coords()
-        self.dx = [self._get_dx(x, space.base_kind(i) == FOURIER_R2C) for i, x in enumerate(self.x)]
+        self.dx = [self._get_dx(x, space.base_kind(i) in (FOURIER_R2C, FOURIER_C2C)) for i, x in enumerate(self.x)]
 
     def close(self):
         if getattr(self, "_h", None) and self._owner:
@@ -365,14 +370,14 @@ class Field2:
     # host views of the device-resident data (this rank's rows)
     @property
     def v(self):
-        out = np.empty((self.local_rows(PHYSICAL)[1], self.space.shape_physical()[1]))
+        out = np.empty((self.local_rows(PHYSICAL)[1], self.space.shape_physical()[1]), dtype=_host_dtype(self.space, PHYSICAL))
         if out.size:
             check(lib().b2_field_get_v_host(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
     @v.setter
     def v(self, a):
-        a = np.ascontiguousarray(a, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=_host_dtype(self.space, PHYSICAL))   # complex only on a FourierC2c axis 0
         if a.shape != (self.local_rows(PHYSICAL)[1], self.space.shape_physical()[1]):
             raise B2Error(f"shape mismatch: got {a.shape}")
         if a.size:

@@ -262,6 +262,7 @@ struct Base1 {
   int kind = 0, n = 0, m = 0;
   bool cheb = false, composite = false;   // composite: ChebDirichlet / ChebNeumann (stencil at even offsets: pair-structured lane operators)
   bool cdn = false;                        // ChebDirichletNeumann (bc = "hc"): three-term stencil, PdmaPlus2 solves
+  bool c2c = false;                        // FourierC2c: complex physical values, n modes in FFT order (k = 0 .. n/2-1, -n/2 .. -1)
   int rows_phys = 0, rows_spec = 0, rows_ortho = 0;  // real rows along this axis (complex => 2 per mode)
   int N = 0;                                          // transform size (n-1 Chebyshev, n Fourier)
   std::vector<double> s2;                             // stencil: ortho_k = c_k + s2[k-2] c_{k-2}
@@ -341,13 +342,18 @@ int Base1::init_host(int kind_, int n_) {
   cheb = (kind <= B2_CHEB_DIRICHLET_NEUMANN);
   composite = (kind == B2_CHEB_DIRICHLET || kind == B2_CHEB_NEUMANN);
   cdn = (kind == B2_CHEB_DIRICHLET_NEUMANN);
-  if (kind == B2_FOURIER_C2C)
-    return fail(B2_ERR_UNSUPPORTED, "fourier_c2c is not built (no Navier2D configuration uses it)");
+  c2c = (kind == B2_FOURIER_C2C);
   if (kind < 0 || kind > B2_FOURIER_C2C) return fail(B2_ERR_ARG, "bad base kind");
   if (n < 5) return fail(B2_ERR_ARG, "n too small");
   if (cheb) {
     m = (composite || cdn) ? n - 2 : n;
     rows_phys = n; rows_spec = m; rows_ortho = n; N = n - 1;
+  } else if (c2c) {
+    // complex in, complex out (bases.rs:15): no Navier2D configuration uses it, so it runs the dense-matrix transform only
+    // (2n x 2n real matrix per lane, OP_DENSE) -- N = 0 keeps it off the FFT thread layouts
+    if (n > 1024) return fail(B2_ERR_UNSUPPORTED, "fourier_c2c: n <= 1024 (dense-matrix transform)");
+    m = n;
+    rows_phys = 2 * n; rows_spec = 2 * n; rows_ortho = 2 * n; N = 0;
   } else {
     if (n % 2) return fail(B2_ERR_UNSUPPORTED, "fourier_r2c needs even n");
     m = n / 2 + 1;
@@ -431,7 +437,20 @@ int Base1::init(int C, int TPL) {
     // any other size: the transforms as dense matrices, applied per lane by OP_DENSE -- O(n^2) per lane, meant
     // for small grids such as the reference's criterion sizes (128, 264, 265, 512)
     const long double PI = 3.14159265358979323846264338327950288L;
-    if (cheb) {   // c = F v: c_k = f_k (-1)^k / (n-1) sum_j g_j v_j cos(pi j k / (n-1));  v = B c: v_j = sum_k (-1)^k c_k cos(pi j k / (n-1))
+    if (c2c) {    // c_k = sum_j v_j e^{-2 pi i j k / n} (unnormalised), v_j = 1/n sum_k c_k e^{+2 pi i j k / n}; rows 2k, 2k+1 = Re, Im
+      std::vector<double> F((size_t)4 * n * n), B((size_t)4 * n * n);
+      const size_t w = (size_t)2 * n;
+      for (int k = 0; k < n; k++)
+        for (int j = 0; j < n; j++) {
+          const long double a = 2 * PI * (long double)((long long)j * k % n) / n;
+          const double ca_ = (double)cosl(a), sa_ = (double)sinl(a), cn_ = (double)(cosl(a) / n), sn_ = (double)(sinl(a) / n);
+          F[(size_t)(2 * k) * w + 2 * j] = ca_;      F[(size_t)(2 * k) * w + 2 * j + 1] = sa_;
+          F[(size_t)(2 * k + 1) * w + 2 * j] = -sa_; F[(size_t)(2 * k + 1) * w + 2 * j + 1] = ca_;
+          B[(size_t)(2 * j) * w + 2 * k] = cn_;      B[(size_t)(2 * j) * w + 2 * k + 1] = -sn_;
+          B[(size_t)(2 * j + 1) * w + 2 * k] = sn_;  B[(size_t)(2 * j + 1) * w + 2 * k + 1] = cn_;
+        }
+      RET(d_dfwd.upload(F)); RET(d_dbwd.upload(B));
+    } else if (cheb) {   // c = F v: c_k = f_k (-1)^k / (n-1) sum_j g_j v_j cos(pi j k / (n-1));  v = B c: v_j = sum_k (-1)^k c_k cos(pi j k / (n-1))
       std::vector<double> F((size_t)n * n), B((size_t)n * n);
       for (int k = 0; k < n; k++)
         for (int j = 0; j < n; j++) {
@@ -611,9 +630,9 @@ struct Prog {
     if (b.dense_tr) { dense(b.n, b.n, mode == 0 ? b.d_dfwd.d : b.d_dbwd.d); return; }
     LaneOp* o = add(OP_DCT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; o->p2 = b.d_isin.d; }
   void rfft(const Base1& b, int mode) {
-    if (b.dense_tr) { if (mode == 0) dense(2 * b.m, b.n, b.d_dfwd.d); else dense(b.n, 2 * b.m, b.d_dbwd.d); return; }
+    if (b.dense_tr) { if (mode == 0) dense(b.rows_ortho, b.rows_phys, b.d_dfwd.d); else dense(b.rows_phys, b.rows_ortho, b.d_dbwd.d); return; }
     LaneOp* o = add(OP_RFFT); o->i0 = b.n; o->i1 = mode; o->p0 = b.d_tw.d; o->p1 = b.d_tw2.d; }
-  void fdiff(int modes, int d, double scale) { LaneOp* o = add(OP_FDIFF); o->i0 = modes; o->i1 = d; o->a = scale; }
+  void fdiff(int modes, int d, double scale, int wrap = 0) { LaneOp* o = add(OP_FDIFF); o->i0 = modes; o->i1 = d; o->a = scale; o->i2 = wrap; }
   void scalevec(int len, const double* v, int shift) { LaneOp* o = add(OP_SCALEVEC); o->i0 = len; o->i1 = shift; o->p0 = v; }
   void zerotail(int from) { LaneOp* o = add(OP_ZEROTAIL); o->i0 = from; }
   void lanemask(int from) { LaneOp* o = add(OP_LANEMASK); o->i0 = from; }
@@ -640,7 +659,7 @@ struct Prog {
   }
   int deriv_axis(const Base1& b, int d, double sc) {  // on ortho coefficients; sc = 1/scale^d
     if (d == 0) { if (sc != 1.0) scale(sc); return b.rows_ortho; }
-    if (b.cheb) deriv(b.n, d, sc); else fdiff(b.m, d, sc);
+    if (b.cheb) deriv(b.n, d, sc); else fdiff(b.m, d, sc, b.c2c ? b.n : 0);
     return b.rows_ortho;
   }
   int backward_ortho(const Base1& b) {  // ortho coefficients -> physical values
@@ -979,7 +998,7 @@ static int shape_of(const b2_space* sp, int shape_kind, int* rows, int* cols) {
   }
   return fail(B2_ERR_ARG, "bad shape kind");
 }
-static bool shape_complex(const b2_space* sp, int shape_kind) { return !sp->b[0].cheb && shape_kind != B2_SHAPE_PHYSICAL; }
+static bool shape_complex(const b2_space* sp, int shape_kind) { return !sp->b[0].cheb && (shape_kind != B2_SHAPE_PHYSICAL || sp->b[0].c2c); }
 
 // ------------------------------------------------------------------------------------------------
 // field operators (2 passes each: along y, transpose, along x, transpose back)
@@ -1078,7 +1097,10 @@ static int hholtz_create(b2_space* sp, double c0, double c1, b2_solver** out) {
       RET(s->pd[ax].upload(pdma_sweep(b.m, d, L)));
     } else if (!b.cheb) {  // Sdma: dia = 1 - c * (-k^2), src/solver/sdma.rs:37-46
       std::vector<double> sd(L, 0.0);
-      for (int k = 0; k < b.m; k++) sd[k] = 1.0 / (1.0 - (-(double)k * k) * c[ax]);
+      for (int k = 0; k < b.m; k++) {
+        const double kk = (b.c2c && 2 * k >= b.n) ? k - b.n : k;   // FourierC2c: modes in FFT order
+        sd[k] = 1.0 / (1.0 - (-kk * kk) * c[ax]);
+      }
       RET(s->sd[ax].upload(sd));
     } else {
       delete s;
@@ -1202,7 +1224,10 @@ static int poisson_create(b2_space* sp, double c0, double c1, const double* lam_
     // Fourier axis 0: lam = diag(laplacian) = -k^2 c0 (fdma_tensor.rs:118-121), singularity shift poisson.rs:84-86
     lanes = 2 * b0.m;
     lam.resize(lanes);
-    for (int k = 0; k < b0.m; k++) lam[2 * k] = lam[2 * k + 1] = -(double)k * k * c0;
+    for (int k = 0; k < b0.m; k++) {
+      const double kk = (b0.c2c && 2 * k >= b0.n) ? k - b0.n : k;   // FourierC2c: modes in FFT order
+      lam[2 * k] = lam[2 * k + 1] = -kk * kk * c0;
+    }
     if (!hholtz && std::fabs(lam[0]) < 1e-10) for (auto& v : lam) v -= 1e-10;
   } else { delete s; return fail(B2_ERR_UNSUPPORTED, "Poisson axis-0 base"); }
   for (auto& v : lam) v += alpha;   // FdmaTensor::solve: (A1 + (lam_i + alpha) C1), src/solver/fdma_tensor.rs:277
@@ -1750,6 +1775,7 @@ int b2_gradient(const b2_field* f, int d0, int d1, const double* scale, b2_array
 int b2_field_dealias(b2_field* f) {
   b2_space* sp = f->sp;
   const Base1& b0 = sp->b[0]; const Base1& b1 = sp->b[1];
+  if (b0.c2c) return fail(B2_ERR_UNSUPPORTED, "dealias: the 2/3 tail rule of functions.rs:72-82 is written for r2c / Chebyshev mode order");
   const int cut0 = (b0.m * 2 / 3) * (b0.cheb ? 1 : 2), cut1 = b1.m * 2 / 3;
   Prog y; y.load(f->vhat->d, b1.rows_spec); y.zerotail(cut1); y.store(sp->tmp[0], b1.rows_spec, ST_TRANS);
   RET(run_pass(sp, 0, y));

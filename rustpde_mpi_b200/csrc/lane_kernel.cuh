@@ -44,7 +44,7 @@ enum LaneOpCode {
   OP_FDMA = 5,     // banded LU solve (fwd elim + back subst)  i0=len i2=flags(FD_*) p0=fl p1=inv_dia p2=u1 p3=u2
   OP_DCT = 6,      // Chebyshev transform, i0=n (=N+1), i1: 0 fwd (values->coeffs) 1 bwd   p0=tw p1=tw2 p2=isin
   OP_RFFT = 7,     // Fourier r2c/c2r, i0=n, i1: 0 fwd 1 bwd                              p0=tw p1=tw2
-  OP_FDIFF = 8,    // interleaved complex modes: c_k *= (i k)^{i1} * a,  i0 = number of modes
+  OP_FDIFF = 8,    // interleaved complex modes: c_k *= (i k)^{i1} * a,  i0 = number of modes, i2 = n for FFT-ordered modes (c2c) else 0
   OP_SCALEVEC = 9, // W[e] *= p0[e >> i1] for e < i0
   OP_ZEROTAIL = 10,// W[e] = 0 for e >= i0
   OP_LANEMASK = 11,// lanes >= i0 zeroed
@@ -1197,11 +1197,12 @@ __device__ __forceinline__ void op_pointwise(const LaneProg& P, const LaneOp& op
   cplx* w2 = reinterpret_cast<cplx*>(W) + 2 * l;
   switch (op.code) {
     case OP_FDIFF: {   // interleaved complex: (re, im) *= (i k)^d * a
-      const int m = op.i0, d = op.i1 & 3;
+      const int m = op.i0, d = op.i1 & 3, wrap = op.i2;   // wrap = n (FourierC2c): modes in FFT order, index k >= n/2 is wavenumber k - n
       for (int k = q; k < m; k += TPL) {
         cplx c = w2[Lay<LN>::pix(k)];
         double f = op.a;
-        for (int t = 0; t < op.i1; t++) f *= (double)k;
+        const double kk = (double)((wrap && 2 * k >= wrap) ? k - wrap : k);
+        for (int t = 0; t < op.i1; t++) f *= kk;
         cplx r;
         if (d == 0) r = make_double2(c.x * f, c.y * f);
         else if (d == 1) r = make_double2(-c.y * f, c.x * f);

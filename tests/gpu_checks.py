@@ -7,7 +7,7 @@ import rustpde_mpi_b200 as b2
 from oracle import rustpde_oracle as o
 
 TOL = 1e-10
-KIND_NAME = {0: "ch", 1: "cd", 2: "cn", 3: "cdn", 4: "r2c"}
+KIND_NAME = {0: "ch", 1: "cd", 2: "cn", 3: "cdn", 4: "r2c", 5: "c2c"}
 
 
 def relerr(a, ref):
@@ -21,6 +21,12 @@ def mk(k0, n0, k1, n1):
     fo = o.Field2(o.Space2(o.Base(k0, n0), o.Base(k1, n1)))
     fg = b2.Field2(b2.Space2((k0, n0), (k1, n1)))
     return fo, fg
+
+
+def rand_phys(fo, rng, dist="normal"):
+    """random physical values (complex on a FourierC2c axis 0)"""
+    draw = (lambda: rng.standard_normal(fo.v.shape)) if dist == "normal" else (lambda: rng.uniform(-0.1, 0.1, fo.v.shape))
+    return draw() + 1j * draw() if fo.v.dtype == np.complex128 else draw()
 
 
 def rand_spec(fo, seed):
@@ -39,14 +45,14 @@ def check_roundtrip_layout(k0, n0, k1, n1, seed=0):
     a = rand_spec(fo, seed)
     fg.vhat = a
     e1 = relerr(fg.vhat, a)
-    v = np.random.default_rng(seed).standard_normal(fo.v.shape)
+    v = rand_phys(fo, np.random.default_rng(seed))
     fg.v = v
     return max(e1, relerr(fg.v, v))
 
 
 def check_forward(k0, n0, k1, n1, seed=1):
     fo, fg = mk(k0, n0, k1, n1)
-    v = np.random.default_rng(seed).uniform(-0.1, 0.1, fo.v.shape)
+    v = rand_phys(fo, np.random.default_rng(seed), "uniform")
     fo.v = v.copy(); fo.forward()
     fg.v = v; fg.forward()
     return relerr(fg.vhat, fo.vhat)

@@ -117,6 +117,19 @@ elif case == "e4":
         for fn in (g.check_backward, g.check_forward, g.check_to_ortho, g.check_hholtz):
             e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
         e = g.check_gradient(*sp, (1, 0)); assert e < g.TOL, ("gradient", sp, e)
+elif case == "c2c":
+    # FourierC2c on axis 0 (bases.rs:15; not on the Navier2D path): complex physical values, modes in FFT order, dense-matrix transform
+    for sp in [(5, 64, 1, 33), (5, 30, 2, 23)]:
+        for fn in (g.check_roundtrip_layout, g.check_forward, g.check_backward, g.check_to_ortho, g.check_from_ortho, g.check_hholtz,
+                   g.check_hholtz_tensor, g.check_poisson):
+            e = fn(*sp); assert e < g.TOL, (fn.__name__, sp, e)
+        for d in ((1, 0), (2, 1), (3, 0)):
+            e = g.check_gradient(*sp, d); assert e < g.TOL, ("gradient", sp, d, e)
+    try:
+        b2.Field2(b2.Space2(b2.fourier_c2c(2048), b2.cheb_dirichlet(17)))
+        raise SystemExit("expected B2_ERR_UNSUPPORTED")
+    except b2.B2Error:
+        pass
 elif case == "navier":
     errs = g.check_navier(65, 65, 1)
     assert max(errs.values()) < g.TOL, errs
@@ -128,7 +141,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot", "anysize"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot", "anysize", "c2c"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]

@@ -1,5 +1,5 @@
-"""GPU parity (-m gpu) at transform sizes that are not 2^k (+1): the dense-matrix transforms (OP_DENSE) with the generic-geometry
-operators.  Kept in the last GPU test file: these sizes are functional coverage of the reference's criterion benches
+"""GPU parity (-m gpu) at transform sizes that are not 2^k (+1), and the FourierC2c base: the dense-matrix transforms (OP_DENSE) with the
+generic-geometry operators.  Kept in the last GPU test file: these sizes are functional coverage of the reference's criterion benches
 (benches/benchmark_navier.rs:6-7: 128, 264, 512 / 129, 265, 513), not the benchmarked path."""
 import pytest
 
@@ -33,3 +33,19 @@ def test_field_ops_any_size(sp, op):
     if op == "hholtz" and 0 in (sp[0], sp[2]):
         pytest.skip("HholtzAdi needs composite / Fourier axes")
     assert getattr(g, "check_" + op)(*sp) < g.TOL
+
+
+C2C_SPACES = [(5, 64, 1, 33), (5, 128, 2, 129), (5, 100, 1, 65), (5, 256, 0, 65)]
+
+
+@pytest.mark.parametrize("sp", C2C_SPACES, ids=["-".join(f"{g.KIND_NAME[s[i]]}{s[i+1]}" for i in (0, 2)) for s in C2C_SPACES])
+@pytest.mark.parametrize("op", ["roundtrip_layout", "forward", "backward", "to_ortho", "from_ortho", "gradient", "hholtz", "hholtz_tensor", "poisson"])
+def test_fourier_c2c(sp, op):
+    """FourierC2c on axis 0 (bases.rs:15): complex physical values, n modes in FFT order (no Navier2D configuration uses it)."""
+    if op in ("hholtz", "hholtz_tensor", "poisson") and sp[2] == 0:
+        pytest.skip("the solvers need a composite Chebyshev axis 1")
+    if op == "gradient":
+        assert max(g.check_gradient(*sp, d) for d in ((1, 0), (0, 2), (2, 1), (3, 0))) < g.TOL
+    else:
+        e = getattr(g, "check_" + op)(*sp)
+        assert e == 0.0 if op == "roundtrip_layout" else e < g.TOL

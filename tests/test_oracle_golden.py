@@ -317,3 +317,20 @@ def test_hholtz_tensor_matches_dense_solve_and_adi_limit():
     fld.vhat = sol
     fld.backward()
     assert np.abs(fld.v - u).max() < 1e-3
+
+
+def test_fourier_c2c_analytic():
+    """FourierC2c (bases.rs:15; funspace semantics unpinned by reference tests): e^{i k x} is mode k with weight n, negative
+    wavenumbers sit in the upper half (FFT order), d/dx multiplies by i k, and the Sdma of HholtzAdi divides by 1 + c k^2."""
+    n, k = 16, -3
+    b = o.fourier_c2c(n)
+    x = b.coords()
+    v = np.exp(1j * k * x)
+    c = b.forward(v)
+    want = np.zeros(n, dtype=complex); want[n + k] = n
+    np.testing.assert_allclose(c, want, atol=1e-12)
+    np.testing.assert_allclose(b.backward(c), v, atol=1e-13)
+    np.testing.assert_allclose(b.backward(b.differentiate(c, 1)), 1j * k * v, atol=1e-12)
+    assert b.wavenumbers()[n + k] == k and b.laplace()[n + k, n + k] == -k * k
+    f = o.Field2(o.Space2(b, o.cheb_dirichlet(9)))
+    assert f.v.dtype == np.complex128 and f.vhat.shape == (n, 7)
