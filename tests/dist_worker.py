@@ -96,6 +96,22 @@ def main():
             assert float(np.abs(got - fo.vhat).max() / np.abs(fo.vhat).max()) < 1e-10
         fg.scatter_spectral_root(fo.vhat if rank == 0 else None, root=0)
         assert np.array_equal(fg.all_gather_spectral(), fo.vhat)
+        # FourierC2c x ChebDirichlet on slabs: complex physical rows, forward / gradient / backward against the serial oracle
+        if not periodic:
+            fo = o.Field2(o.Space2(o.fourier_c2c(48), o.cheb_dirichlet(ny)))
+            fg = b2.Field2(b2.Space2(b2.fourier_c2c(48), b2.cheb_dirichlet(ny), ctx=ctx))
+            rng = np.random.default_rng(9)
+            vg = rng.standard_normal((48, ny)) + 1j * rng.standard_normal((48, ny))
+            fg.v = vg[fg.local_slice(b2.PHYSICAL)]
+            fg.forward()
+            fo.v = vg; fo.forward()
+            got = fg.all_gather_spectral()
+            assert float(np.abs(got - fo.vhat).max() / np.abs(fo.vhat).max()) < 1e-10
+            gr = ctx.all_gather_rows(fg.gradient([1, 1]).get())
+            ref = fo.gradient([1, 1])
+            assert float(np.abs(gr - ref).max() / np.abs(ref).max()) < 1e-10
+            fg.backward(); fo.backward()   # (not the identity: the composite base projects onto the boundary conditions)
+            assert float(np.abs(fg.all_gather_physical() - fo.v).max() / np.abs(fo.v).max()) < 1e-10
         # snapshot / restart on slabs (src/field_mpi/io.rs): gathered write on rank 0, every rank reads its rows back
         import tempfile
         fn = os.path.join(tempfile.gettempdir(), f"b2_snap_{os.environ.get('MASTER_PORT', '0')}.npz")
@@ -115,7 +131,7 @@ def main():
             raise SystemExit("expected the symmetric-heap check to fail")
         except b2.B2Error as e:
             assert "symmetric heap diverged" in str(e), e
-        print(f"rank {rank}/{world}: extras ok (HholtzMpi, PoissonMpi, gather / scatter, snapshot, heap check)", flush=True)
+        print(f"rank {rank}/{world}: extras ok (HholtzMpi, PoissonMpi, gather / scatter, c2c, snapshot, heap check)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
