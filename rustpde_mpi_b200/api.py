@@ -551,14 +551,16 @@ def _poisson_eig(kind0, n0, c0, parity_split=None):
 
 
 class Poisson(_Solver):
-    """``Poisson::new(&field, c)`` (src/solver/poisson.rs:54-94)."""
+    """``Poisson::new(&field, c)`` (src/solver/poisson.rs:54-94).  ``eig``: (lam, fwd, bwd) of axis 0 when the caller already
+    has the host eigendecomposition (as ``Navier2D(pois_eig=...)``)."""
 
-    def __init__(self, field, c):
+    def __init__(self, field, c, eig=None):
         self.field = field
         self._h = C.c_void_p()
         kind0, n0 = field.space.bases[0]
         if kind0 in (CHEB_DIRICHLET, CHEB_NEUMANN):
-            lam, fwd, bwd = poisson_eig(kind0, n0, c[0])
+            lam, fwd, bwd = eig if eig is not None else poisson_eig(kind0, n0, c[0])
+            lam, fwd, bwd = (np.ascontiguousarray(a, dtype=np.float64) for a in (lam, fwd, bwd))
             check(lib().b2_poisson_create(field._h, float(c[0]), float(c[1]), _dp(lam), _dp(fwd), _dp(bwd), C.byref(self._h)))
         else:
             check(lib().b2_poisson_create(field._h, float(c[0]), float(c[1]), None, None, None, C.byref(self._h)))

@@ -1,0 +1,100 @@
+"""The committed fixtures of tests/golden/ (inputs + oracle outputs frozen by tests/golden/make_golden.py):
+ * CPU: the oracle that is checked out still reproduces them (drift pin), and the library's host logic reproduces them through
+   the C ABI in the SIMT emulator (a subset it can afford);
+ * GPU (-m gpu): the CUDA path through the C ABI reproduces every one of them to 1e-10."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import golden_checks as gc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OPERATOR_FIXTURES = gc.fixtures("operators_")
+NAVIER_FIXTURES = gc.fixtures("navier_")
+
+
+def test_fixture_set_is_complete():
+    from tests.golden import make_golden as mk
+
+    assert OPERATOR_FIXTURES == sorted("operators_" + mk.space_name(sp) for sp in mk.OPERATOR_SPACES)
+    assert NAVIER_FIXTURES == sorted(mk.NAVIER_CASES)
+
+
+@pytest.mark.parametrize("name", OPERATOR_FIXTURES)
+def test_oracle_reproduces_operator_fixture(name):
+    from tests.golden import make_golden as mk
+
+    z = gc.load(name)
+    now = mk.operators(tuple(int(v) for v in z["space"]))
+    assert sorted(now) == sorted(z)
+    for k, v in now.items():
+        if k.startswith("poisson_") and k != "poisson_out":
+            continue   # the stored eigendecomposition is an input of the Navier fixtures; LAPACK builds may order / scale it differently
+        assert gc.rel(np.asarray(v), z[k]) < (1e-9 if k == "poisson_out" else 1e-13), k
+
+
+@pytest.mark.parametrize("name", NAVIER_FIXTURES)
+def test_oracle_reproduces_navier_fixture(name):
+    """From the stored input state and the stored eigendecomposition: independent of this host's LAPACK."""
+    from oracle import rustpde_oracle as o
+
+    z = gc.load(name)
+    nx, ny, ra, pr, dt, aspect, periodic, steps = z["params"]
+    eig = (z["poisson_lam"], z["poisson_fwd"], z["poisson_bwd"]) if "poisson_lam" in z else None
+    nav = o.Navier2D(int(nx), int(ny), float(ra), float(pr), float(dt), float(aspect), str(z["bc"]), periodic=bool(periodic), pois_eig=eig)
+    for k in ("temp", "velx", "vely", "pres"):
+        getattr(nav, k).vhat = z[f"in_{k}"].copy()
+    for _ in range(int(steps)):
+        nav.update()
+    for k, v in nav.state().items():
+        assert gc.rel(v, z[f"out_{k}"]) < 1e-12, k
+    assert abs(nav.div_norm() - float(z["div_norm"])) < 1e-12 * float(z["div_norm"])
+
+
+EMU_SCRIPT = r'''
+import sys
+sys.path.insert(0, %r)
+from tests import emu
+emu.activate()
+import rustpde_mpi_b200 as b2
+from tests import golden_checks as gc
+for name in sys.argv[1:]:
+    e = gc.check_operators(b2, name) if name.startswith("operators_") else gc.check_navier(b2, name)
+    dn = e.pop("div_norm", 0.0)
+    assert max(e.values()) < gc.TOL and dn < 1e-8, (name, e, dn)
+    print("ok", name, max(e.values()))
+'''
+
+
+def test_emulated_library_reproduces_fixtures():
+    """Host logic (lane programs, coefficient vectors, index algebra) of the same sources, compiled for the SIMT emulator, against
+    the fixtures -- test infrastructure, says nothing about GPU results."""
+    from tests.emu import build_emu
+
+    build_emu.build()
+    names = ["operators_cd65_cd65", "operators_r2c64_cn65", "operators_cdn65_cd65", "navier_confined_rbc_65_random", "navier_confined_hc_65"]
+    r = subprocess.run([sys.executable, "-c", EMU_SCRIPT % ROOT, *names], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok ") == len(names)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", OPERATOR_FIXTURES)
+def test_gpu_operators_against_fixture(name):
+    import rustpde_mpi_b200 as b2
+
+    errs = gc.check_operators(b2, name)
+    assert max(errs.values()) < gc.TOL, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAVIER_FIXTURES)
+def test_gpu_navier_against_fixture(name):
+    import rustpde_mpi_b200 as b2
+
+    errs = gc.check_navier(b2, name)
+    dn = errs.pop("div_norm")
+    assert max(errs.values()) < gc.TOL and dn < 1e-8, (errs, dn)
