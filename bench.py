@@ -13,6 +13,8 @@ value  : steps/s with state resident in HBM, CUDA events on the library's stream
 e2e    : the same step through the public API with HOST state: every step uploads the four
          spectral state arrays from pinned host memory, steps, and downloads them again.
 roofline: HBM-bound lane kernels: algorithmic bytes per step (728 N) / time in lane kernels.
+ops    : ms / transform and ms / solve (the second half of BASELINE.json's metric): forward, backward, to_ortho, from_ortho,
+         gradient, HholtzAdi and Poisson on standalone fields of the benchmarked size, each against its algorithmic bytes.
 cpu_baseline / --impl reference: the C++/OpenMP restatement of the reference's update() (oracle/cpu_restated.cpp: one
          pass per reference call, lane-parallel, OpenBLAS DGEMM) timed on the host cores (the Rust reference cannot be
          built in this image: no cargo/rustc).
@@ -177,6 +179,69 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def time_ops(b2, ctx, cfg, eig, peak_gbs, world=1, calls=10):
+    """ms / transform and ms / solve (BASELINE.json's metric names them next to timesteps/s; the reference's own harnesses are
+    benches/benchmark_transform.rs and benchmark_solver.rs): the field operators and the two solvers of the step on standalone
+    fields of the benchmarked size, each timed alone with CUDA events on the library's stream (`calls` back-to-back calls after
+    2 warm-ups, results written into preallocated arrays).  `hbm_frac` = SURVEY 8(d)'s algorithmic bytes of the operator
+    (2 sweeps x read + write = 32 N bytes; confined Poisson 48 N + 16 (nx-2)^2) / time / measured HBM peak; the confined Poisson
+    solve is bound by its two FP64 GEMMs, not by HBM (see roofline.gemm)."""
+    nx, ny, ra, dt, per = CONFIGS[cfg]
+    N = nx * ny
+    b0 = b2.fourier_r2c(nx) if per else b2.cheb_dirichlet(nx)
+    p0 = b2.fourier_r2c(nx) if per else b2.cheb_neumann(nx)
+    f = b2.Field2(b2.Space2(b0, b2.cheb_dirichlet(ny), ctx=ctx))       # the space of temp / velx / vely (navier.rs:232-244)
+    fp = b2.Field2(b2.Space2(p0, b2.cheb_neumann(ny), ctx=ctx))        # the space of pres / pseu
+    f.vhat = np_zeros_like_vhat(f)
+    ortho = b2.DeviceArray(f.space, b2.ORTHO)
+    ortho_p = b2.DeviceArray(fp.space, b2.ORTHO)
+    out_p = b2.DeviceArray(fp.space, b2.SPECTRAL)
+    out_h = b2.DeviceArray(f.space, b2.SPECTRAL)
+    hh = b2.HholtzAdi(f, [dt * 1e-3, dt * 1e-3])
+    po = b2.Poisson(fp, [1.0, 1.0], eig=eig) if not per else b2.Poisson(fp, [1.0, 1.0])
+
+    def timed(fn):
+        fn(); fn()
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(calls):
+            fn()
+        return ctx.timer_stop() / calls
+
+    ms = {
+        "backward": timed(f.backward),
+        "forward": timed(f.forward),
+        "to_ortho": timed(lambda: f.to_ortho(out=ortho)),
+        "from_ortho": timed(lambda: f.from_ortho(ortho)),
+        "gradient_10": timed(lambda: f.gradient((1, 0), None, out=ortho)),
+        "gradient_02": timed(lambda: f.gradient((0, 2), None, out=ortho)),
+        "hholtz_adi": timed(lambda: hh.solve(ortho, out_h)),
+        "poisson": timed(lambda: po.solve(ortho_p, out_p)),
+    }
+    alg = {k: 32.0 * N / world for k in ms}
+    if not per:
+        alg["poisson"] = (48.0 * N + 16.0 * (nx - 2) ** 2) / world
+    frac = {k: (alg[k] / (ms[k] * 1e-3) / 1e9 / peak_gbs) if ms[k] > 0 else None for k in ms}
+    for o_ in (hh, po, ortho, ortho_p, out_p, out_h, f, fp):
+        o_.close()
+    return {"ms_per_transform": {"forward": ms["forward"], "backward": ms["backward"]},
+            "ms_per_solve": {"hholtz_adi": ms["hholtz_adi"], "poisson": ms["poisson"]},
+            "ms_per_projection": {k: ms[k] for k in ("to_ortho", "from_ortho", "gradient_10", "gradient_02")},
+            "hbm_frac": frac, "alg_bytes": alg, "calls": calls,
+            "note": "standalone operator calls (2 lane passes each: along y, transposing store, along x, transposing store back); "
+                    "forward / backward include the composite <-> orthonormal projection; inside update() they are fused into the "
+                    "27 lane passes of the step, so these do not add up to ms_per_step"}
+
+
+def np_zeros_like_vhat(f):
+    """a smooth, non-trivial spectral state for the standalone operator timings (timing is data-independent)"""
+    import numpy as np
+
+    a = f.vhat
+    i = np.arange(a.shape[0])[:, None]; j = np.arange(a.shape[1])[None, :]
+    return (1.0 / (1.0 + i + j) ** 2).astype(a.dtype)
+
+
 def parity_small(b2, ctx, dist):
     """2 steps of a 257 x 129 confined problem on the SAME ranks / context as the timed run, gathered and compared with
     the numpy oracle (navier.rs:438-466 / navier_stokes_mpi/navier.rs:497-522).  Cheap; runs before the timing."""
@@ -209,6 +274,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ops", action="store_true", help="skip the standalone ms/transform, ms/solve timings")
+    ap.add_argument("--ops-multi", action="store_true", help="also time the standalone operators on N > 1 ranks (slab fields)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity checks (small multi-rank problem; workload vs CPU restatement)")
     ap.add_argument("--mode", type=int, default=1, help="1 fused+graph (default), 3 fused without graph, 0 one pass pair per reference call")
     args = ap.parse_args()
@@ -240,7 +307,7 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group(backend="cpu:gloo,cuda:nccl")
-        heap = (110 * (nx + 64) * (ny + 64) * 8) // world + (64 << 20)
+        heap = ((160 if args.ops_multi else 110) * (nx + 64) * (ny + 64) * 8) // world + (64 << 20)
         ctx = b2.Context.distributed(local, heap)
     else:
         ctx = b2.Context(local)
@@ -438,6 +505,14 @@ def main():
             assert max(e_smooth.values()) < 1e-10 and max(e_rand.values()) < 1e-6, parity_workload
         del cnav
 
+    # ---- ms / transform, ms / solve (the metric's second half): standalone operators on the benchmarked size ----
+    ops, ops_error = None, None
+    if not args.no_ops and (world == 1 or args.ops_multi):   # N > 1: opt-in (--ops-multi); the slab operators are covered by tests/test_gpu_multi.py
+        try:
+            ops = time_ops(b2, ctx, cfg, eig, peak, world)
+        except Exception as ex:  # noqa: BLE001 - the step line must still be printed
+            ops, ops_error = None, repr(ex)
+
     line = {
         "metric": "Navier2D timesteps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -447,7 +522,7 @@ def main():
                 "schedule": {1: "fused, CUDA-graph replay", 3: "fused, no graph", 0: "one pass pair per reference call"}.get(args.mode, str(args.mode)),
                 "launches_per_step": nav.launches_per_step(), "parallel_branches": bool(info["branches"])},
         "clocks": clocks, "e2e": e2e, "e2e_error": e2e_error, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "parity_check": parity, "parity_check_workload": parity_workload,
+        "parity_check": parity, "parity_check_workload": parity_workload, "ops": ops, "ops_error": ops_error,
         "setup_s": setup_s, "div_norm": div,
     }
     if rank == 0:
