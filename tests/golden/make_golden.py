@@ -25,7 +25,7 @@ if ROOT not in sys.path:
 from oracle import rustpde_oracle as o  # noqa: E402
 
 # (kind, n) pairs: ChebDirichlet 1, ChebNeumann 2, Chebyshev 0, ChebDirichletNeumann 3, FourierR2c 4
-OPERATOR_SPACES = [(1, 65, 1, 65), (2, 65, 2, 65), (0, 65, 0, 65), (4, 64, 1, 65), (4, 64, 2, 65), (3, 65, 1, 65), (1, 129, 2, 65)]
+OPERATOR_SPACES = [(1, 65, 1, 65), (2, 65, 2, 65), (0, 65, 0, 65), (4, 64, 1, 65), (4, 64, 2, 65), (2, 65, 3, 65), (1, 129, 2, 65)]
 GRADIENTS = [(1, 0), (0, 1), (2, 0), (0, 2), (1, 1)]
 NAVIER_CASES = {
     # name: (nx, ny, ra, pr, dt, aspect, bc, periodic, init, steps)
