@@ -5,7 +5,7 @@ the reference's hot path) for the field operators, the solvers and whole ``Navie
 (/root/reference/src/navier_stokes/navier.rs:438-466), frozen as ``.npz`` files.  The reference itself is Rust and cannot be
 built or imported in this image (no cargo / rustc, funspace not vendored), so these vectors are NOT outputs of the
 reference: they pin the oracle against drift (a change to the oracle that moves any of them fails
-``tests/test_golden_fixtures.py`` on the CPU) and give the GPU tests a target that does not depend on the oracle code that
+``tests/test_gpu_w_golden_fixtures.py`` on the CPU) and give the GPU tests a target that does not depend on the oracle code that
 happens to be checked out.  The vectors the reference's own tests hold (hholtz_adi.rs:193-246, poisson.rs:275-361,
 fdma_tensor.rs:386-401, pdma_plus2.rs:210) are in tests/test_oracle_golden.py and pin the oracle itself.
 

@@ -1,4 +1,5 @@
-"""The committed fixtures of tests/golden/ (inputs + oracle outputs frozen by tests/golden/make_golden.py):
+"""(Named test_gpu_w_* so that under `pytest -x -m gpu` it runs after the older GPU suites and before the any-size file.)
+The committed fixtures of tests/golden/ (inputs + oracle outputs frozen by tests/golden/make_golden.py):
  * CPU: the oracle that is checked out still reproduces them (drift pin), and the library's host logic reproduces them through
    the C ABI in the SIMT emulator (a subset it can afford);
  * GPU (-m gpu): the CUDA path through the C ABI reproduces every one of them to 1e-10."""
