@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ops", action="store_true", help="skip the standalone ms/transform, ms/solve timings")
+    ap.add_argument("--ops-calls", type=int, default=10, help="timed calls per standalone operator")
     ap.add_argument("--ops-multi", action="store_true", help="also time the standalone operators on N > 1 ranks (slab fields)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity checks (small multi-rank problem; workload vs CPU restatement)")
     ap.add_argument("--mode", type=int, default=1, help="1 fused+graph (default), 3 fused without graph, 0 one pass pair per reference call")
@@ -509,7 +510,7 @@ def main():
     ops, ops_error = None, None
     if not args.no_ops and (world == 1 or args.ops_multi):   # N > 1: opt-in (--ops-multi); the slab operators are covered by tests/test_gpu_multi.py
         try:
-            ops = time_ops(b2, ctx, cfg, eig, peak, world)
+            ops = time_ops(b2, ctx, cfg, eig, peak, world, calls=max(1, args.ops_calls))
         except Exception as ex:  # noqa: BLE001 - the step line must still be printed
             ops, ops_error = None, repr(ex)
 
