@@ -179,7 +179,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def time_ops(b2, ctx, cfg, eig, peak_gbs, world=1, calls=10):
+def time_ops(b2, ctx, cfg, eig, peak_gbs, world=1, calls=10, dist=None):
     """ms / transform and ms / solve (BASELINE.json's metric names them next to timesteps/s; the reference's own harnesses are
     benches/benchmark_transform.rs and benchmark_solver.rs): the field operators and the two solvers of the step on standalone
     fields of the benchmarked size, each timed alone with CUDA events on the library's stream (`calls` back-to-back calls after
@@ -218,6 +218,12 @@ def time_ops(b2, ctx, cfg, eig, peak_gbs, world=1, calls=10):
         "hholtz_adi": timed(lambda: hh.solve(ortho, out_h)),
         "poisson": timed(lambda: po.solve(ortho_p, out_p)),
     }
+    if dist is not None:   # device time of the slowest rank, as for the step
+        import torch
+
+        t = torch.tensor([ms[k] for k in sorted(ms)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = {k: float(v) for k, v in zip(sorted(ms), t)}
     alg = {k: 32.0 * N / world for k in ms}
     if not per:
         alg["poisson"] = (48.0 * N + 16.0 * (nx - 2) ** 2) / world
@@ -510,7 +516,7 @@ def main():
     ops, ops_error = None, None
     if not args.no_ops and (world == 1 or args.ops_multi):   # N > 1: opt-in (--ops-multi); the slab operators are covered by tests/test_gpu_multi.py
         try:
-            ops = time_ops(b2, ctx, cfg, eig, peak, world, calls=max(1, args.ops_calls))
+            ops = time_ops(b2, ctx, cfg, eig, peak, world, calls=max(1, args.ops_calls), dist=dist)
         except Exception as ex:  # noqa: BLE001 - the step line must still be printed
             ops, ops_error = None, repr(ex)
 

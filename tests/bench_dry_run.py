@@ -15,6 +15,10 @@ import torch  # noqa: E402
 torch.cuda.set_device = lambda *a, **k: None
 torch.cuda.synchronize = lambda *a, **k: None
 torch.Tensor.pin_memory = lambda self, *a, **k: self
+import torch.distributed as _dist  # noqa: E402
+
+_init = _dist.init_process_group
+_dist.init_process_group = lambda backend=None, **k: _init(backend="gloo", **k)   # no NCCL without a GPU
 
 import bench  # noqa: E402
 import rustpde_mpi_b200 as b2  # noqa: E402

@@ -27,3 +27,20 @@ def test_bench_main_dry_run_prints_the_contract_line():
     assert line["ops"]["alg_bytes"]["forward"] == 32.0 * 65 * 65
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(os.environ.get("B2_SLOW_TESTS") != "1", reason="opt-in (B2_SLOW_TESTS=1): ~1 min on 2 emulated ranks")
+def test_bench_main_dry_run_two_ranks():
+    """the N > 1 control flow under torchrun: distributed context, all-reduced timings, identical burst counts on every rank,
+    standalone operators on slabs (--ops-multi), rank 0 alone prints"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", os.path.join(ROOT, "tests", "bench_dry_run.py"), "T0", "--gpus", "2", "--steps", "2", "--warmup", "3",
+                        "--no-parity", "--no-cpu-baseline", "--ops-calls", "1", "--ops-multi"], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["ops_error"] is None and line["e2e_error"] is None and line["gpu_launches"] == 2 * line["run"]["launches_per_step"]
