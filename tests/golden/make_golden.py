@@ -25,7 +25,10 @@ if ROOT not in sys.path:
 from oracle import rustpde_oracle as o  # noqa: E402
 
 # (kind, n) pairs: ChebDirichlet 1, ChebNeumann 2, Chebyshev 0, ChebDirichletNeumann 3, FourierR2c 4
-OPERATOR_SPACES = [(1, 65, 1, 65), (2, 65, 2, 65), (0, 65, 0, 65), (4, 64, 1, 65), (4, 64, 2, 65), (2, 65, 3, 65), (1, 129, 2, 65)]
+# every base pairing the reference uses (cd x cd, cn x cd, cn x cn, ch x ch, r2c x {cd, cn, ch}; cn x cdn for bc = "hc"),
+# at transform sizes (65, 129) and at small sizes (9 .. 33, the dense-matrix transform path)
+OPERATOR_SPACES = [(1, 65, 1, 65), (2, 65, 2, 65), (0, 65, 0, 65), (4, 64, 1, 65), (4, 64, 2, 65), (2, 65, 3, 65), (1, 129, 2, 65),
+                   (2, 65, 1, 65), (4, 64, 0, 65), (1, 9, 1, 9), (2, 17, 1, 17), (4, 16, 1, 17), (0, 33, 0, 33), (4, 32, 2, 33)]
 GRADIENTS = [(1, 0), (0, 1), (2, 0), (0, 2), (1, 1)]
 NAVIER_CASES = {
     # name: (nx, ny, ra, pr, dt, aspect, bc, periodic, init, steps)
@@ -34,6 +37,8 @@ NAVIER_CASES = {
     "navier_confined_hc_65": (65, 65, 1e5, 1.0, 0.01, 1.0, "hc", False, "modes", 3),
     "navier_periodic_rbc_64x65": (64, 65, 1e5, 1.0, 0.01, 1.0, "rbc", True, "modes", 5),
     "navier_confined_rbc_129x65_aspect2": (129, 65, 1e6, 0.7, 0.005, 2.0, "rbc", False, "modes", 3),
+    # BASELINE configs[0] = examples/navier_rbc.rs: 129 x 129, Ra 1e5, Pr 1, dt 0.01, set_velocity / set_temperature(0.2, 1, 1), 100 steps
+    "navier_c1_129_100steps": (129, 129, 1e5, 1.0, 0.01, 1.0, "rbc", False, "modes", 100),
 }
 
 
