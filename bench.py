@@ -114,6 +114,16 @@ def time_cpu(nav, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
+def cpu_ops(nav, calls=3):
+    """ms / transform and ms / solve of the CPU restatement (same operators, same spaces as the repo arm's `ops`)."""
+    sec = nav.time_ops(calls)
+    ms = {k: 1e3 * v for k, v in sec.items()}
+    return {"ms_per_transform": {"forward": ms["forward"], "backward": ms["backward"]},
+            "ms_per_solve": {"hholtz_adi": ms["hholtz_adi"], "poisson": ms["poisson"]},
+            "ms_per_projection": {k: ms[k] for k in ("to_ortho", "from_ortho", "gradient_10", "gradient_02")},
+            "calls": calls, "threads": nav.threads}
+
+
 def cpu_best_threads(cfg, eig):
     """Thread count of the CPU arm: the reference runs its `*_par` passes on the rayon pool and OpenBLAS on its own threads -- more
     threads is not always faster (on the 128-thread GPU host the all-threads run of 1025^2 was 14x slower than one thread), so the
@@ -164,6 +174,10 @@ def run_reference(args):
     nav = cpu_restated(cfg, eig, threads=threads)
     sec = time_cpu(nav, args.steps, args.warmup)
     v = 1.0 / sec
+    try:
+        ops = cpu_ops(nav)
+    except Exception as ex:  # noqa: BLE001 - the step line must still be printed
+        ops = {"error": repr(ex)}
     line = {
         "impl": "reference", "metric": "Navier2D timesteps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
@@ -175,6 +189,7 @@ def run_reference(args):
                                    f"(reference Rust toolchain absent), {nav.threads} threads (best of the sweep)",
                          "threads_tried_s_per_step": tried, "host_cores": os.cpu_count()},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ops": ops,
     }
     print(json.dumps(line), flush=True)
 
@@ -481,6 +496,10 @@ def main():
                "openblas_dgemm": cnav.blas,
                "sample": f"{n_cpu} full update() steps (after 1 warm-up) of the C++/OpenMP restatement of the reference's pass structure at the same config, {cnav.threads} threads ({sec * n_cpu:.1f} s)",
                "threads_tried_s_per_step": cpu_tried, "host_cores": os.cpu_count()}
+        try:
+            cpu["ops"] = cpu_ops(cnav)
+        except Exception as ex:  # noqa: BLE001
+            cpu["ops"] = {"error": repr(ex)}
         if nx * ny <= 1100 * 1100:   # the 1-thread figure (README's OPENBLAS_NUM_THREADS=1 mode) where it costs seconds
             cpu["value_1thread"] = 1.0 / cpu_tried[1]
             del cnav

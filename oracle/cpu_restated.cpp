@@ -562,6 +562,7 @@ struct NavBase {
   virtual void set_vhat(int which, const double* in) = 0;
   virtual double div_norm() = 0;
   virtual void vhat_shape(int which, int* r, int* c, int* cx) = 0;
+  virtual void time_ops(int calls, double* sec) = 0;
 };
 
 template <class T> struct Navier : NavBase {
@@ -684,6 +685,30 @@ template <class T> struct Navier : NavBase {
   void vhat_shape(int which, int* r, int* c, int* cx) override { Field<T>* f = fld(which); *r = f->vhat.r; *c = f->vhat.c; *cx = periodic; }
   void get_vhat(int which, double* out) override { Field<T>* f = fld(which); memcpy(out, f->vhat.data(), f->vhat.bytes()); }
   void set_vhat(int which, const double* in) override { Field<T>* f = fld(which); memcpy(f->vhat.data(), in, f->vhat.bytes()); }
+  // Seconds per call of the standalone operators on the temperature / pseudo-pressure spaces of this problem (the CPU side of
+  // bench.py's ms / transform and ms / solve; the reference's harnesses are benches/benchmark_transform.rs, benchmark_solver.rs).
+  // sec[8] = backward, forward, to_ortho, from_ortho, gradient (1,0), gradient (0,2), HholtzAdi solve, Poisson solve.  The state
+  // of the run is not touched (copies of temp / pseu are used); one untimed call first.
+  void time_ops(int calls, double* sec) override {
+    Arr<T> vh = temp.vhat, o, g, sol, rhs_p, sol_p;
+    Arr<double> v;
+    temp.sp.to_ortho(vh, o);
+    pseu.sp.to_ortho(pseu.vhat, rhs_p);
+    auto timed = [&](auto fn) {
+      fn();
+      const double t0 = omp_get_wtime();
+      for (int i = 0; i < calls; i++) fn();
+      return (omp_get_wtime() - t0) / calls;
+    };
+    sec[0] = timed([&] { temp.sp.backward(vh, v); });
+    sec[1] = timed([&] { temp.sp.forward(v, vh); });
+    sec[2] = timed([&] { temp.sp.to_ortho(vh, o); });
+    sec[3] = timed([&] { temp.sp.from_ortho(o, vh); });
+    sec[4] = timed([&] { temp.sp.gradient(vh, 1, 0, nullptr, g); });
+    sec[5] = timed([&] { temp.sp.gradient(vh, 0, 2, nullptr, g); });
+    sec[6] = timed([&] { hh[2].solve(o, sol); });
+    sec[7] = timed([&] { pois.solve(rhs_p, sol_p); });
+  }
 };
 
 extern "C" {
@@ -726,4 +751,5 @@ void rc_navier_vhat_shape(void* h, int which, int* r, int* c, int* cx) { static_
 void rc_navier_get_vhat(void* h, int which, double* out) { static_cast<NavBase*>(h)->get_vhat(which, out); }
 void rc_navier_set_vhat(void* h, int which, const double* in) { static_cast<NavBase*>(h)->set_vhat(which, in); }
 double rc_navier_div_norm(void* h) { return static_cast<NavBase*>(h)->div_norm(); }
+void rc_navier_time_ops(void* h, int calls, double* sec) { static_cast<NavBase*>(h)->time_ops(calls < 1 ? 1 : calls, sec); }
 }

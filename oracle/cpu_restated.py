@@ -120,6 +120,14 @@ class Navier2D:
     def div_norm(self):
         return float(lib().rc_navier_div_norm(self._h))
 
+    OPS = ("backward", "forward", "to_ortho", "from_ortho", "gradient_10", "gradient_02", "hholtz_adi", "poisson")
+
+    def time_ops(self, calls=3):
+        """Seconds per call of the standalone operators on this problem's temperature / pseudo-pressure spaces (state untouched)."""
+        sec = (C.c_double * 8)()
+        lib().rc_navier_time_ops(self._h, int(calls), sec)
+        return dict(zip(self.OPS, (float(v) for v in sec)))
+
     def state(self):
         return {k: self.vhat(k) for k in ("temp", "velx", "vely", "pres")}
 

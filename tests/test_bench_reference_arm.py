@@ -26,6 +26,8 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and str(cb["cores"]) in cb["threads_tried_s_per_step"]
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    ops = d["ops"]   # ms / transform, ms / solve of the CPU arm (the metric's second half)
+    assert "error" not in ops and all(v > 0 for v in ops["ms_per_transform"].values()) and all(v > 0 for v in ops["ms_per_solve"].values())
 
 
 def test_reference_arm_other_ranks_do_nothing():

@@ -47,3 +47,21 @@ def test_single_thread_equals_all_threads():
     b.update(2)
     for k, v in b.state().items():
         assert np.array_equal(v, sa[k])   # lanes are independent: the thread count must not change a single bit
+
+
+def test_time_ops_leaves_the_state_alone():
+    """bench.py's CPU ms / transform, ms / solve run on copies: the run's state must not move."""
+    from oracle import cpu_restated as cr
+
+    nav = cr.Navier2D(65, 65, 1e5, 1.0, 0.01, 1.0, "rbc", threads=2)
+    nav.set_velocity(0.2, 1.0, 1.0); nav.set_temperature(0.2, 1.0, 1.0)
+    nav.update(2)
+    before = nav.state()
+    sec = nav.time_ops(2)
+    assert set(sec) == set(cr.Navier2D.OPS) and all(v > 0 for v in sec.values())
+    after = nav.state()
+    assert all(np.array_equal(before[k], after[k]) for k in before)
+    navp = cr.Navier2D(64, 65, 1e5, 1.0, 0.01, 1.0, "rbc", periodic=True, threads=2)
+    navp.set_velocity(0.2, 1.0, 1.0); navp.set_temperature(0.2, 1.0, 1.0)
+    navp.update(1)
+    assert all(v > 0 for v in navp.time_ops(1).values())
