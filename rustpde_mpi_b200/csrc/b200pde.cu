@@ -69,6 +69,7 @@ struct b2_ctx {
   long long barriers = 0;
   unsigned long long* d_prof = nullptr;   // per-op cycle counters (debug/profiling)
   int* d_differs = nullptr;               // result word of k_same_value (collective allocator)
+  double* d_acc = nullptr;                // accumulator of the norm reductions (integrate() asks for |div| after every step)
 };
 static const size_t B2_HEAP_RESERVED = 4096;  // flags[0..nranks) + epoch counter live at the start of the heap
 
@@ -1445,6 +1446,7 @@ int b2_ctx_destroy(b2_ctx* c) {
   if (c->stage) cudaFree(c->stage);
   if (c->d_prof) cudaFree(c->d_prof);
   if (c->d_differs) cudaFree(c->d_differs);
+  if (c->d_acc) cudaFree(c->d_acc);
   if (c->d_peers) cudaFree(c->d_peers);
 #ifndef B2_EMU
   for (int r = 0; r < c->nranks; r++) if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
@@ -1709,9 +1711,8 @@ int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const doubl
   return B2_OK;
 }
 static int norm2_dev(b2_space* sp, const double* d, double* out, bool global) {
-  ScratchBuf buf;
-  CK(cudaMalloc(&buf.p, sizeof(double)));
-  double* acc = buf.p;
+  if (!sp->ctx->d_acc) CK(cudaMalloc(&sp->ctx->d_acc, sizeof(double)));   // once per context, released by b2_ctx_destroy
+  double* acc = sp->ctx->d_acc;
   CK(cudaMemsetAsync(acc, 0, sizeof(double), sp->ctx->stream));
   const size_t n = sp->elems();
   B2_LAUNCH(k_sumsq, ew_grid(n), 256, 0, sp->ctx->stream, n, d, acc);
