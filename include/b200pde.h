@@ -89,7 +89,8 @@ int b2_field_array(b2_field* f, int which /* 0 = v, 1 = vhat */, b2_array** out 
 int b2_array_copy(b2_array* dst, const b2_array* src);                                            /* same padded shape */
 int b2_array_combine(b2_array* dst, const b2_array* a, const b2_array* b, int op, double alpha);   /* 0: alpha a b; 1: alpha sqrt(a^2+b^2); 2: dst + alpha a b */
 /* dx-weighted sums over this rank's rows of a real array: mode 0: out[0] = sum_ij w0[i] w1[j] a[i][j]; mode 1: out[j] = sum_i w0[i] a[i][j]
- * (w0: one weight per LOCAL row, w1 / out: one per column; the caller adds the ranks' partial sums -- all_gather_sum) */
+ * (w0: one weight per LOCAL row, w1 / out: one per column; the caller adds the ranks' partial sums -- all_gather_sum);
+ * mode 2: out[i] = sum_j w1[j] a[i][j] for this rank's LOCAL rows i (average_axis(1); the caller concatenates the ranks' parts) */
 int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const double* w1, int mode, double* out);
 int b2_array_norm2(const b2_array* a, double* out);              /* sqrt(sum |a|^2) of the GLOBAL array (collective over the ranks), functions.rs:24-35 */
 

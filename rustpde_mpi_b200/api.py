@@ -288,6 +288,41 @@ class Field2:
             self.x[i] = self.x[i] * sc
             self.dx[i] = self.dx[i] * sc
 
+    def average_axis(self, axis):
+        """``FieldBase::average_axis`` (src/field/average.rs:26-35; slabs: src/field_mpi/average.rs:15-61): dx-weighted mean of
+        ``v`` along ``axis``, reduced on the device; with several ranks the partial sums (axis 0) / row parts (axis 1) are combined
+        like the reference's ``all_gather_sum`` / gather.  Returns the global 1-D array on every rank."""
+        if axis not in (0, 1):
+            raise B2Error("average_axis: axis 0 or 1")
+        arr = C.c_void_p()
+        check(lib().b2_field_array(self._h, 0, C.byref(arr)))
+        lo = self.local_slice(PHYSICAL)
+        w0 = np.ascontiguousarray((self.dx[0] / abs(self.x[0][-1] - self.x[0][0]))[lo])
+        w1 = np.ascontiguousarray(self.dx[1] / abs(self.x[1][-1] - self.x[1][0]))
+        if len(w0) == 0:
+            w0 = np.zeros(1)   # a rank without rows still takes part in the collective below
+        ctx = self.space.ctx
+        if axis == 0:
+            out = np.zeros(len(w1))
+            check(lib().b2_array_weighted_sum(arr, _dp(w0), _dp(w1), 1, _dp(out)))
+            return ctx.all_reduce_sum(out)
+        out = np.zeros(max(1, lo.stop - lo.start))
+        check(lib().b2_array_weighted_sum(arr, _dp(w0), _dp(w1), 2, _dp(out)))
+        return ctx.all_gather_rows(out[: lo.stop - lo.start])
+
+    def average(self):
+        """``FieldBase::average`` (src/field/average.rs:53-59): volume-weighted mean of ``v``."""
+        arr = C.c_void_p()
+        check(lib().b2_field_array(self._h, 0, C.byref(arr)))
+        lo = self.local_slice(PHYSICAL)
+        w0 = np.ascontiguousarray((self.dx[0] / abs(self.x[0][-1] - self.x[0][0]))[lo])
+        w1 = np.ascontiguousarray(self.dx[1] / abs(self.x[1][-1] - self.x[1][0]))
+        if len(w0) == 0:
+            w0 = np.zeros(1)
+        out = np.zeros(1)
+        check(lib().b2_array_weighted_sum(arr, _dp(w0), _dp(w1), 0, _dp(out)))
+        return float(self.space.ctx.all_reduce_sum(out)[0])
+
     def local_rows(self, kind):
         """(first row, count) of this rank's slab of ``v`` (PHYSICAL) or ``vhat`` (SPECTRAL): axis 0 is
         split in contiguous blocks (y-pencil of src/field_mpi.rs:71-88); one rank owns everything."""

@@ -598,6 +598,14 @@ __global__ void k_weighted_sum(const double* __restrict__ a, int rows, int cols,
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
+// mode 2: thread per local row i, out[i] = sum_j w1[j] a[i][j]  (average_axis(1): one value per x row of this rank's slab)
+__global__ void k_weighted_rowsum(const double* __restrict__ a, int rows, int cols, int tiles, const double* __restrict__ w1, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double s = 0.0;
+  for (int j = 0; j < cols; j++) s += w1[j] * a[tiled_index(i, j, tiles)];
+  out[i] = s;
+}
 
 static int ew_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 8); }
 
@@ -1690,23 +1698,27 @@ struct ScratchBuf {
   ~ScratchBuf() { if (p) cudaFree(p); }
 };
 int b2_array_weighted_sum(const b2_array* a, const double* w0_local, const double* w1, int mode, double* out) {
-  if (!a || !w0_local || !w1 || !out || (mode != 0 && mode != 1)) return fail(B2_ERR_ARG, "b2_array_weighted_sum: null argument or mode not 0 / 1");
+  if (!a || !w0_local || !w1 || !out || mode < 0 || mode > 2) return fail(B2_ERR_ARG, "b2_array_weighted_sum: null argument or mode not 0 / 1 / 2");
   b2_space* sp = a->sp;
   if (shape_complex(sp, a->shape_kind)) return fail(B2_ERR_UNSUPPORTED, "weighted sums are defined on real (physical) arrays");
   int rows, cols, row0, cnt;
   RET(shape_of(sp, a->shape_kind, &rows, &cols));
   local_rows(sp, rows, &row0, &cnt);
-  const int nout = mode == 1 ? cols : 1;
+  const int nout = mode == 1 ? cols : mode == 2 ? cnt : 1;
   ScratchBuf buf;
   CK(cudaMalloc(&buf.p, (size_t)(cnt + cols + nout + 1) * sizeof(double)));
   double* dw0 = buf.p; double* dw1 = buf.p + cnt; double* dout = dw1 + cols;
   if (cnt) CK(cudaMemcpyAsync(dw0, w0_local, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
   CK(cudaMemcpyAsync(dw1, w1, (size_t)cols * sizeof(double), cudaMemcpyHostToDevice, sp->ctx->stream));
   CK(cudaMemsetAsync(dout, 0, (size_t)nout * sizeof(double), sp->ctx->stream));
-  B2_LAUNCH(k_weighted_sum, (cols + 127) / 128, 128, 0, sp->ctx->stream, a->d, cnt, cols, sp->P[1] / 4, dw0, dw1, mode, dout);
+  if (mode == 2) {
+    if (cnt) B2_LAUNCH(k_weighted_rowsum, (cnt + 127) / 128, 128, 0, sp->ctx->stream, a->d, cnt, cols, sp->P[1] / 4, dw1, dout);
+  } else {
+    B2_LAUNCH(k_weighted_sum, (cols + 127) / 128, 128, 0, sp->ctx->stream, a->d, cnt, cols, sp->P[1] / 4, dw0, dw1, mode, dout);
+  }
   CK(cudaGetLastError());
   sp->ctx->launches++;
-  CK(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
+  if (nout) CK(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, sp->ctx->stream));
   CK(cudaStreamSynchronize(sp->ctx->stream));
   return B2_OK;
 }

@@ -96,6 +96,14 @@ def main():
             assert float(np.abs(got - fo.vhat).max() / np.abs(fo.vhat).max()) < 1e-10
         fg.scatter_spectral_root(fo.vhat if rank == 0 else None, root=0)
         assert np.array_equal(fg.all_gather_spectral(), fo.vhat)
+        # average_axis / average on slabs (src/field_mpi/average.rs:15-61): partial sums added over the ranks (axis 0), row parts
+        # concatenated (axis 1)
+        fg.scatter_physical_root(vg if rank == 0 else None, root=0)
+        fo.v = vg
+        for ax in (0, 1):
+            a, b = fg.average_axis(ax), o.Navier2D.average_axis(fo, ax)
+            assert a.shape == b.shape and float(np.abs(a - b).max()) < 1e-13, (ax, a.shape, b.shape)
+        assert abs(fg.average() - o.Navier2D.average(fo)) < 1e-13
         # FourierC2c x ChebDirichlet on slabs: complex physical rows, forward / gradient / backward against the serial oracle
         if not periodic:
             fo = o.Field2(o.Space2(o.fourier_c2c(48), o.cheb_dirichlet(ny)))

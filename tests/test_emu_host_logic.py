@@ -54,6 +54,20 @@ elif case == "golden":
         raise SystemExit("expected a shape error")
     except b2.B2Error:
         pass
+elif case == "average":
+    # the reference's doc tests of average_axis / average (src/field/average.rs:12-25, 38-52) through the C ABI: Chebyshev 6 x 5,
+    # v[i, j] = j  =>  average_axis(0) = [0, 1, 2, 3, 4], average() = 2; both axes against the oracle on a random field
+    f = b2.Field2(b2.Space2(b2.chebyshev(6), b2.chebyshev(5)))
+    f.v = np.tile(np.arange(5.0), (6, 1))
+    np.testing.assert_allclose(f.average_axis(0), np.arange(5.0), rtol=0, atol=2e-15)
+    assert abs(f.average() - 2.0) < 2e-15
+    for sp in [(1, 65, 2, 33), (4, 64, 1, 65)]:
+        fo, fg = g.mk(*sp)
+        v = np.random.default_rng(3).standard_normal(fo.v.shape)
+        fo.v = v; fg.v = v
+        for ax in (0, 1):
+            np.testing.assert_allclose(fg.average_axis(ax), o.Navier2D.average_axis(fo, ax), rtol=0, atol=1e-14)
+        assert abs(fg.average() - o.Navier2D.average(fo)) < 1e-14
 elif case == "variants":
     # the same step through the alternative data-movement paths selected by the environment of this process
     errs = g.check_navier(65, 65, 1)
@@ -141,7 +155,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "navier", "hc", "snapshot", "anysize", "c2c"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "average", "navier", "hc", "snapshot", "anysize", "c2c"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]

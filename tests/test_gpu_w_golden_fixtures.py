@@ -100,3 +100,24 @@ def test_gpu_navier_against_fixture(name):
     errs = gc.check_navier(b2, name)
     dn = errs.pop("div_norm")
     assert max(errs.values()) < gc.TOL and dn < 1e-8, (errs, dn)
+
+
+@pytest.mark.gpu
+def test_gpu_average_doctest_goldens():
+    """The reference's doc tests of ``average_axis`` / ``average`` (src/field/average.rs:12-25, 38-52) on the device reductions:
+    Chebyshev 6 x 5, v[i, j] = j  =>  average_axis(0) = [0, 1, 2, 3, 4], average() = 2; both axes against the oracle."""
+    import rustpde_mpi_b200 as b2
+    from oracle import rustpde_oracle as o
+    from tests import gpu_checks as g
+
+    f = b2.Field2(b2.Space2(b2.chebyshev(6), b2.chebyshev(5)))
+    f.v = np.tile(np.arange(5.0), (6, 1))
+    np.testing.assert_allclose(f.average_axis(0), np.arange(5.0), rtol=0, atol=1e-14)
+    assert abs(f.average() - 2.0) < 1e-14
+    for sp in [(1, 65, 2, 129), (4, 64, 1, 65), (2, 1025, 1, 257)]:
+        fo, fg = g.mk(*sp)
+        v = np.random.default_rng(3).standard_normal(fo.v.shape)
+        fo.v = v; fg.v = v
+        for ax in (0, 1):
+            np.testing.assert_allclose(fg.average_axis(ax), o.Navier2D.average_axis(fo, ax), rtol=0, atol=1e-13)
+        assert abs(fg.average() - o.Navier2D.average(fo)) < 1e-13

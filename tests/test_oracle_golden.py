@@ -395,3 +395,21 @@ def test_sdma_like_the_reference_tests():
     np.testing.assert_allclose(mc @ o.Sdma(mc).solve(dc, 0), dc, atol=1e-14)
     d2 = np.arange(nx * 4, dtype=float).reshape(4, nx)   # along axis 1 of a 2-D array
     np.testing.assert_allclose(o.Sdma(m).solve(d2, 1) @ m.T, d2, atol=1e-13)
+
+
+def test_average_doctest_goldens():
+    # src/field/average.rs:12-25 and :38-52 (doc tests): Chebyshev 6 x 5, v[i, j] = j  =>  average_axis(0) = [0, 1, 2, 3, 4],
+    # average() = 2 -- pins the dx weights of Field2 (src/field.rs:135-163) and both reductions
+    f = o.Field2(o.Space2(o.chebyshev(6), o.chebyshev(5)))
+    f.v = np.tile(np.arange(5.0), (6, 1))
+    np.testing.assert_allclose(o.Navier2D.average_axis(f, 0), np.arange(5.0), rtol=0, atol=2e-15)
+    assert abs(o.Navier2D.average(f) - 2.0) < 2e-15
+
+
+def test_eig_like_the_reference_test():
+    # src/solver/utils.rs:183-204: Q diag(lam) Q^-1 reproduces the matrix (1e-3 absolute in the reference); eigenvalues descending
+    a = np.tile(np.arange(1.0, 6.0), (5, 1))
+    lam, q, qinv = o.eig(a)
+    np.testing.assert_allclose(q @ np.diag(lam) @ qinv, a, atol=1e-3)
+    np.testing.assert_allclose(q @ np.diag(lam) @ qinv, a, atol=1e-12)
+    assert np.all(np.diff(lam) <= 1e-12) and abs(lam[0] - 15.0) < 1e-12
