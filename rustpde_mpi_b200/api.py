@@ -651,7 +651,7 @@ class Navier2D:
     def close(self):
         """Free every device array, solver and space of this solver."""
         if getattr(self, "_h", None):
-            for k in ("_field", "_field2", "_temp_twin", "_diag_a", "_diag_b"):
+            for k in ("_field", "_field2", "_temp_twin", "_diag_a", "_diag_b", "_vel_twin", "_div_a", "_div_b"):
                 if getattr(self, k, None) is not None:
                     setattr(self, k, None)
             _release(lib().b2_navier_destroy, self._h)
@@ -712,6 +712,25 @@ class Navier2D:
         v = C.c_double()
         check(lib().b2_navier_div_norm(self._h, C.byref(v)))   # same value on every rank (all_gather_sum of navier_eq.rs:51,64)
         return v.value
+
+    def div(self):
+        """``Navier2D::div`` (src/navier_stokes/navier_eq.rs:19-24): d(velx)/dx + d(vely)/dy in the orthonormal space, computed
+        on the device (two gradients on a twin of the velocity space, summed); returns the global array on every rank."""
+        if getattr(self, "_vel_twin", None) is None:
+            self._vel_twin = Field2(Space2(*self.velx.space.bases, ctx=self.ctx))
+            self._div_a = DeviceArray(self._vel_twin.space, ORTHO)
+            self._div_b = DeviceArray(self._vel_twin.space, ORTHO)
+        tw = self._vel_twin
+        check(lib().b2_array_copy(self._borrow(tw, 1)._h, self._borrow(self.velx, 1)._h))
+        tw.gradient([1, 0], self.scale, out=self._div_a)
+        check(lib().b2_array_copy(self._borrow(tw, 1)._h, self._borrow(self.vely, 1)._h))
+        tw.gradient([0, 1], self.scale, out=self._div_b)
+        self._div_a.axpy(1.0, self._div_b)
+        return self.ctx.all_gather_rows(self._div_a.get())
+
+    def reset_time(self):
+        """navier.rs:185-187."""
+        self.set_time(0.0)
 
     def exit(self):
         """navier.rs:482-489: break when |div| is NaN."""

@@ -68,6 +68,18 @@ elif case == "average":
         for ax in (0, 1):
             np.testing.assert_allclose(fg.average_axis(ax), o.Navier2D.average_axis(fo, ax), rtol=0, atol=1e-14)
         assert abs(fg.average() - o.Navier2D.average(fo)) < 1e-14
+elif case == "div":
+    # Navier2D::div (navier_eq.rs:19-24) and reset_time (navier.rs:185-187) through the host mirror
+    for periodic in (False, True):
+        no, ng = g.make_navier_pair(64 if periodic else 65, 65, 1e5, 1.0, 0.01, 1.0, periodic)
+        no.update(); ng.update(1)
+        d, dref = ng.div(), no.div()
+        assert d.shape == dref.shape and d.dtype == dref.dtype
+        assert float(np.abs(d - dref).max() / np.abs(dref).max()) < g.TOL
+        assert abs(np.sqrt(np.sum(np.abs(d) ** 2)) - ng.div_norm()) < 1e-12 * max(1.0, ng.div_norm())
+        assert ng.get_time() > 0
+        ng.reset_time()
+        assert ng.get_time() == 0.0
 elif case == "variants":
     # the same step through the alternative data-movement paths selected by the environment of this process
     errs = g.check_navier(65, 65, 1)
@@ -155,7 +167,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "average", "navier", "hc", "snapshot", "anysize", "c2c"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "average", "div", "navier", "hc", "snapshot", "anysize", "c2c"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
