@@ -812,16 +812,44 @@ class Navier2D:
         check(lib().b2_array_combine(fv._h, self._borrow(self.velx, 0)._h, self._borrow(self.vely, 0)._h, 1, 2.0 * self.scale[1] / self.nu))
         return self._wsum(fv, 0)
 
-    def callback(self, info_name=None):
-        """The I/O part of ``callback_from_filename`` (src/navier_stokes/navier_io.rs:122-147): print time, |div|, Nu,
-        Nuv, Re and append ``time nu nuv re`` to ``info_name``.  HDF5 snapshots / statistics are out of scope
-        (SURVEY 2 rows 23, 28)."""
+    def callback_from_filename(self, flow_name, info_name, suppress_io=False, write_flow_intervall=None):
+        """``Navier2D::callback_from_filename`` (src/navier_stokes/navier_io.rs:84-147): write the flow field (always, or when
+        the time is within dt of a multiple of ``write_flow_intervall``), then print ``time |div| Nu Nuv Re`` and append
+        ``time nu nuv re`` to ``info_name`` unless ``suppress_io``.  The running statistics of the reference (``statistics.h5``)
+        are out of scope.  Snapshots use the dataset names of the reference's HDF5 files (snapshot.py)."""
+        t, dt = self.get_time(), self.get_dt()
+        if flow_name:
+            d = os.path.dirname(flow_name)
+            if d and self.ctx.rank == 0:
+                os.makedirs(d, exist_ok=True)
+            if write_flow_intervall is None or (t + dt / 2.0) % write_flow_intervall < dt:
+                self.write_unwrap(flow_name)
+        if suppress_io:
+            return None
         div, nu, nuv, re = self.div_norm(), self.eval_nu(), self.eval_nuvol(), self.eval_re()
-        print(f"time = {self.get_time():4.2f}      |div| = {div:4.2e}     Nu = {nu:5.3e}     Nuv = {nuv:5.3e}    Re = {re:5.3e}")
-        if info_name:
-            with open(info_name, "a") as fh:
-                fh.write(f"{self.get_time()} {nu} {nuv} {re}\n")
+        if self.ctx.rank == 0:
+            print(f"time = {t:4.2f}      |div| = {div:4.2e}     Nu = {nu:5.3e}     Nuv = {nuv:5.3e}    Re = {re:5.3e}")
+            if info_name:
+                d = os.path.dirname(info_name)
+                if d:
+                    os.makedirs(d, exist_ok=True)
+                with open(info_name, "a") as fh:
+                    fh.write(f"{t} {nu} {nuv} {re}\n")
         return div, nu, nuv, re
+
+    io_dir = None            # set to a directory (the reference uses "data") to make callback() write flow files and info.txt there
+    write_intervall = None   # navier.rs: Option<f64>, forwarded to callback_from_filename by callback()
+
+    def callback(self, info_name=None):
+        """``Integrate::callback`` (navier.rs:476-480).  With ``io_dir`` set it is the reference's callback: flow field to
+        ``<io_dir>/flow{time:0>8.2}.h5`` (``.npz`` when h5py is not installed) and one line to ``<io_dir>/info.txt``; by default (``io_dir`` None) it only prints the
+        diagnostics line (and appends to ``info_name`` when given) so that library users do not get files they did not ask for."""
+        if self.io_dir is not None:
+            from . import snapshot as sn
+
+            flow = os.path.join(self.io_dir, f"flow{self.get_time():0>8.2f}{sn.default_ext()}")   # .npz container without h5py
+            return self.callback_from_filename(flow, os.path.join(self.io_dir, "info.txt"), False, self.write_intervall)
+        return self.callback_from_filename(None, info_name, False, None)
 
     def set_mode(self, fused):
         check(lib().b2_navier_set_mode(self._h, int(fused)))

@@ -19,6 +19,15 @@ def _is_h5(filename):
     return str(filename).endswith((".h5", ".hdf5"))
 
 
+def default_ext():
+    """".h5" (the reference's container) when h5py is importable, else ".npz" (same dataset paths in a numpy container)."""
+    try:
+        import h5py  # noqa: F401
+        return ".h5"
+    except ImportError:
+        return ".npz"
+
+
 def save_datasets(filename, data):
     """data: {dataset path: array or scalar}."""
     if _is_h5(filename):

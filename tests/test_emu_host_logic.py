@@ -80,6 +80,30 @@ elif case == "div":
         assert ng.get_time() > 0
         ng.reset_time()
         assert ng.get_time() == 0.0
+elif case == "callback":
+    # integrate() + the reference's callback (navier.rs:476-480, navier_io.rs:84-147): flow files and info.txt under io_dir at the
+    # save times, readable back into a fresh solver
+    import tempfile, os, glob
+    d = tempfile.mkdtemp()
+    ng = b2.Navier2D.new_confined(65, 65, 1e5, 1.0, 0.01, 1.0, "rbc")
+    ng.set_velocity(0.2, 1.0, 1.0); ng.set_temperature(0.2, 1.0, 1.0)
+    ng.io_dir = os.path.join(d, "data")
+    b2.integrate(ng, 0.04, 0.02)
+    flows = sorted(os.path.basename(f) for f in glob.glob(os.path.join(d, "data", "flow*")))
+    from rustpde_mpi_b200 import snapshot as sn
+    ext = sn.default_ext()
+    assert flows == ["flow00000.02" + ext, "flow00000.04" + ext], flows
+    lines = open(os.path.join(d, "data", "info.txt")).read().strip().splitlines()
+    assert len(lines) == 2 and abs(float(lines[1].split()[0]) - 0.04) < 1e-12 and len(lines[1].split()) == 4
+    n2 = b2.Navier2D.new_confined(65, 65, 1e5, 1.0, 0.01, 1.0, "rbc")
+    n2.read(os.path.join(d, "data", "flow00000.04" + ext))
+    assert abs(n2.get_time() - 0.04) < 1e-12
+    for k, v in ng.state().items():
+        assert np.array_equal(n2.state()[k], v), k
+    ng.write_intervall = 100.0   # navier_io.rs:98-101: only near multiples of the interval
+    ng.callback()
+    assert len(glob.glob(os.path.join(d, "data", "flow*"))) == 2
+    assert ng.callback_from_filename(None, None, True) is None   # suppress_io
 elif case == "variants":
     # the same step through the alternative data-movement paths selected by the environment of this process
     errs = g.check_navier(65, 65, 1)
@@ -167,7 +191,7 @@ print("ok")
 ''' % ROOT
 
 
-@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "average", "div", "navier", "hc", "snapshot", "anysize", "c2c"])
+@pytest.mark.parametrize("case", ["ops", "poisson", "golden", "average", "div", "callback", "navier", "hc", "snapshot", "anysize", "c2c"])
 def test_emulated_host_logic(case):
     r = subprocess.run([sys.executable, "-c", SCRIPT, case], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
