@@ -13,7 +13,7 @@
 //! NOTE: this image has no Rust toolchain (probed: no cargo / rustc), so these sources are unbuilt here; the same ABI
 //! is exercised through ctypes (rustpde_mpi_b200/api.py) and through examples/cpp_driver.
 use b200pde_sys as sys;
-use ndarray::{Array2, ArrayBase, Data, DataMut, Ix2};
+use ndarray::{Array1, Array2, ArrayBase, Data, DataMut, Ix2};
 use std::ffi::{CStr, CString};
 use std::os::raw::c_void;
 use std::ptr;
@@ -190,6 +190,27 @@ impl GpuField2 {
         unsafe { sys::b2_array_destroy(arr) };
         out
     }
+    /// `FieldBase::average_axis` (src/field/average.rs:26-35) on one rank: the dx-weighted mean of `v` along `axis`, reduced on
+    /// the device (`w0`, `w1` = `dx / length` per axis, as the reference computes them from `self.dx`, `self.x`).  With several
+    /// ranks pass the weights of this rank's rows as `w0` and combine the results like src/field_mpi/average.rs:15-61
+    /// (axis 0: `all_gather_sum`; axis 1: concatenate the ranks' parts).
+    pub fn average_axis(&self, axis: usize, w0_local: &[f64], w1: &[f64]) -> Array1<f64> {
+        assert!(axis < 2);
+        let mut arr = ptr::null_mut();
+        check(unsafe { sys::b2_field_array(self.raw, 0, &mut arr) });
+        let mut out = Array1::<f64>::zeros(if axis == 0 { w1.len() } else { w0_local.len() });
+        let mode = if axis == 0 { 1 } else { 2 };
+        check(unsafe { sys::b2_array_weighted_sum(arr, w0_local.as_ptr(), w1.as_ptr(), mode, out.as_mut_ptr()) });
+        out
+    }
+    /// `FieldBase::average` (src/field/average.rs:53-59): this rank's part of the volume-weighted mean
+    pub fn average(&self, w0_local: &[f64], w1: &[f64]) -> f64 {
+        let mut arr = ptr::null_mut();
+        check(unsafe { sys::b2_field_array(self.raw, 0, &mut arr) });
+        let mut out = 0.0;
+        check(unsafe { sys::b2_array_weighted_sum(arr, w0_local.as_ptr(), w1.as_ptr(), 0, &mut out) });
+        out
+    }
 }
 impl Drop for GpuField2 {
     fn drop(&mut self) {
@@ -319,6 +340,10 @@ impl GpuNavier2D {
     }
     pub fn set_time(&mut self, t: f64) {
         check(unsafe { sys::b2_navier_set_time(self.raw, t) });
+    }
+    /// navier.rs:185-187
+    pub fn reset_time(&mut self) {
+        self.set_time(0.0);
     }
 }
 impl Integrate for GpuNavier2D {
