@@ -121,3 +121,36 @@ def test_gpu_average_doctest_goldens():
         for ax in (0, 1):
             np.testing.assert_allclose(fg.average_axis(ax), o.Navier2D.average_axis(fo, ax), rtol=0, atol=1e-13)
         assert abs(fg.average() - o.Navier2D.average(fo)) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("periodic", [False, True])
+def test_gpu_div_reset_time_and_reference_callback(periodic, tmp_path):
+    """``Navier2D::div`` (navier_eq.rs:19-24) against the oracle, ``reset_time`` (navier.rs:185-187) and ``integrate`` with the
+    reference's callback (navier.rs:476-480, navier_io.rs:84-147): flow files at the save times + info.txt."""
+    import glob
+
+    import rustpde_mpi_b200 as b2
+    from rustpde_mpi_b200 import snapshot as sn
+    from tests import gpu_checks as g
+
+    no, ng = g.make_navier_pair(128 if periodic else 129, 129, 1e5, 1.0, 0.01, 1.0, periodic)
+    ng.io_dir = str(tmp_path / "data")
+    b2.integrate(ng, 0.03, 0.01)
+    for _ in range(3):
+        no.update()
+    d, dref = ng.div(), no.div()
+    assert d.shape == dref.shape and d.dtype == dref.dtype
+    assert float(np.abs(d - dref).max() / np.abs(dref).max()) < 1e-9   # a derivative of the 1e-10 state
+    assert abs(np.sqrt(np.sum(np.abs(d) ** 2)) - ng.div_norm()) < 1e-12 * max(1.0, ng.div_norm())
+    ext = sn.default_ext()
+    flows = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "data" / "flow*")))
+    assert flows == [f"flow00000.0{k}{ext}" for k in (1, 2, 3)], flows
+    lines = open(tmp_path / "data" / "info.txt").read().strip().splitlines()
+    assert len(lines) == 3
+    t, nu, nuv, re = (float(v) for v in lines[-1].split())
+    assert abs(t - 0.03) < 1e-12
+    for got, ref in ((nu, no.eval_nu()), (nuv, no.eval_nuvol()), (re, no.eval_re())):
+        assert abs(got - ref) <= 1e-9 * abs(ref)
+    ng.reset_time()
+    assert ng.get_time() == 0.0
