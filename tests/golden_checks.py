@@ -72,3 +72,48 @@ def check_navier(b2, name, max_steps=None):
     errs["div_norm"] = abs(nav.div_norm() - dn) / dn   # O(1e-3 .. 1e-1) in every fixture; a derived quantity: callers bound it by 1e-8
     nav.close()
     return errs
+
+
+def check_roundtrip_and_linearity(b2, sp, seed=21):
+    """Size-independent properties of the transforms on an orthonormal / Fourier space (no oracle needed, any size):
+    forward(backward(c)) == c for a valid spectrum c, and forward(a u + v) == a forward(u) + forward(v)."""
+    k0, n0, k1, n1 = sp
+    f = b2.Field2(b2.Space2((k0, n0), (k1, n1)))
+    shape, cx = f.space.shape(b2.SPECTRAL)
+    rng = np.random.default_rng(seed)
+    c = rng.standard_normal(shape)
+    if cx:
+        c = c + 1j * rng.standard_normal(shape)
+        c[0] = c[0].real      # DC and Nyquist modes of a real signal are real
+        c[-1] = c[-1].real
+    f.vhat = c
+    f.backward()
+    v = f.v
+    f.forward()
+    errs = {"roundtrip": rel(f.vhat, c)}
+    u = rng.standard_normal(v.shape)
+    f.v = u
+    f.forward()
+    fu = f.vhat
+    f.v = 0.5 * u + v
+    f.forward()
+    errs["linearity"] = rel(f.vhat, 0.5 * fu + c)
+    f.close()
+    return errs
+
+
+def check_hholtz_linearity(b2, sp, seed=22):
+    """HholtzAdi::solve is linear: solve(a r1 + r2) == a solve(r1) + solve(r2) (any size, no oracle needed)."""
+    k0, n0, k1, n1 = sp
+    f = b2.Field2(b2.Space2((k0, n0), (k1, n1)))
+    hh = b2.HholtzAdi(f, [1e-3, 2e-3])
+    shape, cx = f.space.shape(b2.ORTHO)
+    rng = np.random.default_rng(seed)
+    r1, r2 = rng.standard_normal(shape), rng.standard_normal(shape)
+    if cx:
+        r1 = r1 + 1j * rng.standard_normal(shape)
+        r2 = r2 + 1j * rng.standard_normal(shape)
+    x1, x2 = hh.solve(r1).get(), hh.solve(r2).get()
+    x3 = hh.solve(0.25 * r1 + r2).get()
+    hh.close(); f.close()
+    return {"linearity": rel(x3, 0.25 * x1 + x2)}

@@ -154,3 +154,26 @@ def test_gpu_div_reset_time_and_reference_callback(periodic, tmp_path):
         assert abs(got - ref) <= 1e-9 * abs(ref)
     ng.reset_time()
     assert ng.get_time() == 0.0
+
+
+FULL = {"C4-size": (0, 4097, 0, 4097), "C5-size": (4, 8192, 0, 4097), "C2-size": (0, 1025, 0, 1025), "C3-size": (4, 2048, 0, 1025)}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(FULL))
+def test_gpu_full_size_roundtrip_and_linearity(name):
+    """BASELINE.json's full sizes through size-independent properties (no oracle at these sizes): forward(backward(c)) == c on the
+    orthonormal / Fourier spaces of the configurations, and the forward transform is linear."""
+    import rustpde_mpi_b200 as b2
+
+    errs = gc.check_roundtrip_and_linearity(b2, FULL[name])
+    assert max(errs.values()) < gc.TOL, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sp", [(1, 4097, 1, 4097), (4, 2048, 1, 1025)], ids=["C4-size", "C3-size"])
+def test_gpu_full_size_hholtz_linearity(sp):
+    import rustpde_mpi_b200 as b2
+
+    errs = gc.check_hholtz_linearity(b2, sp)
+    assert max(errs.values()) < gc.TOL, errs
