@@ -47,5 +47,6 @@ def _profile_ms(self, on):
 b2.Context.timer_start, b2.Context.timer_stop, b2.Context.profile = _timer_start, _timer_stop, _profile_ms
 bench.CONFIGS["T0"] = (65, 65, 1e5, 1e-2, False)     # emulator-sized stand-ins for the confined / periodic workloads
 bench.CONFIGS["T0p"] = (64, 65, 1e5, 1e-2, True)
+bench.CONFIGS["T1"] = (129, 129, 1e5, 1e-2, False)   # smallest confined size with a thread layout on 8 ranks
 sys.argv = ["bench.py", "--config", sys.argv[1], *sys.argv[2:]]
 bench.main()
